@@ -1,0 +1,146 @@
+"""Oracle part 3: domain membership, volumes, bounding boxes and deterministic grids.
+
+TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  float32 numpy restatement of the
+constant-parameter case of the reference's domains (paths relative to
+``/root/reference/src/torchphysics/problem/domains``).  Membership is evaluated with the
+same float32 operation order as the reference so that the answers agree bit-for-bit.
+
+A domain is described by a small tuple tree:
+    ("interval", lo, hi) | ("parallelogram", origin, c1, c2) | ("circle", center, r)
+    ("cut", A, B) | ("union", A, B) | ("product", A, B)   (product: A columns first)
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+def dim(dom):
+    kind = dom[0]
+    if kind == "interval":
+        return 1
+    if kind in ("parallelogram", "circle"):
+        return 2
+    if kind in ("cut", "union"):
+        return dim(dom[1])
+    if kind == "product":
+        return dim(dom[1]) + dim(dom[2])
+    raise ValueError(kind)
+
+
+def contains(dom, pts):
+    """pts (N, dim) float32 -> bool (N,)."""
+    pts = np.asarray(pts, dtype=f32)
+    kind = dom[0]
+    if kind == "interval":
+        # domain1D/interval.py:37-43 -- closed interval
+        lo, hi = f32(dom[1]), f32(dom[2])
+        return (pts[:, 0] >= lo) & (pts[:, 0] <= hi)
+    if kind == "parallelogram":
+        # domain2D/parallelogram.py:83-103 -- Cramer solve for barycentric coordinates
+        o = np.asarray(dom[1], f32)
+        d1 = np.asarray(dom[2], f32) - o
+        d2 = np.asarray(dom[3], f32) - o
+        p = pts - o
+        det = d1[0] * d2[1] - d1[1] * d2[0]
+        xd = d2[1] * p[:, 0] - d2[0] * p[:, 1]
+        yd = d1[0] * p[:, 1] - d1[1] * p[:, 0]
+        bx = xd / det
+        by = yd / det
+        return (bx >= 0) & (bx <= 1) & (by >= 0) & (by <= 1)
+    if kind == "circle":
+        # domain2D/circle.py:34-40 -- ||p - c||_2 <= r
+        c = np.asarray(dom[1], f32)
+        q = pts - c
+        nrm = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1], dtype=f32)
+        return nrm <= f32(dom[2])
+    if kind == "cut":
+        # domainoperations/cut.py:39-42
+        return contains(dom[1], pts) & ~contains(dom[2], pts)
+    if kind == "union":
+        # domainoperations/union.py:45-48
+        return contains(dom[1], pts) | contains(dom[2], pts)
+    if kind == "product":
+        # domainoperations/product.py:108-111
+        da = dim(dom[1])
+        return contains(dom[1], pts[:, :da]) & contains(dom[2], pts[:, da:])
+    raise ValueError(kind)
+
+
+def volume(dom):
+    kind = dom[0]
+    if kind == "interval":
+        return f32(dom[2]) - f32(dom[1])                        # interval.py:72-75
+    if kind == "parallelogram":
+        o = np.asarray(dom[1], f32)
+        d1 = np.asarray(dom[2], f32) - o
+        d2 = np.asarray(dom[3], f32) - o
+        return d1[0] * d2[1] - d1[1] * d2[0]                    # parallelogram.py:54-58
+    if kind == "circle":
+        return f32(np.pi) * f32(dom[2]) ** 2                    # circle.py:101-104
+    if kind == "cut":
+        return volume(dom[1])                                   # cut.py:44-55 (not contained)
+    if kind == "union":
+        return volume(dom[1]) + volume(dom[2])                  # union.py:26-42
+    if kind == "product":
+        return volume(dom[1]) * volume(dom[2])                  # product.py:145-147
+    raise ValueError(kind)
+
+
+def bounding_box(dom):
+    kind = dom[0]
+    if kind == "interval":
+        return [float(dom[1]), float(dom[2])]
+    if kind == "parallelogram":
+        o, c1, c2 = (np.asarray(v, f32) for v in dom[1:4])
+        c3 = c1 + c2 - o
+        cs = np.stack([o, c1, c2, c3])
+        return [float(cs[:, 0].min()), float(cs[:, 0].max()), float(cs[:, 1].min()), float(cs[:, 1].max())]
+    if kind == "circle":
+        c, r = np.asarray(dom[1], f32), f32(dom[2])
+        return [float(c[0] - r), float(c[0] + r), float(c[1] - r), float(c[1] + r)]
+    if kind == "cut":
+        return bounding_box(dom[1])
+    if kind == "union":
+        a, b = bounding_box(dom[1]), bounding_box(dom[2])
+        out = []
+        for i in range(len(a) // 2):
+            out += [min(a[2 * i], b[2 * i]), max(a[2 * i + 1], b[2 * i + 1])]
+        return out
+    if kind == "product":
+        return bounding_box(dom[1]) + bounding_box(dom[2])
+    raise ValueError(kind)
+
+
+def grid(dom, n):
+    """Deterministic part of ``sample_grid(n)`` for the three primitives."""
+    kind = dom[0]
+    if kind == "interval":
+        # interval.py:57-65 -- n interior points of linspace(0,1,n+2)
+        lo, hi = f32(dom[1]), f32(dom[2])
+        t = np.linspace(0, 1, n + 2, dtype=f32)[1:-1]
+        return ((hi - lo) * t + lo).reshape(-1, 1)
+    if kind == "parallelogram":
+        # parallelogram.py:119-152 -- n1 x n2 interior barycentric grid (may be < n points;
+        # the reference tops up with random points, which are not part of this oracle)
+        o = np.asarray(dom[1], f32)
+        d1 = np.asarray(dom[2], f32) - o
+        d2 = np.asarray(dom[3], f32) - o
+        l1 = np.sqrt(d1[0] * d1[0] + d1[1] * d1[1], dtype=f32)
+        l2 = np.sqrt(d2[0] * d2[0] + d2[1] * d2[1], dtype=f32)
+        n1 = int(np.sqrt(f32(n) * l1 / l2, dtype=f32))
+        n2 = int(np.sqrt(f32(n) * l2 / l1, dtype=f32))
+        bx = np.linspace(0, 1, n1 + 2, dtype=f32)[1:-1]
+        by = np.linspace(0, 1, n2 + 2, dtype=f32)[1:-1]
+        # reference ordering: y index outer, x index inner
+        B = np.stack([np.tile(bx, n2), np.repeat(by, n1)], axis=1)
+        return B[:, :1] * d1 + B[:, 1:] * d2 + o
+    if kind == "circle":
+        # circle.py:70-99 -- sunflower/Vogel spiral
+        c, r = np.asarray(dom[1], f32), f32(dom[2])
+        gr = (np.sqrt(5) + 1) / 2.0
+        k = np.arange(1, n + 1)
+        phi = f32(2 * np.pi / gr) * k.astype(f32)      # torch: python scalar * int64 tensor -> float32 product
+        rad = (np.sqrt((k - 0.5).astype(f32), dtype=f32) / f32(np.sqrt(n + 0.5))).astype(f32)
+        P = np.stack([rad * np.cos(phi, dtype=f32), rad * np.sin(phi, dtype=f32)], axis=1)
+        return r * P + c
+    raise ValueError(kind)

@@ -1,0 +1,255 @@
+"""Generates tests/golden/*.npz by RUNNING THE REAL REFERENCE (boschresearch/torchphysics
+v1.1.0) in the authoring container:
+
+    python tests/golden/make_golden.py
+
+It imports ``torchphysics`` from /root/reference/src (never copied into this repo) with
+the two import stubs in oracle/stubs (matplotlib and pytorch_lightning are not
+installed).  The .npz files are the parity pins of the oracle (tests/test_oracle_golden.py)
+and of the CUDA path (tests/test_gpu_*.py).  /root/reference does not exist on the GPU
+box, so only the committed .npz files travel.
+"""
+import math
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "stubs"))
+sys.path.insert(0, "/root/reference/src")
+warnings.filterwarnings("ignore")
+
+import torchphysics as tp  # noqa: E402  (the reference)
+
+
+def params_of(model):
+    return [p.detach().numpy().copy() for p in model.parameters()]
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, (list, tuple)):
+            out[k + "__n"] = np.array(len(v))
+            for i, a in enumerate(v):
+                out[f"{k}__{i}"] = np.zeros(0, np.float32) if a is None else np.asarray(a)
+                out[f"{k}__{i}__none"] = np.array(a is None)
+        else:
+            out[k] = v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def grads_of(model):
+    return [None if p.grad is None else p.grad.detach().numpy().copy() for p in model.parameters()]
+
+
+# ---------------------------------------------------------------------------- config 1
+def poisson(hidden, n, name, act=None):
+    torch.manual_seed(0)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    kw = {} if act is None else {"activations": act}
+    model = tp.models.FCN(X, U, hidden=hidden, **kw)
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    torch.manual_seed(1)
+    pts = tp.samplers.RandomUniformSampler(sq, n_points=n).make_static()
+    x = pts.sample_points().as_tensor.clone()
+
+    def f(x):
+        return 2 * math.pi ** 2 * torch.sin(math.pi * x[:, :1]) * torch.sin(math.pi * x[:, 1:])
+
+    captured = {}
+
+    def residual(u, x, f):
+        captured["u"] = u
+        captured["grad"] = tp.utils.grad(u, x)
+        captured["lap"] = tp.utils.laplacian(u, x)
+        return captured["lap"] + f
+
+    cond = tp.conditions.PINNCondition(model, pts, residual, data_functions={"f": f})
+    model.zero_grad()
+    loss = cond(device="cpu")
+    loss.backward()
+    save(name, x=x, params=params_of(model), u=captured["u"], grad=captured["grad"],
+         lap=captured["lap"], loss=loss, dtheta=grads_of(model), hidden=np.array(hidden))
+
+
+# ---------------------------------------------------------------------------- config 2
+def heat(hidden, n, name):
+    torch.manual_seed(2)
+    X, T, U = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
+    model = tp.models.FCN(X * T, U, hidden=hidden)
+    dom = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1]) * tp.domains.Interval(T, 0, 1)
+    torch.manual_seed(3)
+    pts = tp.samplers.RandomUniformSampler(dom, n_points=n).make_static()
+    P = pts.sample_points()
+    xt = torch.cat([P.coordinates["x"], P.coordinates["t"]], dim=1).clone()
+    captured = {}
+
+    def residual(u, x, t):
+        captured["ut"] = tp.utils.grad(u, t)
+        captured["lap"] = tp.utils.laplacian(u, x)
+        captured["u"] = u
+        return captured["ut"] - captured["lap"]
+
+    cond = tp.conditions.PINNCondition(model, pts, residual)
+    model.zero_grad()
+    loss = cond(device="cpu")
+    loss.backward()
+    save(name, xt=xt, params=params_of(model), u=captured["u"], ut=captured["ut"],
+         lap=captured["lap"], loss=loss, dtheta=grads_of(model), hidden=np.array(hidden))
+
+
+# ---------------------------------------------------------------------------- config 3
+def navier_stokes(hidden, n, name):
+    torch.manual_seed(4)
+    X, U, Pp = tp.spaces.R2("x"), tp.spaces.R2("u"), tp.spaces.R1("p")
+    model = tp.models.FCN(X, U * Pp, hidden=hidden)
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    torch.manual_seed(5)
+    pts = tp.samplers.RandomUniformSampler(sq, n_points=n).make_static()
+    x = pts.sample_points().as_tensor.clone()
+    nu = 0.01
+    captured = {}
+
+    def residual(u, p, x):
+        conv = tp.utils.convective(u, u, x)
+        lap = torch.cat([tp.utils.laplacian(u[:, :1], x), tp.utils.laplacian(u[:, 1:], x)], dim=1)
+        gp = tp.utils.grad(p, x)
+        cont = tp.utils.div(u, x)
+        captured.update(conv=conv, lap=lap, gp=gp, div=cont, u=u, p=p,
+                        jac=tp.utils.jac(torch.cat([u, p], dim=1), x))
+        return torch.cat([conv - nu * lap + gp, cont], dim=1)
+
+    cond = tp.conditions.PINNCondition(model, pts, residual)
+    model.zero_grad()
+    loss = cond(device="cpu")
+    loss.backward()
+    save(name, x=x, params=params_of(model), y=torch.cat([captured["u"], captured["p"]], dim=1),
+         jac=captured["jac"], lap=captured["lap"], conv=captured["conv"], div=captured["div"],
+         loss=loss, dtheta=grads_of(model), hidden=np.array(hidden))
+
+
+# ---------------------------------------------------------------------------- config 5
+def deep_ritz(hidden, n, name):
+    torch.manual_seed(6)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=hidden)
+    dom = tp.domains.Circle(X, [0, 0], 1.0) - tp.domains.Parallelogram(
+        X, [-0.25, -0.25], [0.25, -0.25], [-0.25, 0.25])
+    torch.manual_seed(7)
+    pts = tp.samplers.RandomUniformSampler(dom, n_points=n).make_static()
+    x = pts.sample_points().as_tensor.clone()
+    captured = {}
+
+    def integrand(u, x):
+        g = tp.utils.grad(u, x)
+        captured.update(u=u, grad=g)
+        return 0.5 * (g ** 2).sum(dim=1, keepdim=True) - u
+
+    cond = tp.conditions.DeepRitzCondition(model, pts, integrand)
+    model.zero_grad()
+    loss = cond(device="cpu")
+    loss.backward()
+    save(name, x=x, params=params_of(model), u=captured["u"], grad=captured["grad"],
+         loss=loss, dtheta=grads_of(model), hidden=np.array(hidden))
+
+
+# ---------------------------------------------------------------------------- config 4
+def deeponet(n_fn, n_pts, p, name):
+    torch.manual_seed(8)
+    T, U, Fs, K = tp.spaces.R1("t"), tp.spaces.R1("u"), tp.spaces.R1("f"), tp.spaces.R1("k")
+    trunk = tp.models.FCTrunkNet(T, hidden=(32, 32))
+    branch = tp.models.FCBranchNet(tp.spaces.FunctionSpace(T, Fs), hidden=(24, 24),
+                                   grid=tp.samplers.GridSampler(tp.domains.Interval(T, 0, 1), n_points=10).sample_points())
+    net = tp.models.DeepONet(trunk, branch, U, output_neurons=p)
+    int_t = tp.domains.Interval(T, 0, 1)
+
+    def fn(k, t):
+        return k * torch.sin(math.pi * t)
+
+    param_sampler = tp.samplers.RandomUniformSampler(tp.domains.Interval(K, -1, 1), n_points=n_fn)
+    fset = tp.domains.CustomFunctionSet(tp.spaces.FunctionSpace(T, Fs), param_sampler, fn)
+    fsampler = tp.samplers.FunctionSamplerRandomUniform(n_fn, fset, function_creation_interval=1)
+    torch.manual_seed(9)
+    tsampler = tp.samplers.RandomUniformSampler(int_t, n_points=n_pts).make_static()
+    tt = tsampler.sample_points().as_tensor.clone()
+    captured = {}
+
+    def residual(u, t, f):
+        captured["u"] = u
+        captured["lap"] = tp.utils.laplacian(u, t)
+        captured["f"] = f
+        return captured["lap"] + f
+
+    cond = tp.conditions.PIDeepONetCondition(net, fsampler, tsampler, residual)
+    net.zero_grad()
+    torch.manual_seed(10)
+    loss = cond(device="cpu")
+    loss.backward()
+    # branch input actually used in this call
+    binp = captured["f"]
+    trunk_params = [q.detach().numpy().copy() for q in trunk.parameters()]
+    branch_params = [q.detach().numpy().copy() for q in branch.parameters()]
+    save(name, t=tt, fvals=captured["f"], u=captured["u"], lap=captured["lap"], loss=loss,
+         trunk_params=trunk_params, branch_params=branch_params,
+         branch_in=net.branch.current_out.detach() if False else np.zeros(0),
+         branch_out=net.branch.current_out.detach(),
+         trunk_dtheta=[None if q.grad is None else q.grad.numpy().copy() for q in trunk.parameters()],
+         branch_dtheta=[None if q.grad is None else q.grad.numpy().copy() for q in branch.parameters()],
+         p=np.array(p))
+
+
+# ---------------------------------------------------------------------------- domains
+def domains():
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    g = torch.Generator().manual_seed(11)
+    cand = (torch.rand(4000, 2, generator=g) * 3.0 - 1.5)
+    cand1 = (torch.rand(2000, 1, generator=g) * 3.0 - 1.5)
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    ival = tp.domains.Interval(T, -0.3, 0.8)
+    sq = tp.domains.Parallelogram(X, [-0.25, -0.25], [0.25, -0.25], [-0.25, 0.25])
+    cut = circ - sq
+    uni = para + circ
+    out = {"cand": cand, "cand1": cand1}
+    for nm, d in [("para", para), ("circ", circ), ("sq", sq), ("cut", cut), ("uni", uni)]:
+        out["in_" + nm] = d._contains(tp.spaces.Points(cand.clone(), X)).reshape(-1)
+        out["bbox_" + nm] = d.bounding_box()
+        out["vol_" + nm] = d.volume().reshape(-1)
+    out["in_ival"] = ival._contains(tp.spaces.Points(cand1.clone(), T)).reshape(-1)
+    out["bbox_ival"] = ival.bounding_box()
+    out["vol_ival"] = ival.volume().reshape(-1)
+    prod = para * ival
+    cand3 = torch.cat([cand[:2000], cand1], dim=1)
+    out["cand3"] = cand3
+    out["in_prod"] = prod._contains(tp.spaces.Points(cand3.clone(), X * T)).reshape(-1)
+    out["vol_prod"] = prod.volume().reshape(-1)
+    for n in (1, 7, 50):
+        out[f"grid_ival_{n}"] = ival.sample_grid(n).as_tensor
+        out[f"grid_circ_{n}"] = circ.sample_grid(n).as_tensor
+    for n in (16, 50, 100):
+        torch.manual_seed(0)
+        gpts = para.sample_grid(n).as_tensor
+        out[f"grid_para_{n}"] = gpts
+    # sample counts / membership of the reference's random samplers (n_points mode)
+    torch.manual_seed(12)
+    for nm, d in [("para", para), ("circ", circ), ("cut", cut), ("uni", uni)]:
+        s = tp.samplers.RandomUniformSampler(d, n_points=500).sample_points()
+        out["n_random_" + nm] = np.array(len(s))
+        out["allin_random_" + nm] = np.array(bool(d._contains(s).all()))
+    save("domains", **out)
+
+
+if __name__ == "__main__":
+    poisson((64, 64, 64, 64), 257, "poisson_4x64")
+    poisson((20, 20, 20), 100, "poisson_3x20_sin", act=tp.models.Sinus())
+    heat((48, 48, 48), 193, "heat_3x48")
+    navier_stokes((32, 32, 32), 130, "ns_3x32")
+    deep_ritz((40, 40, 40, 40), 150, "ritz_4x40")
+    domains()
