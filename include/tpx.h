@@ -1,0 +1,109 @@
+/*
+ * tpx.h -- C ABI of libtpx.so, the B200 (sm_100a) engine behind the TorchPhysics API.
+ *
+ * The reference (boschresearch/torchphysics v1.1.0) is pure Python and has no FFI of
+ * its own: its hot path is the chain of Python calls listed next to each entry point
+ * below (paths relative to src/torchphysics in the reference).  This library is what a
+ * maintainer binds with ctypes *inside* those Python functions.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative TPX_E_* code on failure; the
+ *     message of the last failure on the calling thread is tpx_last_error();
+ *   - all pointers are DEVICE pointers unless the name ends in _host; buffers are owned
+ *     by the caller (PyTorch's allocator in the Python binding), nothing is retained;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work;
+ *   - float32 row-major everywhere, gradient accumulators are float64;
+ *   - re-entrant: no global mutable state except the per-thread error string.
+ */
+#ifndef TPX_H_
+#define TPX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPX_VERSION 100
+#define TPX_MAX_HIDDEN 16   /* hidden layers (Linear+activation pairs)            */
+#define TPX_MAX_DIN 8       /* columns of the model input                          */
+#define TPX_MAX_ND 3        /* derivative directions propagated through the net    */
+#define TPX_MAX_WIDTH 256   /* widest hidden layer                                 */
+#define TPX_MAX_DOUT 256
+
+#define TPX_E_ARG (-1)       /* invalid argument                      */
+#define TPX_E_UNSUPPORTED (-2) /* valid network, but no kernel for it  */
+#define TPX_E_CUDA (-3)      /* CUDA runtime error                    */
+#define TPX_E_WORKSPACE (-4) /* caller workspace too small            */
+
+#define TPX_ACT_TANH 0 /* nn.Tanh          (models/fcn.py:66)            */
+#define TPX_ACT_SIN 1  /* tp.models.Sinus  (models/activation_fn.py:76)  */
+
+/* Fully connected network  x -> W_L s(... s(W_0 x + b_0) ...) + b_L
+ * (models/fcn.py:9-29, _construct_FC_layers; models/deeponet/trunknets.py:70-87). */
+typedef struct tpx_fcn_desc {
+  int32_t d_in;                     /* input columns                         */
+  int32_t d_out;                    /* output columns                        */
+  int32_t n_hidden;                 /* number of hidden layers, >= 1         */
+  int32_t widths[TPX_MAX_HIDDEN];   /* hidden widths                         */
+  int32_t activation;               /* TPX_ACT_*  (same for every layer)     */
+} tpx_fcn_desc;
+
+/* Which derivative streams ("jet") are propagated next to the value.
+ *   nd      directions, 0..3;  dcol[k] = input column of direction k
+ *   lap     0/1: also propagate  L u = sum_k lap_w[k] d^2 u / d x_dcol[k]^2
+ * This is what tp.utils.grad / laplacian / div / jac / partial / normal_derivative /
+ * convective (utils/differentialoperators/differentialoperators.py:11-342) read from. */
+typedef struct tpx_jet_desc {
+  int32_t nd;
+  int32_t dcol[TPX_MAX_ND];
+  int32_t lap;
+  float lap_w[TPX_MAX_ND];
+} tpx_jet_desc;
+
+int tpx_version(void);
+const char* tpx_last_error(void);
+
+/* Number of floats of the packed (padded, both orientations) parameter image, and of
+ * the float64 gradient accumulator that uses the same indexing. */
+int tpx_fcn_packed_floats(const tpx_fcn_desc* net, size_t* n_floats);
+
+/* Re-layout the nn.Linear parameters (weight (out,in) row-major, bias) into the packed
+ * image the kernels read.  params_host = {W0,b0,W1,b1,...,WL,bL}: a HOST array of
+ * 2*(n_hidden+1) device pointers.  One launch.  Replaces nothing in the reference
+ * (its nn.Linear modules are used as they are, models/fcn.py:18-28). */
+int tpx_fcn_pack(const tpx_fcn_desc* net, const void* const* params_host, float* packed, void* stream);
+
+/* Forward jet.  Replaces FCN.forward (models/fcn.py:85-87) and, for the requested
+ * streams, the autograd sweeps of grad/laplacian/div/jac
+ * (utils/differentialoperators/differentialoperators.py:34,40,64,160,254).
+ *   x   (n, d_in)            u   (n, d_out)
+ *   du  (n, d_out, nd)       lap (n, d_out)      (du/lap may be NULL if not requested) */
+int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                        const float* x, int64_t n, float* u, float* du, float* lap, void* stream);
+
+/* Bytes of scratch tpx_fcn_jet_backward needs (per-CTA activation checkpoints that are
+ * written and re-read within one kernel, sized to stay in the 126 MB L2). */
+int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, size_t* bytes);
+
+/* Reverse sweep.  Replaces loss.backward() through the graphs built by the calls above
+ * (solver.py:100-109 + every create_graph=True sweep).  Recomputes the forward jet per
+ * tile of points on chip, then accumulates dLoss/dtheta into the float64 image
+ * `grad_acc` (packed indexing; caller zeroes it).
+ *   gu (n,d_out), gdu (n,d_out,nd), glap (n,d_out): dLoss/d(outputs); any may be NULL. */
+int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                         const float* x, int64_t n, const float* gu, const float* gdu,
+                         const float* glap, double* grad_acc, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* float64 packed accumulator -> per-parameter float32 gradients (layout of nn.Linear).
+ * grads_host: HOST array of 2*(n_hidden+1) device pointers (entries may be NULL).
+ * accumulate != 0 adds to the existing gradient (PyTorch .grad semantics). */
+int tpx_fcn_unpack_grads(const tpx_fcn_desc* net, const double* grad_acc, void* const* grads_host,
+                         int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPX_H_ */

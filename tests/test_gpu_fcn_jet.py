@@ -1,0 +1,178 @@
+"""Parity of the CUDA jet kernels (through the C ABI) against the oracle and the golden
+outputs of the real reference.  Tolerance: 1e-5 max-norm relative (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import jet_numpy, ref_autograd
+from tests.golden_io import load, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _engine(params, act):
+    from torchphysics_b200.engine import FcnEngine
+    lins = []
+    for i in range(len(params) // 2):
+        W = torch.as_tensor(params[2 * i]).float()
+        lin = nn.Linear(W.shape[1], W.shape[0])
+        with torch.no_grad():
+            lin.weight.copy_(W)
+            lin.bias.copy_(torch.as_tensor(params[2 * i + 1]).float())
+        lins.append(lin.cuda())
+    return FcnEngine(lins, act), lins
+
+
+def _run(params, act, x, dcols, lap_w, gu=None, gdu=None, glap=None):
+    from torchphysics_b200.engine import JetSpec
+    eng, lins = _engine(params, act)
+    spec = JetSpec(dcols, lap_w)
+    xs = torch.as_tensor(x).float().cuda()
+    u, du, lap = eng.jet(xs, spec)
+    loss = 0
+    if gu is not None:
+        loss = loss + (u * torch.as_tensor(gu).float().cuda()).sum()
+    if gdu is not None:
+        loss = loss + (du * torch.as_tensor(gdu).float().cuda()).sum()
+    if glap is not None:
+        loss = loss + (lap * torch.as_tensor(glap).float().cuda()).sum()
+    grads = None
+    if gu is not None or gdu is not None or glap is not None:
+        ps = eng.params()
+        grads = torch.autograd.grad(loss, ps, allow_unused=True)
+        grads = [None if g is None else g.cpu().numpy() for g in grads]
+    torch.cuda.synchronize()
+    return u.detach().cpu().numpy(), du.detach().cpu().numpy(), lap.detach().cpu().numpy(), grads
+
+
+@pytest.mark.parametrize("name,act", [("poisson_4x64", "tanh"), ("poisson_3x20_sin", "sin")])
+def test_poisson_golden(name, act):
+    G = load(name)
+    x = G["x"]
+    N = x.shape[0]
+    f = ref_autograd.poisson_source(torch.from_numpy(x)).numpy()
+    u, du, lap, _ = _run(G["params"], act, x, (0, 1), (1.0, 1.0))
+    assert relerr(u, G["u"]) < TOL
+    assert relerr(du[:, 0, :], G["grad"]) < TOL
+    assert relerr(lap, G["lap"]) < TOL
+    r = lap + f
+    loss = float(np.mean(r.astype(np.float64) ** 2))
+    assert abs(loss - float(G["loss"])) < TOL * abs(float(G["loss"]))
+    _, _, _, grads = _run(G["params"], act, x, (0, 1), (1.0, 1.0), glap=2 * r / N)
+    assert grads[-1] is None and G["dtheta"][-1] is None     # reference: output bias has no grad
+    for g, w in zip(grads[:-1], G["dtheta"][:-1]):
+        assert relerr(g, w) < TOL
+
+
+def test_heat_golden():
+    G = load("heat_3x48")
+    xt = G["xt"]
+    N = xt.shape[0]
+    u, du, lap, _ = _run(G["params"], "tanh", xt, (0, 1, 2), (1.0, 1.0, 0.0))
+    assert relerr(u, G["u"]) < TOL
+    assert relerr(du[:, 0, 2:3], G["ut"]) < TOL
+    assert relerr(lap, G["lap"]) < TOL
+    r = du[:, 0, 2:3] - lap
+    gdu = np.zeros((N, 1, 3), np.float32)
+    gdu[:, 0, 2] = (2 * r / N)[:, 0]
+    _, _, _, grads = _run(G["params"], "tanh", xt, (0, 1, 2), (1.0, 1.0, 0.0), gdu=gdu, glap=-2 * r / N)
+    for g, w in zip(grads[:-1], G["dtheta"][:-1]):
+        assert relerr(g, w) < TOL
+
+
+def test_navier_stokes_golden():
+    G = load("ns_3x32")
+    u, du, lap, _ = _run(G["params"], "tanh", G["x"], (0, 1), (1.0, 1.0))
+    assert relerr(u, G["y"]) < TOL
+    assert relerr(du, G["jac"]) < TOL
+    assert relerr(lap[:, :2], G["lap"]) < TOL
+
+
+def test_deep_ritz_golden():
+    G = load("ritz_4x40")
+    x = G["x"]
+    N = x.shape[0]
+    u, du, lap, _ = _run(G["params"], "tanh", x, (0, 1), None)
+    assert lap.size == 0
+    assert relerr(du[:, 0, :], G["grad"]) < TOL
+    _, _, _, grads = _run(G["params"], "tanh", x, (0, 1), None, gu=-np.ones((N, 1), np.float32) / N, gdu=du / N)
+    for g, w in zip(grads, G["dtheta"]):
+        assert relerr(g, w) < TOL
+
+
+CASES = [
+    # d_in, d_out, hidden, act, dcols, lap_w, N
+    (2, 1, (64,) * 4, "tanh", (0, 1), (1.0, 1.0), 1000),
+    (3, 1, (128,) * 6, "tanh", (0, 1, 2), (1.0, 1.0, 0.0), 333),
+    (2, 3, (128,) * 6, "tanh", (0, 1), (1.0, 1.0), 200),
+    (2, 1, (256,) * 8, "tanh", (0, 1), None, 150),
+    (2, 1, (256,) * 3, "sin", (0, 1), (1.0, 0.5), 100),
+    (1, 64, (64,) * 4, "tanh", (0,), (1.0,), 300),
+    (4, 2, (20, 50, 30), "tanh", (3, 1), (0.0, 2.0), 77),
+    (3, 1, (17,), "sin", (), None, 65),
+    (2, 1, (32, 32), "tanh", (1,), None, 1),
+]
+
+
+@pytest.mark.parametrize("d_in,d_out,hidden,act,dcols,lap_w,N", CASES)
+def test_against_float64_oracle(d_in, d_out, hidden, act, dcols, lap_w, N):
+    """Full-size networks of BASELINE.json's configs (and ragged shapes) vs the float64
+    closed-form oracle on seeded inputs."""
+    torch.manual_seed(1234)
+    seq = ref_autograd.build_fcn(d_in, d_out, hidden, act)
+    params = [p.detach().numpy() for p in ref_autograd.linear_params(seq)]
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, size=(N, d_in)).astype(np.float32)
+    nd = len(dcols)
+    gu = rng.standard_normal((N, d_out)).astype(np.float32)
+    gdu = rng.standard_normal((N, d_out, nd)).astype(np.float32) if nd else None
+    glap = rng.standard_normal((N, d_out)).astype(np.float32) if lap_w is not None else None
+    u, du, lap, grads = _run(params, act, x, dcols, lap_w, gu=gu, gdu=gdu, glap=glap)
+    # oracle propagates all d_in directions; pick the requested ones
+    c = np.zeros(d_in)
+    if lap_w is not None:
+        for col, w in zip(dcols, lap_w):
+            c[col] = w
+    ou, odu, olap = jet_numpy.jet_forward(params, x, c if lap_w is not None else None, act)
+    assert relerr(u, ou) < TOL
+    if nd:
+        assert relerr(du, odu[:, :, list(dcols)]) < TOL
+    if lap_w is not None:
+        assert relerr(lap, olap) < TOL
+    full_gdu = np.zeros((N, d_out, d_in))
+    if nd:
+        full_gdu[:, :, list(dcols)] = gdu
+    ograds = jet_numpy.jet_backward(params, x, gu, full_gdu, glap, c if lap_w is not None else None, act)
+    for g, w in zip(grads, ograds):
+        assert relerr(g, w) < TOL
+
+
+def test_empty_batch():
+    torch.manual_seed(0)
+    seq = ref_autograd.build_fcn(2, 1, (32, 32))
+    params = [p.detach().numpy() for p in ref_autograd.linear_params(seq)]
+    u, du, lap, _ = _run(params, "tanh", np.zeros((0, 2), np.float32), (0, 1), (1.0, 1.0))
+    assert u.shape == (0, 1) and du.shape == (0, 1, 2) and lap.shape == (0, 1)
+
+
+def test_linearity_of_reverse_at_scale():
+    """Size-independent property at a BASELINE-sized batch: dtheta is linear in the adjoints and
+    additive over a split of the points."""
+    from torchphysics_b200.engine import FcnEngine, JetSpec
+    torch.manual_seed(0)
+    seq = ref_autograd.build_fcn(2, 1, (64,) * 4).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    spec = JetSpec((0, 1), (1.0, 1.0))
+    N = 1 << 20
+    x = torch.rand(N, 2, device="cuda")
+    g = torch.randn(N, 1, device="cuda")
+    packed = eng.packed(eng.params())
+    full = eng.backward_raw(packed, x, spec, None, None, g)
+    a = eng.backward_raw(packed, x[: N // 3].contiguous(), spec, None, None, g[: N // 3].contiguous())
+    b = eng.backward_raw(packed, x[N // 3:].contiguous(), spec, None, None, g[N // 3:].contiguous())
+    twice = eng.backward_raw(packed, x, spec, None, None, 2 * g)
+    den = full.abs().max()
+    assert ((a + b - full).abs().max() / den) < 1e-6
+    assert ((twice - 2 * full).abs().max() / den) < 1e-6

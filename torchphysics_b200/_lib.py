@@ -1,0 +1,104 @@
+"""ctypes binding of libtpx.so (C ABI declared in include/tpx.h).
+
+The library is the product; there is no Python or CPU substitute for it.  ``lib()``
+raises ``TpxLibraryError`` when the shared object is missing or does not export every
+symbol of the header, and every wrapper raises ``TpxError`` on a non-zero return code.
+"""
+import ctypes
+import os
+
+TPX_MAX_HIDDEN = 16
+TPX_MAX_DIN = 8
+TPX_MAX_ND = 3
+TPX_MAX_WIDTH = 256
+TPX_MAX_DOUT = 256
+TPX_ACT_TANH = 0
+TPX_ACT_SIN = 1
+
+TPX_E_ARG = -1
+TPX_E_UNSUPPORTED = -2
+TPX_E_CUDA = -3
+TPX_E_WORKSPACE = -4
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtpx.so")
+
+EXPORTS = (
+    "tpx_version",
+    "tpx_last_error",
+    "tpx_fcn_packed_floats",
+    "tpx_fcn_pack",
+    "tpx_fcn_jet_forward",
+    "tpx_fcn_backward_workspace_bytes",
+    "tpx_fcn_jet_backward",
+    "tpx_fcn_unpack_grads",
+)
+
+
+class TpxLibraryError(RuntimeError):
+    pass
+
+
+class TpxError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libtpx error {code}: {message}")
+        self.code = code
+
+
+class FcnDesc(ctypes.Structure):
+    _fields_ = [
+        ("d_in", ctypes.c_int32),
+        ("d_out", ctypes.c_int32),
+        ("n_hidden", ctypes.c_int32),
+        ("widths", ctypes.c_int32 * TPX_MAX_HIDDEN),
+        ("activation", ctypes.c_int32),
+    ]
+
+
+class JetDesc(ctypes.Structure):
+    _fields_ = [
+        ("nd", ctypes.c_int32),
+        ("dcol", ctypes.c_int32 * TPX_MAX_ND),
+        ("lap", ctypes.c_int32),
+        ("lap_w", ctypes.c_float * TPX_MAX_ND),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libtpx.so once; fail loudly if it is missing or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TpxLibraryError(
+            f"{LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C torchphysics_b200/csrc`). There is no fallback path."
+        )
+    handle = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in EXPORTS if not hasattr(handle, s)]
+    if missing:
+        raise TpxLibraryError(f"{LIB_PATH} does not export {missing}; rebuild it")
+    handle.tpx_version.restype = ctypes.c_int
+    handle.tpx_last_error.restype = ctypes.c_char_p
+    for name in EXPORTS[2:]:
+        getattr(handle, name).restype = ctypes.c_int
+    _lib = handle
+    return handle
+
+
+def check(rc):
+    if rc != 0:
+        raise TpxError(rc, lib().tpx_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or NULL for None)."""
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,220 @@
+"""Host side of the native FCN jet engine: builds the C descriptors, keeps the packed
+parameter image fresh, and exposes the forward/reverse kernels as ONE autograd node.
+
+Replaces, for a stack of ``nn.Linear`` + tanh/sin layers, what the reference does with
+``nn.Sequential.forward`` (reference ``models/fcn.py:85-87``) followed by 1 + d
+``torch.autograd.grad(create_graph=True)`` sweeps (reference ``utils/differentialoperators/
+differentialoperators.py:34,40,64``) and the final ``loss.backward()`` through all of them.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class JetSpec:
+    """Which derivative streams to propagate: ``dcols`` = input columns of the (<= 3)
+    directions, ``lap_w`` = weights of the second-derivative sum (None: no Laplacian)."""
+
+    __slots__ = ("dcols", "lap_w")
+
+    def __init__(self, dcols=(), lap_w=None):
+        self.dcols = tuple(int(c) for c in dcols)
+        self.lap_w = None if lap_w is None else tuple(float(w) for w in lap_w)
+        if len(self.dcols) > _lib.TPX_MAX_ND:
+            raise ValueError(f"at most {_lib.TPX_MAX_ND} derivative directions")
+        if self.lap_w is not None and len(self.lap_w) != len(self.dcols):
+            raise ValueError("lap_w must have one weight per direction")
+
+    @property
+    def nd(self):
+        return len(self.dcols)
+
+    @property
+    def lap(self):
+        return self.lap_w is not None
+
+    def covers(self, other):
+        """True if a jet computed with self also answers every request of other."""
+        if not set(other.dcols) <= set(self.dcols):
+            return False
+        if other.lap:
+            if not self.lap:
+                return False
+            mine = {c: w for c, w in zip(self.dcols, self.lap_w)}
+            theirs = {c: w for c, w in zip(other.dcols, other.lap_w)}
+            return all(mine.get(c, 0.0) == theirs.get(c, 0.0) for c in set(mine) | set(theirs))
+        return True
+
+    def key(self):
+        return (self.dcols, self.lap_w)
+
+    def c_struct(self):
+        j = _lib.JetDesc()
+        j.nd = self.nd
+        for k, c in enumerate(self.dcols):
+            j.dcol[k] = c
+        j.lap = 1 if self.lap else 0
+        if self.lap:
+            for k, w in enumerate(self.lap_w):
+                j.lap_w[k] = w
+        return j
+
+    def __repr__(self):
+        return f"JetSpec(dcols={self.dcols}, lap_w={self.lap_w})"
+
+
+def _void_p_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class FcnEngine:
+    """Native evaluator of one fully connected net (list of nn.Linear + one activation)."""
+
+    def __init__(self, linears, activation):
+        self.linears = list(linears)
+        if activation not in ("tanh", "sin"):
+            raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, f"activation {activation!r}")
+        self.activation = activation
+        d = _lib.FcnDesc()
+        d.d_in = self.linears[0].in_features
+        d.d_out = self.linears[-1].out_features
+        d.n_hidden = len(self.linears) - 1
+        if d.n_hidden < 1 or d.n_hidden > _lib.TPX_MAX_HIDDEN:
+            raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, f"{d.n_hidden} hidden layers")
+        for l, lin in enumerate(self.linears[:-1]):
+            d.widths[l] = lin.out_features
+        d.activation = _lib.TPX_ACT_TANH if activation == "tanh" else _lib.TPX_ACT_SIN
+        self.desc = d
+        self.d_in, self.d_out = d.d_in, d.d_out
+        n = ctypes.c_size_t(0)
+        _lib.check(_lib.lib().tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)))
+        self.packed_floats = n.value
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+
+    # ---- parameters ------------------------------------------------------------------
+    def params(self):
+        out = []
+        for lin in self.linears:
+            if lin.bias is None:
+                raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "Linear without bias")
+            out += [lin.weight, lin.bias]
+        return out
+
+    def packed(self, params):
+        """Packed image of the current parameter values (re-packed when they changed)."""
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key or self._packed.device != params[0].device:
+            dev = params[0].device
+            buf = torch.empty(self.packed_floats, dtype=torch.float32, device=dev)
+            srcs = [p.detach() for p in params]
+            for s in srcs:
+                if s.dtype != torch.float32 or not s.is_contiguous():
+                    raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "parameters must be contiguous float32")
+            arr = _void_p_array(srcs)
+            _lib.check(_lib.lib().tpx_fcn_pack(ctypes.byref(self.desc), arr, _lib.ptr(buf), _lib.stream_ptr()))
+            self._packed, self._packed_key = buf, key
+        return self._packed
+
+    def workspace(self, spec, device):
+        k = (spec.nd, spec.lap, str(device))
+        ws = self._ws.get(k)
+        if ws is None:
+            nbytes = ctypes.c_size_t(0)
+            j = spec.c_struct()
+            _lib.check(_lib.lib().tpx_fcn_backward_workspace_bytes(ctypes.byref(self.desc), ctypes.byref(j), ctypes.byref(nbytes)))
+            ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=device)
+            self._ws[k] = ws
+        return ws
+
+    # ---- raw kernels -----------------------------------------------------------------
+    def forward_raw(self, packed, x, spec):
+        n = x.shape[0]
+        u = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device)
+        du = torch.empty((n, self.d_out, spec.nd), dtype=torch.float32, device=x.device) if spec.nd else None
+        lap = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device) if spec.lap else None
+        j = spec.c_struct()
+        _lib.check(_lib.lib().tpx_fcn_jet_forward(
+            ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+            _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.stream_ptr()))
+        return u, du, lap
+
+    def backward_raw(self, packed, x, spec, gu, gdu, glap):
+        """returns the float64 packed gradient accumulator."""
+        n = x.shape[0]
+        gacc = torch.zeros(self.packed_floats, dtype=torch.float64, device=x.device)
+        ws = self.workspace(spec, x.device)
+        j = spec.c_struct()
+        _lib.check(_lib.lib().tpx_fcn_jet_backward(
+            ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+            _lib.ptr(gu), _lib.ptr(gdu), _lib.ptr(glap), _lib.ptr(gacc), _lib.ptr(ws),
+            ctypes.c_size_t(ws.numel()), _lib.stream_ptr()))
+        return gacc
+
+    def unpack(self, gacc, params, skip_last_bias=False):
+        grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
+        if skip_last_bias:
+            grads[-1] = None
+        arr = _void_p_array(grads)
+        _lib.check(_lib.lib().tpx_fcn_unpack_grads(ctypes.byref(self.desc), _lib.ptr(gacc), arr, 0, _lib.stream_ptr()))
+        return grads
+
+    # ---- autograd entry point --------------------------------------------------------
+    def jet(self, x, spec):
+        """(u, du, lap) as differentiable functions of the network parameters."""
+        if not x.is_cuda:
+            raise _lib.TpxError(_lib.TPX_E_ARG, "the native engine only runs on CUDA tensors")
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        params = self.params()
+        return _FcnJetFn.apply(self, x, spec, *params)
+
+
+class _FcnJetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine, x, spec, *params):
+        packed = engine.packed(params)
+        u, du, lap = engine.forward_raw(packed, x, spec)
+        ctx.engine, ctx.spec, ctx.x, ctx.packed = engine, spec, x, packed
+        ctx.params = params
+        ctx.set_materialize_grads(False)
+        outs = [u]
+        outs.append(du if du is not None else x.new_zeros((x.shape[0], engine.d_out, 0)))
+        outs.append(lap if lap is not None else x.new_zeros((x.shape[0], 0)))
+        ctx.mark_non_differentiable(*[o for o in outs[1:] if o.numel() == 0 and x.shape[0] > 0])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, gu, gdu, glap):
+        engine, spec = ctx.engine, ctx.spec
+        needs = ctx.needs_input_grad[3:]
+        if not any(needs):
+            return (None, None, None) + (None,) * len(needs)
+
+        def prep(g):
+            if g is None:
+                return None
+            g = g.contiguous()
+            return g if g.dtype == torch.float32 else g.float()
+
+        gu, gdu, glap = prep(gu), prep(gdu), prep(glap)
+        if spec.nd == 0:
+            gdu = None
+        if not spec.lap:
+            glap = None
+        if gu is None and gdu is None and glap is None:
+            return (None, None, None) + (None,) * len(needs)
+        gacc = engine.backward_raw(ctx.packed, ctx.x, spec, gu, gdu, glap)
+        # reference parity: a parameter the loss does not depend on keeps grad None;
+        # that is exactly the output bias when the value stream carries no adjoint.
+        grads = engine.unpack(gacc, ctx.params, skip_last_bias=(gu is None))
+        grads = [g if need else None for g, need in zip(grads, needs)]
+        return (None, None, None) + tuple(grads)
