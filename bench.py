@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the PINN residual hot path (BASELINE.json metric): collocation-point
+residual+grad evaluations per second, 2-D Poisson -Laplace(u)=f, FCN 4x64 tanh.
+
+One "step" = for one batch of N collocation points per GPU: forward jet (u, grad u,
+Laplace u), residual r = Laplace u + f, loss = mean(r^2), reverse sweep dLoss/dtheta,
+and (N GPUs) ONE all-reduce of the flat gradient.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl native|reference]
+
+`value`  : points/s with the points already resident in HBM (C-ABI kernels + residual).
+`e2e`    : the same step through the public API (tp.conditions.PINNCondition.forward +
+           backward) with the points in pinned HOST memory: H2D of x every step, D2H of the
+           loss every step.
+`roofline`: dominant kernel (reverse sweep) timed alone with CUDA events.
+`cpu_baseline` / `--impl reference`: the reference's torch.autograd path (oracle/ref_autograd,
+           a restatement of the reference call sites on the same torch CPU kernels) on the
+           host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIDDEN = (64, 64, 64, 64)
+D_IN, D_OUT, S_STREAMS = 2, 1, 4
+F_FWD = 2 * (D_IN * 64 + S_STREAMS * 3 * 64 * 64 + S_STREAMS * 64 * D_OUT)   # 99,072
+F_ALG = 3 * F_FWD                                                             # 297,216 FLOP / point
+METRIC = "collocation-point residual+grad evals/sec (PINN Laplacian, FCN 4x64)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--points", type=int, default=1 << 22, help="collocation points per GPU per step")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm: torch CPU autograd restatement of the reference path (oracle/)
+# ----------------------------------------------------------------------------------------
+def cpu_reference_rate(steps, warmup, n_points):
+    import torch
+    from oracle import ref_autograd
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    seq = ref_autograd.build_fcn(D_IN, D_OUT, HIDDEN)
+    gen = torch.Generator().manual_seed(1)
+    times = []
+    for i in range(warmup + steps):
+        x = torch.rand(n_points, D_IN, generator=gen)
+        t0 = time.perf_counter()
+        out = ref_autograd.poisson_step(seq, x)
+        float(out["loss"])
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return n_points * len(times) / total, 1e3 * total / len(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = 20000
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
+    rate, ms, cores = cpu_reference_rate(steps, warmup, n)
+    line = {
+        "metric": METRIC, "value": rate, "unit": "points/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "2D Poisson -Lap u = f on the unit square, FCN 4x64 tanh, residual lap(u)+f, "
+                               "loss mean(r^2), dLoss/dtheta", "points_per_step": n},
+        "cpu_baseline": {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of {n} points, torch {__import__('torch').__version__} CPU autograd "
+                                   "(oracle/ref_autograd.poisson_step: reference call sites on the same torch ops)"},
+        "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampler
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import _lib
+    from torchphysics_b200.engine import JetSpec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()                                            # fail loudly if libtpx.so is missing
+
+    N = args.points
+    torch.manual_seed(0)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=HIDDEN).to(dev)
+    eng = model._native_engine()
+    params = eng.params()
+    spec = JetSpec((0, 1), (1.0, 1.0))
+    n_theta = sum(p.numel() for p in params)
+
+    import math
+    def source(x):
+        return 2 * math.pi ** 2 * torch.sin(math.pi * x[:, :1]) * torch.sin(math.pi * x[:, 1:2])
+
+    # rotating batches so that consecutive steps never reuse L2-resident inputs
+    bytes_per_batch = N * (D_IN + 1) * 4
+    n_batches = max(2, int(math.ceil(160e6 / bytes_per_batch)) + 1)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    xs = [torch.rand(N, D_IN, device=dev, generator=gen) for _ in range(n_batches)]
+    fs = [source(x) for x in xs]
+    flat = torch.zeros(n_theta + 1, dtype=torch.float32, device=dev)
+    launches = {"n": 0}
+
+    def step_resident(i):
+        """forward jet + residual + loss + reverse + flat gradient (+ all-reduce)."""
+        x, f = xs[i % n_batches], fs[i % n_batches]
+        packed = eng.packed(params)
+        u, du, lap = eng.forward_raw(packed, x, spec)
+        r = lap + f
+        loss = torch.mean(r * r)
+        glap = r * (2.0 / N)
+        gacc = eng.backward_raw(packed, x, spec, None, None, glap)
+        grads = eng.unpack(gacc, params, skip_last_bias=True)
+        off = 0
+        for g in grads:
+            if g is not None:
+                flat[off:off + g.numel()].copy_(g.reshape(-1))
+                off += g.numel()
+        flat[-1] = loss
+        if world > 1:
+            dist.all_reduce(flat)
+        launches["n"] += 3                                # fwd kernel, bwd kernel, unpack kernel
+        return loss
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches["n"] = 0
+    ms_step = timed(step_resident, args.steps, args.warmup)
+    n_launch = launches["n"] * args.steps // (args.steps + args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    value = N * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API, host buffers ---------------------------------
+    host_x = [x.cpu().pin_memory() for x in xs[:2]]
+    state = {"i": 0}
+
+    class HostBatches(tp.samplers.PointSampler):
+        """hands the condition this step's points: pinned host memory -> device copy"""
+        def __init__(self):
+            super().__init__(n_points=N)
+        def sample_points(self, params=tp.spaces.Points.empty(), device="cpu"):
+            hx = host_x[state["i"] % len(host_x)]
+            state["i"] += 1
+            return tp.spaces.Points(hx.to(device, non_blocking=True), X)
+
+    cond = tp.conditions.PINNCondition(model, HostBatches(), lambda u, x, f: tp.utils.laplacian(u, x) + f,
+                                       data_functions={"f": source})
+    reducer = tp.parallel.FlatGradAllReduce(list(model.parameters()), n_scalars=1)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e(i):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device=dev)
+        loss.backward()
+        (mean_loss,) = reducer([loss])
+        loss_host.copy_(mean_loss.reshape(1), non_blocking=False)      # D2H read of the step's result
+        return loss_host
+
+    ms_e2e = timed(step_e2e, max(3, args.steps // 2), max(3, args.warmup))
+    e2e = N * world / (ms_e2e * 1e-3)
+
+    # ---- dominant kernel alone (roofline) ---------------------------------------------------
+    packed = eng.packed(params)
+    glap = torch.randn(N, 1, device=dev) / N
+    def bwd_only(i):
+        eng.backward_raw(packed, xs[i % n_batches], spec, None, None, glap)
+    def fwd_only(i):
+        eng.forward_raw(packed, xs[i % n_batches], spec)
+    ms_bwd = timed(bwd_only, 10, 3)
+    ms_fwd = timed(fwd_only, 10, 3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+        achieved = N * 2 * F_FWD / (ms_bwd * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "2D Poisson -Lap u = f on the unit square, FCN 4x64 tanh, residual lap(u)+f, "
+                                   "loss mean(r^2), dLoss/dtheta", "points_per_gpu_per_step": N,
+                       "global_points_per_step": N * world, "parallelism": f"dp{world}",
+                       "l2": f"{n_batches} rotating input batches of {bytes_per_batch/1e6:.0f} MB (> 126 MB L2 in total)",
+                       "theta": n_theta},
+            "e2e": {"value": e2e, "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": N * D_IN * 4, "d2h_bytes_per_step": 4,
+                    "path": "tp.conditions.PINNCondition.forward + loss.backward(), x from pinned host memory"},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "tensor", "kernel": "fcn_bwd_kernel (reverse sweep incl. forward recompute)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_flop_per_point": 2 * F_FWD, "ms_per_launch": ms_bwd,
+                         "forward_kernel_ms": ms_fwd,
+                         "note": "fp32 CUDA-core kernel in this round; FLOP = GEMM FLOP of SURVEY 8(d) "
+                                 "(reverse = 2 x forward), recompute not counted"},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            n_cpu = 20000
+            rate, ms, cores = cpu_reference_rate(8, 2, n_cpu)
+            line["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
+                                    "sample": f"8 steps of {n_cpu} points, torch CPU autograd restatement of the "
+                                              "reference call sites (oracle/ref_autograd.poisson_step)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

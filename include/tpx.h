@@ -103,6 +103,81 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
 int tpx_fcn_unpack_grads(const tpx_fcn_desc* net, const double* grad_acc, void* const* grads_host,
                          int accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Collocation-point samplers (problem/domains + problem/samplers of the reference).
+ * A shape is one of the reference's basic domains with CONSTANT parameters; `col` is the
+ * first column of the point row it occupies (product domains put shapes side by side,
+ * domainoperations/product.py:233-267).  A region is a boolean combination of shapes as a
+ * postfix program: Cut = A B NOT AND (cut.py:39-42), Union = A B OR (union.py:45-48),
+ * Intersection = A B AND, Product = A B AND on different columns (product.py:108-111).
+ * ------------------------------------------------------------------------------------ */
+#define TPX_SHAPE_INTERVAL 1      /* p = {lower, upper}                  domain1D/interval.py       */
+#define TPX_SHAPE_PARALLELOGRAM 2 /* p = {ox, oy, c1x, c1y, c2x, c2y}    domain2D/parallelogram.py  */
+#define TPX_SHAPE_CIRCLE 3        /* p = {cx, cy, r}                     domain2D/circle.py         */
+#define TPX_MAX_SHAPES 8
+#define TPX_MAX_OPS 24
+#define TPX_OP_SHAPE 0 /* push membership of shapes[arg]; op word = opcode | arg << 8 */
+#define TPX_OP_AND 1
+#define TPX_OP_OR 2
+#define TPX_OP_NOT 3
+
+typedef struct tpx_shape {
+  int32_t kind;
+  int32_t col;
+  float p[6];
+} tpx_shape;
+
+typedef struct tpx_region {
+  int32_t n_shapes;
+  int32_t n_ops;
+  tpx_shape shapes[TPX_MAX_SHAPES];
+  int32_t ops[TPX_MAX_OPS];
+} tpx_region;
+
+/* mask[i] = 1 if row i of `points` (n rows of row_stride floats) lies in the region.
+ * Replaces Domain._contains (interval.py:37-43, parallelogram.py:83-103, circle.py:34-40,
+ * cut.py:39-42, union.py:45-48) with the same float32 operation order. */
+int tpx_region_contains(const tpx_region* region, const float* points, int64_t n, int32_t row_stride,
+                        uint8_t* mask, void* stream);
+
+/* n uniform points of one shape written to columns [col, col+dim) of `out`; point i is a
+ * pure function of (seed, offset + i) (Philox4x32-10).  Replaces sample_random_uniform of
+ * interval.py:45-55, parallelogram.py:105-117, circle.py:52-68. */
+int tpx_sample_uniform(const tpx_shape* shape, uint64_t seed, uint64_t offset, int64_t n, float* out,
+                       int32_t row_stride, void* stream);
+
+/* Rejection sampling without a host round trip (replaces the host-synchronising loop of
+ * domainoperations/sampler_helper.py:50-76 and the filter loop of
+ * samplers/random_samplers.py:60-90): n_candidates points of `generator` are tested
+ * against `accept`; the accepted ones are appended IN CANDIDATE ORDER (stable warp-ballot
+ * compaction) to `out` starting at row counters[0], never beyond row n_wanted.
+ * counters (device, int64[4], caller zeroes before the first round):
+ *   [0] rows filled so far (<= n_wanted)   [1] candidates offered so far
+ *   [2] scratch                            [3] candidates accepted so far (unclamped)   */
+int tpx_sample_reject_workspace_bytes(int64_t n_candidates, size_t* bytes);
+int tpx_sample_uniform_reject(const tpx_shape* generator, const tpx_region* accept, uint64_t seed,
+                              uint64_t offset, int64_t n_candidates, int64_t n_wanted, float* out,
+                              int32_t row_stride, int64_t* counters, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* Deterministic grids: Interval interior linspace (interval.py:57-65), Parallelogram
+ * barycentric n1 x n2 grid (parallelogram.py:119-152; n = n1*n2), Circle sunflower
+ * arrangement (circle.py:70-99). */
+int tpx_sample_grid(const tpx_shape* shape, int64_t n, int32_t n1, int32_t n2, float* out, int32_t row_stride,
+                    void* stream);
+
+/* Latin hypercube (samplers/random_samplers.py:203-221): keys = iid 63-bit sort keys (their
+ * argsort is the random permutation of one axis); tpx_sample_lhs writes column c of row i
+ * as box[2c] + len_c * perm[c*n+i]/n + len_c/n * U(0,1). */
+int tpx_sample_keys(uint64_t seed, uint64_t offset, int64_t n, int64_t* keys, void* stream);
+int tpx_sample_lhs(int32_t d, const float* box, const int64_t* perm, uint64_t seed, uint64_t offset, int64_t n,
+                   float* out, int32_t row_stride, int32_t col, void* stream);
+
+/* Union pick (domainoperations/union.py:72-93): out[i] = a[i] if b[i] lies in region in_a or
+ * U(0,1) <= ratio (= vol_A / (vol_A + vol_B)), else b[i]. */
+int tpx_union_pick(const tpx_region* in_a, const float* a, const float* b, int64_t n, int32_t d, int32_t row_stride,
+                   float ratio, uint64_t seed, uint64_t offset, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

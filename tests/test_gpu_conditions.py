@@ -1,0 +1,157 @@
+"""The hot path through the reference-facing API (tp.models / tp.utils / tp.conditions /
+tp.solver) on the GPU, against the golden outputs of the real reference and the oracle.
+Tolerance 1e-5 max-norm relative (BASELINE.json)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jet_numpy, ref_autograd
+from tests.golden_io import load, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _load_params(model, params):
+    lins = [m for m in model.sequential if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        for i, lin in enumerate(lins):
+            lin.weight.copy_(torch.as_tensor(params[2 * i]))
+            lin.bias.copy_(torch.as_tensor(params[2 * i + 1]))
+
+
+def _grads(model):
+    return [None if p.grad is None else p.grad.cpu().numpy() for p in model._native_engine().params()]
+
+
+def test_pinn_condition_poisson_matches_reference():
+    import torchphysics_b200 as tp
+    G = load("poisson_4x64")
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(64,) * 4).cuda()
+    _load_params(model, G["params"])
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["x"]), X))
+    cond = tp.conditions.PINNCondition(model, sampler, lambda u, x, f: tp.utils.laplacian(u, x) + f,
+                                       data_functions={"f": ref_autograd.poisson_source})
+    for it in range(3):                       # 1st call learns the jet spec, later calls are steady state
+        model.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+        assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
+        g = _grads(model)
+        assert g[-1] is None and G["dtheta"][-1] is None      # output bias untouched, as in the reference
+        for a, w in zip(g[:-1], G["dtheta"][:-1]):
+            assert relerr(a, w) < TOL
+
+
+def test_operators_on_model_output_match_reference():
+    import torchphysics_b200 as tp
+    G = load("ns_3x32")
+    X, Y = tp.spaces.R2("x"), tp.spaces.R2("u") * tp.spaces.R1("p")
+    model = tp.models.FCN(X, Y, hidden=(32,) * 3).cuda()
+    _load_params(model, G["params"])
+    pts = tp.spaces.Points(torch.from_numpy(G["x"]).cuda(), X)
+    coords, pts = pts.track_coord_gradients()
+    out = model(pts)
+    u, p = out.coordinates["u"], out.coordinates["p"]
+    x = coords["x"]
+    assert relerr(out.as_tensor.detach().cpu().numpy(), G["y"]) < TOL
+    assert relerr(tp.utils.jac(out.as_tensor, x).detach().cpu().numpy(), G["jac"]) < TOL
+    assert relerr(tp.utils.div(u, x).detach().cpu().numpy(), G["div"]) < TOL
+    assert relerr(tp.utils.convective(u, u, x).detach().cpu().numpy(), G["conv"]) < TOL
+    lap = torch.cat([tp.utils.laplacian(u[:, :1], x), tp.utils.laplacian(u[:, 1:2], x)], dim=1)
+    assert relerr(lap.detach().cpu().numpy(), G["lap"]) < TOL
+    gp = tp.utils.grad(p, x)
+    assert relerr(gp.detach().cpu().numpy(), G["jac"][:, 2, :]) < TOL
+    # whole Navier-Stokes residual loss and its parameter gradient
+    r = torch.cat([tp.utils.convective(u, u, x) - 0.01 * lap + gp, tp.utils.div(u, x)], dim=1)
+    loss = tp.conditions.SquaredError()(r).mean()
+    assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
+    loss.backward()
+    for a, w in zip(_grads(model), G["dtheta"]):
+        if w is None:
+            assert a is None or np.abs(a).max() == 0
+        else:
+            assert relerr(a, w) < TOL
+
+
+def test_heat_condition_with_product_space():
+    import torchphysics_b200 as tp
+    G = load("heat_3x48")
+    X, T, U = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
+    model = tp.models.FCN(X * T, U, hidden=(48,) * 3).cuda()
+    _load_params(model, G["params"])
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["xt"]), X * T))
+    cond = tp.conditions.PINNCondition(model, sampler, lambda u, x, t: tp.utils.grad(u, t) - tp.utils.laplacian(u, x))
+    for it in range(2):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+    assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
+    for a, w in zip(_grads(model)[:-1], G["dtheta"][:-1]):
+        assert relerr(a, w) < TOL
+
+
+def test_deep_ritz_condition():
+    import torchphysics_b200 as tp
+    G = load("ritz_4x40")
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(40,) * 4).cuda()
+    _load_params(model, G["params"])
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["x"]), X))
+    cond = tp.conditions.DeepRitzCondition(
+        model, sampler, lambda u, x: 0.5 * (tp.utils.grad(u, x) ** 2).sum(dim=1, keepdim=True) - u)
+    for it in range(2):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+    assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
+    for a, w in zip(_grads(model), G["dtheta"]):
+        assert relerr(a, w) < TOL
+
+
+def test_solver_trains_poisson():
+    """a few Adam steps through Solver/Trainer reduce the PINN loss; steady state uses one
+    forward and one reverse launch per condition."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(0)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(32,) * 3)
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    f = lambda x: 2 * math.pi ** 2 * torch.sin(math.pi * x[:, :1]) * torch.sin(math.pi * x[:, 1:])
+    pde = tp.conditions.PINNCondition(model, tp.samplers.RandomUniformSampler(sq, n_points=4096),
+                                      lambda u, x, f: tp.utils.laplacian(u, x) + f, data_functions={"f": f})
+    solver = tp.solver.Solver([pde], optimizer_setting=tp.solver.OptimizerSetting(torch.optim.Adam, lr=2e-3))
+    trainer = tp.solver.Trainer(max_steps=60)
+    trainer.fit(solver)
+    first = float(torch.stack(trainer.losses[:5]).mean())
+    last = float(torch.stack(trainer.losses[-5:]).mean())
+    assert last < 0.5 * first
+
+
+def test_cpu_tensors_and_unsupported_nets_fail_loudly():
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import _lib
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(16, 16))
+    with pytest.raises(_lib.TpxError):
+        model(tp.spaces.Points(torch.rand(4, 2), X))
+    relu = tp.models.FCN(X, U, hidden=(16, 16), activations=torch.nn.ReLU()).cuda()
+    with pytest.raises(_lib.TpxError):
+        relu(tp.spaces.Points(torch.rand(4, 2).cuda(), X))
+
+
+def test_generic_operator_semantics_on_plain_tensors():
+    """operators on hand-written torch functions keep the reference's autograd definition
+    (closed-form cases of the reference's tests/tests_utils/test_differentialoperators.py)."""
+    import torchphysics_b200 as tp
+    a = torch.tensor([[1.0, 1.0], [2.0, 0.5]], requires_grad=True, device="cuda")
+    u = (a ** 2).sum(dim=1, keepdim=True)
+    assert torch.allclose(tp.utils.laplacian(u, a), torch.full((2, 1), 4.0, device="cuda"))
+    assert torch.allclose(tp.utils.grad(u, a), 2 * a)
+    v = torch.stack([a[:, 0] ** 2, a[:, 0] * a[:, 1]], dim=1)
+    assert torch.allclose(tp.utils.div(v, a).reshape(-1), 2 * a[:, 0] + a[:, 0])
+    j = tp.utils.jac(v, a)
+    assert j.shape == (2, 2, 2) and torch.allclose(j[:, 1, 0], a[:, 1])

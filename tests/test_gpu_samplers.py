@@ -1,0 +1,190 @@
+"""Sampler / domain kernels (through the C ABI, via tp.domains / tp.samplers) against the
+numpy oracle and the golden outputs of the real reference: exact point counts, bit-exact
+membership, deterministic grids, seeded reproducibility."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry
+from tests.golden_io import load
+from tests.test_oracle_golden import DOMS
+
+pytestmark = pytest.mark.gpu
+
+
+def _tp():
+    import torchphysics_b200 as tp
+    return tp
+
+
+def _build(tp, dom, names=None):
+    """oracle tuple tree -> tp.domains object."""
+    kind = dom[0]
+    if kind == "interval":
+        return tp.domains.Interval(tp.spaces.R1("t"), dom[1], dom[2])
+    if kind == "parallelogram":
+        return tp.domains.Parallelogram(tp.spaces.R2("x"), dom[1], dom[2], dom[3])
+    if kind == "circle":
+        return tp.domains.Circle(tp.spaces.R2("x"), dom[1], dom[2])
+    a, b = _build(tp, dom[1]), _build(tp, dom[2])
+    return {"cut": lambda: a - b, "union": lambda: a + b, "product": lambda: a * b}[kind]()
+
+
+@pytest.mark.parametrize("name", ["para", "circ", "sq", "cut", "uni", "ival", "prod"])
+def test_membership_matches_reference_bit_for_bit(name):
+    tp = _tp()
+    G = load("domains")
+    dom = _build(tp, DOMS[name])
+    cand = {"ival": "cand1", "prod": "cand3"}.get(name, "cand")
+    pts = tp.spaces.Points(torch.from_numpy(G[cand]).cuda(), dom.space)
+    got = dom._contains(pts).cpu().numpy().reshape(-1)
+    assert np.array_equal(got, G["in_" + name])
+    assert np.array_equal(got, geometry.contains(DOMS[name], G[cand]))
+
+
+@pytest.mark.parametrize("name", ["para", "circ", "sq", "cut", "uni", "ival", "prod"])
+@pytest.mark.parametrize("n", [1, 500, 100003])
+def test_random_uniform_counts_and_membership(name, n):
+    tp = _tp()
+    dom = _build(tp, DOMS[name])
+    pts = tp.samplers.RandomUniformSampler(dom, n_points=n).sample_points(device="cuda")
+    assert len(pts) == n and pts.as_tensor.shape == (n, dom.dim) and pts.as_tensor.is_cuda
+    x = pts.as_tensor.cpu().numpy()
+    assert geometry.contains(DOMS[name], x).all()          # oracle membership, float32 op order
+    assert bool(dom._contains(pts).all())
+    bb = geometry.bounding_box(DOMS[name])
+    for c in range(dom.dim):
+        assert x[:, c].min() >= bb[2 * c] - 1e-6 and x[:, c].max() <= bb[2 * c + 1] + 1e-6
+
+
+def test_seeded_reproducibility_and_streams():
+    tp = _tp()
+    dom = _build(tp, DOMS["cut"])
+    torch.manual_seed(7)
+    a = dom.sample_random_uniform(n=20000, device="cuda").as_tensor.clone()
+    b = dom.sample_random_uniform(n=20000, device="cuda").as_tensor.clone()
+    torch.manual_seed(7)
+    a2 = dom.sample_random_uniform(n=20000, device="cuda").as_tensor
+    b2 = dom.sample_random_uniform(n=20000, device="cuda").as_tensor
+    assert torch.equal(a, a2) and torch.equal(b, b2) and not torch.equal(a, b)
+    # the points do not depend on the acceptance estimate the domain has learned
+    dom._accept_rate = 0.2
+    torch.manual_seed(7)
+    assert torch.equal(a, dom.sample_random_uniform(n=20000, device="cuda").as_tensor)
+    tp.domains.set_rank_stream(1)
+    torch.manual_seed(7)
+    c = dom.sample_random_uniform(n=20000, device="cuda").as_tensor
+    tp.domains.set_rank_stream(0)
+    assert not torch.equal(a, c)
+
+
+def test_uniformity_moments():
+    """size-independent property at scale: first/second moments of 4M points of the unit disc
+    minus a square agree with the closed form."""
+    tp = _tp()
+    X = tp.spaces.R2("x")
+    dom = tp.domains.Circle(X, [0, 0], 1.0) - tp.domains.Parallelogram(X, [-.25, -.25], [.25, -.25], [-.25, .25])
+    n = 1 << 22
+    x = dom.sample_random_uniform(n=n, device="cuda").as_tensor.double()
+    area = np.pi - 0.25
+    ex2 = (np.pi / 4 - 0.5 ** 4 / 12 * 1.0) / area      # int x^2 over disc = pi/4, over square side .5: s^4/12
+    assert abs(float(x[:, 0].mean())) < 3e-3 and abs(float(x[:, 1].mean())) < 3e-3
+    assert abs(float((x[:, 0] ** 2).mean()) - ex2) < 3e-3
+    r = x.norm(dim=1)
+    assert float(r.max()) <= 1.0 and float(x.abs().max(dim=1).values.min()) > 0.25 - 1e-7
+
+
+def test_density_mode_counts():
+    tp = _tp()
+    G = load("domains")
+    dom = _build(tp, DOMS["circ"])
+    pts = tp.samplers.RandomUniformSampler(dom, density=40.0).sample_points(device="cuda")
+    assert len(pts) == int(np.ceil(np.float32(40.0) * np.float32(G["vol_circ"])))
+    cut = _build(tp, DOMS["cut"])
+    with pytest.warns(UserWarning):
+        pts = tp.samplers.RandomUniformSampler(cut, density=500.0).sample_points(device="cuda")
+    assert 0 < len(pts) < 500 * float(G["vol_circ"]) and geometry.contains(DOMS["cut"], pts.as_tensor.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("n", [1, 7, 50])
+def test_grids_interval_circle(n):
+    tp = _tp()
+    G = load("domains")
+    g = tp.samplers.GridSampler(_build(tp, DOMS["ival"]), n_points=n).sample_points(device="cuda")
+    assert np.allclose(g.as_tensor.cpu().numpy(), G[f"grid_ival_{n}"], rtol=1e-6, atol=1e-7)
+    g = tp.samplers.GridSampler(_build(tp, DOMS["circ"]), n_points=n).sample_points(device="cuda")
+    assert np.allclose(g.as_tensor.cpu().numpy(), G[f"grid_circ_{n}"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("n", [16, 50, 100])
+def test_grid_parallelogram(n):
+    tp = _tp()
+    G = load("domains")
+    dom = _build(tp, DOMS["para"])
+    g = tp.samplers.GridSampler(dom, n_points=n).sample_points(device="cuda")
+    ref = G[f"grid_para_{n}"]
+    want = geometry.grid(DOMS["para"], n)
+    assert len(g) == n == len(ref)
+    got = g.as_tensor.cpu().numpy()
+    assert np.allclose(got[: len(want)], ref[: len(want)], rtol=1e-6, atol=1e-7)
+    assert geometry.contains(DOMS["para"], got).all()
+
+
+def test_grid_on_cut_and_union():
+    tp = _tp()
+    for name in ("cut", "uni"):
+        dom = _build(tp, DOMS[name])
+        with pytest.warns(UserWarning) if name == "uni" else _nullcontext():
+            g = tp.samplers.GridSampler(dom, n_points=200).sample_points(device="cuda")
+        assert len(g) == 200
+        assert geometry.contains(DOMS[name], g.as_tensor.cpu().numpy()).all()
+
+
+class _nullcontext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def test_lhs_sampler():
+    tp = _tp()
+    dom = _build(tp, DOMS["para"])
+    n = 1000
+    pts = tp.samplers.LHSSampler(dom, n).sample_points(device="cuda")
+    assert len(pts) == n and geometry.contains(DOMS["para"], pts.as_tensor.cpu().numpy()).all()
+    # on an axis-aligned box every one of the n strata of every axis holds exactly one point
+    box = tp.domains.Parallelogram(tp.spaces.R2("x"), [0, 0], [2, 0], [0, 1])
+    x = tp.samplers.LHSSampler(box, n).sample_points(device="cuda").as_tensor.cpu().numpy()
+    assert sorted(np.floor(x[:, 0] / 2 * n).astype(int).tolist()) == list(range(n))
+    assert sorted(np.floor(x[:, 1] * n).astype(int).tolist()) == list(range(n))
+
+
+def test_filter_and_product_and_static_samplers():
+    tp = _tp()
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    s = tp.samplers.RandomUniformSampler(sq, n_points=300, filter_fn=lambda x: x[:, :1] <= 0.5)
+    p = s.sample_points(device="cuda")
+    assert len(p) == 300 and float(p.as_tensor[:, 0].max()) <= 0.5
+    ps = tp.samplers.RandomUniformSampler(sq, n_points=10) * tp.samplers.GridSampler(tp.domains.Interval(T, 0, 1), n_points=4)
+    q = ps.sample_points(device="cuda")
+    assert len(q) == 40 and list(q.space.keys()) == ["x", "t"]
+    st = tp.samplers.RandomUniformSampler(sq * tp.domains.Interval(T, 0, 2), n_points=64).make_static()
+    a = st.sample_points(device="cuda")
+    b = st.sample_points(device="cuda")
+    assert a == b and a.as_tensor.shape == (64, 3) and float(a.as_tensor[:, 2].max()) <= 2.0
+
+
+def test_empty_and_error_paths():
+    tp = _tp()
+    from torchphysics_b200 import _lib
+    X = tp.spaces.R2("x")
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    assert len(sq.sample_random_uniform(n=0, device="cuda")) == 0
+    with pytest.raises(_lib.TpxError):
+        tp.domains.Circle(X, [0, 0], lambda t: t + 1)
+    far = tp.domains.Circle(X, [10, 10], 0.1)
+    with pytest.raises(RuntimeError):
+        (sq & far).sample_random_uniform(n=5, device="cuda")

@@ -1,0 +1,175 @@
+"""Host logic that needs no GPU: the C-ABI library loads and exports every symbol of
+include/tpx.h, descriptor construction, spaces/Points/UserFunction semantics, condition
+orchestration with a stand-in module, gradient all-reduce over gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from torchphysics_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tpx.h")).read()
+    declared = set(re.findall(r"\b(tpx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.tpx_version() == 100
+
+
+def test_struct_layouts_match_header():
+    from torchphysics_b200 import _lib
+    assert ctypes.sizeof(_lib.FcnDesc) == 4 * (3 + 16 + 1)
+    assert ctypes.sizeof(_lib.JetDesc) == 4 * (1 + 3 + 1 + 3)
+    assert ctypes.sizeof(_lib.Shape) == 32
+    assert ctypes.sizeof(_lib.Region) == 8 + 8 * 32 + 24 * 4
+
+
+def test_argument_errors_without_gpu():
+    from torchphysics_b200 import _lib
+    lib = _lib.lib()
+    d = _lib.FcnDesc()
+    d.d_in, d.d_out, d.n_hidden = 2, 1, 0
+    n = ctypes.c_size_t(0)
+    assert lib.tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)) == _lib.TPX_E_ARG
+    assert b"n_hidden" in lib.tpx_last_error()
+    d.n_hidden = 2
+    d.widths[0], d.widths[1] = 64, 300
+    assert lib.tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)) == _lib.TPX_E_UNSUPPORTED
+    d.widths[1] = 64
+    assert lib.tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)) == 0 and n.value > 64 * 64
+
+
+def test_region_programs():
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import _lib
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    c = tp.domains.Circle(X, [0, 0], 1.0)
+    sq = tp.domains.Parallelogram(X, [-.25, -.25], [.25, -.25], [-.25, .25])
+    iv = tp.domains.Interval(T, 0, 2)
+    S, A, O, N = _lib.TPX_OP_SHAPE, _lib.TPX_OP_AND, _lib.TPX_OP_OR, _lib.TPX_OP_NOT
+    shapes, ops = (c - sq)._program(0)
+    assert [s.kind for s in shapes] == [3, 2] and ops == [S, S | 1 << 8, N, A]
+    shapes, ops = ((c + sq) * iv)._program(0)
+    assert [s.col for s in shapes] == [0, 0, 2] and ops == [S, S | 1 << 8, O, S | 2 << 8, A]
+    gen = ((c - sq) - tp.domains.Circle(X, [.5, .5], .1))._generator(0)
+    assert gen[0].kind == 3 and gen[2] == [S, N, S | 1 << 8, N, A]
+    assert (c + sq)._generator(0) is None
+    assert abs(float((c - sq).bounding_box()[0]) + 1) < 1e-7
+    assert (sq * iv).dim == 3 and list((sq * iv).space.keys()) == ["x", "t"]
+    assert abs(float((sq * iv).volume()) - 0.5) < 1e-6
+    assert c.compute_n_from_density(10.0) == 32
+
+
+def test_points_and_spaces():
+    import torchphysics_b200 as tp
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    sp = X * T
+    assert sp.dim == 3 and list(sp.keys()) == ["x", "t"] and "x" in sp and X in sp
+    p = tp.spaces.Points(torch.arange(12.0).reshape(4, 3), sp)
+    assert len(p) == 4 and p.coordinates["t"].shape == (4, 1)
+    assert p[:, ["t", "x"]].as_tensor[0].tolist() == [2.0, 0.0, 1.0]
+    assert p[1:3].as_tensor.shape == (2, 3)
+    q = tp.spaces.Points(torch.ones(4, 1), tp.spaces.R1("u"))
+    assert list(p.join(q).space.keys()) == ["x", "t", "u"]
+    assert len(p | p) == 8
+    coords, tracked = p.track_coord_gradients()
+    assert coords["x"].requires_grad and tracked.as_tensor.requires_grad and set(tracked._coord_leaves) == {"x", "t"}
+    with pytest.raises(AssertionError):
+        tp.spaces.Points(torch.ones(4, 2), sp)
+
+
+def test_user_function_binds_by_name():
+    import torchphysics_b200 as tp
+    f = tp.utils.UserFunction(lambda u, x, k=2.0: u + k * x)
+    assert f.necessary_args == ["u", "x"] and f.optional_args == ["k"]
+    out = f({"x": torch.ones(2, 1), "u": torch.zeros(2, 1), "unused": 5})
+    assert out.tolist() == [[2.0], [2.0]]
+    with pytest.raises(AssertionError):
+        f({"x": torch.ones(2, 1)})
+    with pytest.raises(ValueError):
+        tp.utils.UserFunction(lambda *args: 0)
+
+
+def test_condition_orchestration_with_stand_in_module():
+    """reference tests/test_conditions.py style: the module is a UserFunction, so the
+    condition's sample -> track -> data -> module -> residual -> error -> reduce chain runs
+    without a GPU (the generic autograd definition of the operators)."""
+    import torchphysics_b200 as tp
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+
+    class Sq(torch.nn.Module):
+        def forward(self, points):
+            x = points.coordinates["x"]
+            return tp.spaces.Points((x ** 2).sum(dim=1, keepdim=True), U)
+
+    pts = tp.spaces.Points(torch.tensor([[0.0, 0.0], [1.0, 0.5], [0.5, 2.0]]), X)
+    sampler = tp.samplers.DataSampler(pts)
+    cond = tp.conditions.PINNCondition(Sq(), sampler, lambda u, x, f: tp.utils.laplacian(u, x) - f,
+                                       data_functions={"f": lambda x: 3.0 * torch.ones_like(x[:, :1])})
+    loss = cond()
+    assert abs(float(loss) - 1.0) < 1e-6           # (4 - 3)^2
+    ritz = tp.conditions.DeepRitzCondition(Sq(), sampler, lambda u, x: 0.5 * (tp.utils.grad(u, x) ** 2).sum(1, keepdim=True))
+    want = float((2.0 * (pts.as_tensor ** 2).sum(1)).mean())
+    assert abs(float(ritz()) - want) < 1e-6
+    assert tp.conditions.SquaredError()(torch.ones(3, 2, 2)).tolist() == [4.0, 4.0, 4.0]
+
+
+def test_fcn_layout_matches_reference_state_dict():
+    import torchphysics_b200 as tp
+    from tests.golden_io import load
+    G = load("poisson_4x64")
+    torch.manual_seed(0)
+    m = tp.models.FCN(tp.spaces.R2("x"), tp.spaces.R1("u"), hidden=(64,) * 4)
+    keys = list(m.state_dict().keys())
+    assert keys == [f"sequential.{2 * i}.{k}" for i in range(5) for k in ("weight", "bias")]
+    for p, w in zip(m.parameters(), G["params"]):
+        assert np.array_equal(p.detach().numpy(), w)        # same RNG draw order as the reference
+
+
+def _gloo_worker(rank, size, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from torchphysics_b200 import parallel
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(3, 2)
+    unused = torch.nn.Parameter(torch.zeros(2))
+    x = torch.arange(24.0).reshape(8, 3)
+    n = parallel.shard_count(8)
+    lo = sum(parallel.shard_count(8, r, size) for r in range(rank))
+    loss = (lin(x[lo:lo + n]) ** 2).mean()
+    loss.backward()
+    red = parallel.FlatGradAllReduce([lin.weight, lin.bias, unused], n_scalars=1)
+    (mean_loss,) = red([loss])
+    out.put((rank, lin.weight.grad.clone(), float(mean_loss), unused.grad is None))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(3, 2)
+    x = torch.arange(24.0).reshape(8, 3)
+    loss = (lin(x) ** 2).mean()
+    loss.backward()
+    for rank, g, l, unused_none in res:
+        assert torch.allclose(g, lin.weight.grad, rtol=1e-5, atol=1e-5)
+        assert abs(l - float(loss)) < 1e-4 * abs(float(loss))
+        assert unused_none

@@ -31,7 +31,22 @@ EXPORTS = (
     "tpx_fcn_backward_workspace_bytes",
     "tpx_fcn_jet_backward",
     "tpx_fcn_unpack_grads",
+    "tpx_region_contains",
+    "tpx_sample_uniform",
+    "tpx_sample_reject_workspace_bytes",
+    "tpx_sample_uniform_reject",
+    "tpx_sample_grid",
+    "tpx_sample_keys",
+    "tpx_sample_lhs",
+    "tpx_union_pick",
 )
+
+TPX_SHAPE_INTERVAL = 1
+TPX_SHAPE_PARALLELOGRAM = 2
+TPX_SHAPE_CIRCLE = 3
+TPX_MAX_SHAPES = 8
+TPX_MAX_OPS = 24
+TPX_OP_SHAPE, TPX_OP_AND, TPX_OP_OR, TPX_OP_NOT = 0, 1, 2, 3
 
 
 class TpxLibraryError(RuntimeError):
@@ -60,6 +75,19 @@ class JetDesc(ctypes.Structure):
         ("dcol", ctypes.c_int32 * TPX_MAX_ND),
         ("lap", ctypes.c_int32),
         ("lap_w", ctypes.c_float * TPX_MAX_ND),
+    ]
+
+
+class Shape(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("col", ctypes.c_int32), ("p", ctypes.c_float * 6)]
+
+
+class Region(ctypes.Structure):
+    _fields_ = [
+        ("n_shapes", ctypes.c_int32),
+        ("n_ops", ctypes.c_int32),
+        ("shapes", Shape * TPX_MAX_SHAPES),
+        ("ops", ctypes.c_int32 * TPX_MAX_OPS),
     ]
 
 

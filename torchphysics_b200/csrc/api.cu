@@ -5,18 +5,20 @@
 #include <cstring>
 
 #include "fcn_kernels.cuh"
+#include "tpx_internal.h"
 
 namespace tpx {
 
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
+const char* last_error() { return g_err; }
 
 static int pad_width(int w) {
   if (w <= 32) return 32;
@@ -165,7 +167,7 @@ static int sm_count() {
   return n;
 }
 
-static int cuda_fail(const char* what) {
+int cuda_fail(const char* what) {
   cudaError_t e = cudaGetLastError();
   return fail(TPX_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }

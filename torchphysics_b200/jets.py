@@ -1,0 +1,196 @@
+"""Bridges the tensor-in / tensor-out operator API of the reference onto the native jets.
+
+The reference's operators receive *tensors* (``laplacian(u, x)``) and rely on the autograd
+graph between them (reference ``utils/differentialoperators/differentialoperators.py``).
+Here a model evaluated on tracked points returns a ``JetTensor``: an ordinary tensor that
+remembers (a) the ``JetEvaluation`` that produced it and (b) which output columns it
+holds.  The operators in ``operators.py`` look the requested derivatives up in the
+evaluation's streams when the derivative variables are exactly the coordinate leaves
+created by ``Points.track_coord_gradients``; every other use of the tensor behaves like
+a plain tensor.
+
+Which streams a model computes is learned per call site: the first call computes the
+value only, an operator that needs more re-evaluates with the larger ``JetSpec`` and
+records it as the hint for the next call from the same condition -- from the second
+training step on, one condition = one forward launch + one reverse launch.
+"""
+import threading
+import warnings
+
+import torch
+
+from .engine import JetSpec
+
+_tls = threading.local()
+
+
+def current_scope():
+    return getattr(_tls, "scope", None)
+
+
+class scope:
+    """``with scope(key):`` marks which condition the enclosed model calls belong to."""
+
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        self.prev = current_scope()
+        _tls.scope = self.key
+        return self
+
+    def __exit__(self, *exc):
+        _tls.scope = self.prev
+        return False
+
+
+class TpxFallbackWarning(UserWarning):
+    pass
+
+
+_warned = set()
+
+
+def warn_fallback(reason):
+    if reason not in _warned:
+        _warned.add(reason)
+        warnings.warn(f"native jet path not used: {reason}; evaluating with torch.autograd", TpxFallbackWarning)
+
+
+class JetEvaluation:
+    """One evaluation of a natively supported network on a batch of tracked points."""
+
+    def __init__(self, engine, x2d, batch_shape, leaf_cols, hints, hint_key, autograd_fn, spec):
+        self.engine = engine
+        self.x = x2d                        # (N, d_in) detached, contiguous
+        self.batch_shape = tuple(batch_shape)
+        self.leaf_cols = leaf_cols          # id(leaf) -> (leaf, [input columns])
+        self.hints, self.hint_key = hints, hint_key
+        self.autograd_fn = autograd_fn      # () -> plain autograd output (generic path)
+        self._plain = None
+        self.spec = spec
+        self.u, self.du, self.lap = engine.jet(x2d, spec)
+
+    def columns_of(self, var):
+        hit = self.leaf_cols.get(id(var))
+        if hit is None or hit[0] is not var:
+            return None
+        return hit[1]
+
+    def ensure(self, need):
+        """make sure the computed streams cover ``need``; returns False if impossible."""
+        if self.spec.covers(need):
+            return True
+        cols = list(self.spec.dcols)
+        for c in need.dcols:
+            if c not in cols:
+                cols.append(c)
+        cols.sort()
+        lap_w = None
+        if need.lap and self.spec.lap:
+            # two different Laplacians requested from one evaluation: not one stream
+            return False
+        src = need if need.lap else self.spec
+        if src.lap:
+            wmap = dict(zip(src.dcols, src.lap_w))
+            lap_w = [wmap.get(c, 0.0) for c in cols]
+        if len(cols) > 3:
+            return False
+        new = JetSpec(cols, lap_w)
+        u, du, lap = self.engine.jet(self.x, new)
+        self.spec, self.du, self.lap = new, du, lap      # value stream: keep the first u
+        self._u2 = u
+        self.hints[self.hint_key] = new
+        return True
+
+    # streams reshaped back to the batch shape of the points
+    def value(self):
+        return self.u.reshape(*self.batch_shape, self.engine.d_out)
+
+    def first(self, out_cols, in_col):
+        k = self.spec.dcols.index(in_col)
+        return self.du[:, out_cols, k].reshape(*self.batch_shape, len(out_cols))
+
+    def second(self, out_cols):
+        return self.lap[:, out_cols].reshape(*self.batch_shape, len(out_cols))
+
+    def plain(self):
+        """the same output through torch ops with a graph to the coordinate leaves."""
+        if self._plain is None:
+            self._plain = self.autograd_fn()
+        return self._plain
+
+
+class JetTensor(torch.Tensor):
+    """A tensor of model outputs that remembers its JetEvaluation and output columns."""
+
+    @staticmethod
+    def wrap(t, ev, cols):
+        out = t.as_subclass(JetTensor)
+        out._jet, out._cols = ev, list(cols)
+        return out
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = {} if kwargs is None else kwargs
+        with torch._C.DisableTorchFunctionSubclass():
+            out = func(*args, **kwargs)
+        if func is torch.Tensor.__getitem__ and len(args) == 2 and isinstance(args[0], JetTensor):
+            cols = _column_selection(args[0], args[1])
+            if cols is not None and isinstance(out, torch.Tensor):
+                return JetTensor.wrap(out, args[0]._jet, cols)
+        elif func in (torch.Tensor.narrow, torch.narrow) and isinstance(args[0], JetTensor):
+            a = list(args) + [kwargs[k] for k in ("dim", "start", "length") if k in kwargs]
+            if len(a) == 4:
+                src, dim, start, length = a
+                if dim in (-1, src.dim() - 1) and isinstance(start, int):
+                    return JetTensor.wrap(out, src._jet, src._cols[start:start + length])
+        return out
+
+
+def _column_selection(src, idx):
+    """columns kept by ``src[idx]`` if idx only slices the last axis, else None."""
+    if not hasattr(src, "_cols"):
+        return None
+    if not isinstance(idx, tuple):
+        if idx is Ellipsis or (isinstance(idx, slice) and idx == slice(None) and src.dim() > 1):
+            return list(src._cols)
+        return None
+    idx = list(idx)
+    if len(idx) == 0:
+        return None
+    last = idx[-1]
+    lead = idx[:-1]
+    if any(v is Ellipsis for v in lead):
+        if len(lead) != 1:
+            return None
+    elif len(idx) != src.dim():
+        return None
+    if not all(v is Ellipsis or (isinstance(v, slice) and v == slice(None)) for v in lead):
+        return None
+    if isinstance(last, slice):
+        return src._cols[last]
+    if isinstance(last, int):
+        return [src._cols[last]]
+    if isinstance(last, (list, tuple)) and all(isinstance(v, int) for v in last):
+        return [src._cols[v] for v in last]
+    return None
+
+
+def jet_of(t):
+    """(evaluation, columns) if ``t`` is a live JetTensor, else (None, None)."""
+    if isinstance(t, JetTensor) and getattr(t, "_jet", None) is not None:
+        return t._jet, t._cols
+    return None, None
+
+
+def plain_of(t):
+    """tensor with a torch.autograd graph to the coordinate leaves (generic operator path)."""
+    ev, cols = jet_of(t)
+    if ev is None:
+        return t
+    full = ev.plain()
+    if cols == list(range(full.shape[-1])) and t.dim() == full.dim():
+        return full
+    sel = full[..., cols]
+    return sel if t.dim() == full.dim() else sel.squeeze(-1)

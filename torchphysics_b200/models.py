@@ -1,0 +1,244 @@
+"""Models with the reference's interface (``models/model.py``, ``models/fcn.py``,
+``models/activation_fn.py``, ``models/parameter.py``).
+
+``FCN`` keeps the reference's ``nn.Sequential`` parameter layout
+(``sequential.{0,2,4,...}.{weight,bias}``, Xavier-normal gain 5/3, output gain 1 --
+reference ``fcn.py:9-29``) so ``state_dict``s interchange.  Its forward is the native jet
+engine (``engine.py``) and nothing else: CPU tensors and networks without a kernel raise.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib, jets
+from .engine import FcnEngine, JetSpec
+from .spaces import Points, Space
+from .userfn import UserFunction
+
+
+class Sinus(nn.Module):
+    """sin activation (reference ``activation_fn.py:76-85``)."""
+
+    def forward(self, input):
+        return torch.sin(input)
+
+
+class AdaptiveActivationFunction(nn.Module):
+    """activation_fn(scaling * a * x) with learnable a (reference ``activation_fn.py:5-38``)."""
+
+    def __init__(self, activation_fn, inital_a=1.0, scaling=1.0):
+        super().__init__()
+        self.activation_fn = activation_fn
+        self.a = nn.Parameter(torch.tensor(inital_a))
+        self.scaling = scaling
+
+    def forward(self, x):
+        return self.activation_fn(self.scaling * self.a * x)
+
+
+class Parameter(Points):
+    """Learnable parameter of an inverse problem (reference ``parameter.py:6-32``)."""
+
+    def __init__(self, init, space, **kwargs):
+        init = torch.as_tensor(init).float().reshape(1, -1)
+        super().__init__(nn.Parameter(init), space, **kwargs)
+
+
+class Model(nn.Module):
+    def __init__(self, input_space, output_space):
+        super().__init__()
+        self.input_space = input_space
+        self.output_space = output_space
+
+    def _fix_points_order(self, points):
+        if points.space != self.input_space:
+            if points.space.keys() != self.input_space.keys():
+                raise ValueError(f"Points are in {points.space} but should lie in {self.input_space}.")
+            leaves = getattr(points, "_coord_leaves", None)
+            points = points[..., list(self.input_space.keys())]
+            if leaves is not None:
+                points._coord_leaves = leaves
+        return points
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path))
+
+
+def _fc_layers(hidden, input_dim, output_dim, activations, xavier_gains):
+    if not isinstance(activations, (list, tuple)):
+        activations = len(hidden) * [activations]
+    if not isinstance(xavier_gains, (list, tuple)):
+        xavier_gains = len(hidden) * [xavier_gains]
+    widths = [input_dim] + list(hidden)
+    layers = []
+    for i in range(len(hidden)):
+        lin = nn.Linear(widths[i], widths[i + 1])
+        nn.init.xavier_normal_(lin.weight, gain=xavier_gains[i])
+        layers += [lin, activations[i]]
+    out = nn.Linear(widths[-1], output_dim)
+    nn.init.xavier_normal_(out.weight, gain=1)
+    layers.append(out)
+    return layers
+
+
+def _activation_kind(mods):
+    kinds = set()
+    for m in mods:
+        if isinstance(m, nn.Tanh):
+            kinds.add("tanh")
+        elif isinstance(m, Sinus) or type(m).__name__ == "Sinus":
+            kinds.add("sin")
+        else:
+            return None
+    return kinds.pop() if len(kinds) == 1 else None
+
+
+def strict_native():
+    """Default: a network the kernels do not cover raises.  TPX_ALLOW_TORCH=1 lets such a
+    network be evaluated by torch (with a TpxFallbackWarning) -- never silently."""
+    return os.environ.get("TPX_ALLOW_TORCH", "0") != "1"
+
+
+class _NativeFcnMixin:
+    """Shared by FCN and the DeepONet trunk: route CUDA evaluations through the engine."""
+
+    def _native_engine(self):
+        eng = getattr(self, "_engine", None)
+        if eng is None:
+            seq = self.sequential
+            lins = [m for m in seq if isinstance(m, nn.Linear)]
+            acts = [m for m in seq if not isinstance(m, nn.Linear)]
+            ok = (len(seq) == 2 * len(lins) - 1 and len(lins) >= 2
+                  and all(isinstance(seq[2 * i], nn.Linear) for i in range(len(lins))))
+            kind = _activation_kind(acts) if ok else None
+            eng = False
+            if kind is not None:
+                try:
+                    eng = FcnEngine(lins, kind)
+                except _lib.TpxError as err:
+                    if err.code != _lib.TPX_E_UNSUPPORTED:
+                        raise
+                    self._engine_reason = str(err)
+            else:
+                self._engine_reason = "layer structure or activation has no native kernel"
+            object.__setattr__(self, "_engine", eng)
+        return eng
+
+    def _evaluate(self, points):
+        """points: Points in model input order -> tensor (..., d_out) (JetTensor if native)."""
+        x = points.as_tensor
+        if not x.is_cuda:
+            raise _lib.TpxError(_lib.TPX_E_ARG, "FCN evaluation runs on the sm_100a kernels only: the points "
+                                "must live on a CUDA device (there is no CPU path)")
+        eng = self._native_engine()
+        if eng is False:
+            if strict_native():
+                raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, self._engine_reason)
+            jets.warn_fallback(self._engine_reason)
+            return self.sequential(x)
+        batch_shape = x.shape[:-1]
+        x2d = x.detach().reshape(-1, x.shape[-1])
+        leaves = getattr(points, "_coord_leaves", None)
+        leaf_cols = {}
+        if leaves is not None:
+            sl = self.input_space.column_slices()
+            for name, leaf in leaves.items():
+                if name in sl:
+                    leaf_cols[id(leaf)] = (leaf, list(range(sl[name].start, sl[name].stop)))
+        hints = self.__dict__.setdefault("_jet_hints", {})
+        key = jets.current_scope()
+        spec = hints.get(key) if leaves is not None else None
+        if spec is None:
+            spec = JetSpec()
+        seq = self.sequential
+        ev = jets.JetEvaluation(eng, x2d, batch_shape, leaf_cols, hints, key, lambda: seq(x), spec)
+        return jets.JetTensor.wrap(ev.value(), ev, range(eng.d_out))
+
+
+class FCN(Model, _NativeFcnMixin):
+    """Fully connected network (reference ``fcn.py:32-87``)."""
+
+    def __init__(self, input_space, output_space, hidden=(20, 20, 20), activations=nn.Tanh(),
+                 xavier_gains=5 / 3, activation_fn_output=None):
+        super().__init__(input_space, output_space)
+        layers = _fc_layers(hidden, self.input_space.dim, self.output_space.dim, activations, xavier_gains)
+        if activation_fn_output is not None:
+            layers.append(activation_fn_output)
+        self.sequential = nn.Sequential(*layers)
+
+    def forward(self, points):
+        points = self._fix_points_order(points)
+        return Points(self._evaluate(points), self.output_space)
+
+
+class NormalizationLayer(Model):
+    """Trainable affine map of a domain's bounding box onto (-1,1)^d (reference ``model.py:57-92``)."""
+
+    def __init__(self, domain):
+        super().__init__(input_space=domain.space, output_space=domain.space)
+        self.normalize = nn.Linear(domain.space.dim, domain.space.dim)
+        box = domain.bounding_box()
+        lo, hi = box[::2], box[1::2]
+        width = torch.tensor([float(hi[i] - lo[i]) for i in range(domain.dim)])
+        centre = torch.tensor([float(hi[i] + lo[i]) / 2 for i in range(domain.dim)])
+        scale = 2.0 / width
+        with torch.no_grad():
+            self.normalize.weight.copy_(torch.diag(scale))
+            self.normalize.bias.copy_(-centre * scale)
+
+    def forward(self, points):
+        points = self._fix_points_order(points)
+        return Points(self.normalize(points), self.output_space)
+
+
+class Parallel(Model):
+    def __init__(self, *models):
+        input_space, output_space = Space({}), Space({})
+        for m in models:
+            assert output_space.keys().isdisjoint(m.output_space)
+            input_space = input_space * Space(m.input_space - input_space)
+            output_space = output_space * m.output_space
+        super().__init__(input_space, output_space)
+        self.models = nn.ModuleList(models)
+
+    def forward(self, points):
+        outs = []
+        for m in self.models:
+            sub = points[..., list(m.input_space.keys())]
+            leaves = getattr(points, "_coord_leaves", None)
+            if leaves is not None:
+                sub._coord_leaves = leaves
+            outs.append(m(sub))
+        return Points.joined(*outs)
+
+
+class Sequential(Model):
+    def __init__(self, *models):
+        super().__init__(models[0].input_space, models[-1].output_space)
+        self.models = nn.ModuleList(models)
+
+    def forward(self, points):
+        points = self._fix_points_order(points)
+        for m in self.models:
+            points = m(points)
+        return points
+
+
+class HardConstraint(Model):
+    def __init__(self, model, constraint):
+        super().__init__(model.input_space, model.output_space)
+        self.model = model
+        self.constraint = UserFunction(constraint)
+
+    def forward(self, points):
+        out = self.model(points)
+        res = self.constraint(points.join(out).coordinates)
+        if isinstance(res, torch.Tensor):
+            return Points(res, self.output_space)
+        if isinstance(res, (tuple, list)):
+            return Points(torch.column_stack(res), self.output_space)
+        raise AssertionError("Constraint function should return a tensor or a tuple of tensors.")

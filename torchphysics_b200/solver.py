@@ -1,0 +1,119 @@
+"""``Solver`` / ``OptimizerSetting`` with the reference's constructor and ``training_step``
+semantics (reference ``solver.py:9-136``), plus the minimal ``Trainer`` the reference gets
+from pytorch_lightning (not installed in this image): device placement, the step loop,
+``optimizer.step()`` and -- when launched with one process per GPU -- the single all-reduce
+of dL/dtheta per step (``parallel.FlatGradAllReduce``)."""
+import torch
+import torch.nn as nn
+
+from . import domains, parallel
+
+
+class OptimizerSetting:
+    def __init__(self, optimizer_class, lr, optimizer_args={}, scheduler_class=None, scheduler_args={},
+                 scheduler_frequency=1):
+        self.optimizer_class = optimizer_class
+        self.lr = lr
+        self.optimizer_args = optimizer_args
+        self.scheduler_class = scheduler_class
+        self.scheduler_args = scheduler_args
+        self.scheduler_frequency = scheduler_frequency
+
+
+class Solver(nn.Module):
+    def __init__(self, train_conditions, val_conditions=(), optimizer_setting=OptimizerSetting(torch.optim.Adam, 1e-3)):
+        super().__init__()
+        self.train_conditions = nn.ModuleList(train_conditions)
+        self.val_conditions = nn.ModuleList(val_conditions)
+        self.optimizer_setting = optimizer_setting
+        self.n_training_step = 0
+        self.logged = {}
+        self._device = torch.device("cpu")
+
+    @property
+    def device(self):
+        return self._device
+
+    def log(self, name, value, **kwargs):
+        self.logged[name] = value.detach() if isinstance(value, torch.Tensor) else value
+
+    def on_train_start(self):
+        for condition in list(self.train_conditions) + list(self.val_conditions):
+            condition._move_static_data(self.device)
+        self.n_training_step = 0
+
+    def training_step(self, batch=None, batch_idx=None):
+        loss = torch.zeros(1, requires_grad=True, device=self.device)
+        for condition in self.train_conditions:
+            cond_loss = condition(device=self.device, iteration=self.n_training_step)
+            self.log(f"train/{condition.name}", cond_loss)
+            loss = loss + condition.weight * cond_loss
+        self.log("train/loss", loss, prog_bar=True)
+        self.n_training_step += 1
+        return loss
+
+    def validation_step(self, batch=None, batch_idx=None):
+        for condition in self.val_conditions:
+            with torch.set_grad_enabled(condition.track_gradients is not False):
+                self.log(f"val/{condition.name}", condition(device=self.device))
+
+    def configure_optimizers(self):
+        setting = self.optimizer_setting
+        optimizer = setting.optimizer_class(self.parameters(), lr=setting.lr, **setting.optimizer_args)
+        if setting.scheduler_class is None:
+            return optimizer
+        scheduler = setting.scheduler_class(optimizer, **setting.scheduler_args)
+        return [optimizer], [{"scheduler": scheduler, "name": "learning_rate", "interval": "step",
+                              "frequency": setting.scheduler_frequency}]
+
+
+class Trainer:
+    """The slice of ``pl.Trainer`` the reference's examples use:
+    ``Trainer(devices=1, accelerator='gpu', max_steps=K).fit(solver)``."""
+
+    def __init__(self, max_steps=1000, accelerator="gpu", devices=1, device=None, **unused):
+        self.max_steps = max_steps
+        if device is None:
+            if accelerator in ("gpu", "cuda", "auto") and torch.cuda.is_available():
+                device = torch.device("cuda", torch.cuda.current_device())
+            else:
+                device = torch.device("cpu")
+        self.device = torch.device(device)
+        self.losses = []
+
+    def fit(self, solver):
+        rank, size = parallel.world()
+        if size > 1:
+            domains.set_rank_stream(rank)
+        solver.to(self.device)
+        solver._device = self.device
+        solver.trainer = self
+        configured = solver.configure_optimizers()
+        schedulers = []
+        if isinstance(configured, tuple) or isinstance(configured, list):
+            optimizer = configured[0][0]
+            schedulers = configured[1]
+        else:
+            optimizer = configured
+        solver.on_train_start()
+        params = [p for p in solver.parameters() if p.requires_grad]
+        reducer = parallel.FlatGradAllReduce(params, n_scalars=1)
+        closure_based = isinstance(optimizer, torch.optim.LBFGS)
+        for step in range(self.max_steps):
+            def closure():
+                optimizer.zero_grad(set_to_none=True)
+                loss = solver.training_step(None, step)
+                loss.backward()
+                (mean_loss,) = reducer([loss])
+                self._last = mean_loss if size > 1 else loss.detach()
+                return loss
+            if closure_based:
+                optimizer.step(closure)
+            else:
+                closure()
+                optimizer.step()
+            for sch in schedulers:
+                if (step + 1) % sch["frequency"] == 0:
+                    sch["scheduler"].step()
+            self.losses.append(self._last)
+        return solver
