@@ -43,8 +43,8 @@ def main():
         glap = torch.randn(N, d_out, device="cuda") if lapw else None
         tf = timeit(lambda: eng.forward_raw(packed, x, spec))
         tb = timeit(lambda: eng.backward_raw(packed, x, spec, gu, gdu, glap))
-        print(f"{name}: N={N} fwd {tf:.3f} ms ({N/tf/1e3:.3e} pts/s)  bwd {tb:.3f} ms ({N/tb/1e3:.3e} pts/s)  "
-              f"fwd+bwd {N/(tf+tb)/1e3:.3e} pts/s", flush=True)
+        print(f"{name}: N={N} fwd {tf:.3f} ms ({N/tf*1e3:.3e} pts/s)  bwd {tb:.3f} ms ({N/tb*1e3:.3e} pts/s)  "
+              f"fwd+bwd {N/(tf+tb)*1e3:.3e} pts/s", flush=True)
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "fcn_kernels.cuh"
+#include "tc_kernels.h"
 #include "tpx_internal.h"
 
 namespace tpx {
@@ -150,6 +151,9 @@ __global__ void unpack_kernel(Layout lay, UnpackArgs ua, const double* __restric
   }
 }
 
+// the packed buffer is [FP32-kernel image | tensor-core image]; the second starts 1 KB aligned
+static size_t tc_image_offset(const Layout& lay) { return (lay.total() + 255) / 256 * 256; }
+
 static void fill_dims(const tpx_fcn_desc* net, int* in_w, int* out_w) {
   for (int l = 0; l <= net->n_hidden; ++l) {
     in_w[l] = (l == 0) ? net->d_in : net->widths[l - 1];
@@ -180,13 +184,15 @@ extern "C" {
 
 int tpx_version(void) { return TPX_VERSION; }
 const char* tpx_last_error(void) { return g_err; }
+// development hook (not in tpx.h): device buffer that receives phase timestamps of one tile
+void tpx_debug_set_timestamps(long long* device_buffer) { tpx::g_tc_debug = device_buffer; }
 
 int tpx_fcn_packed_floats(const tpx_fcn_desc* net, size_t* n_floats) {
   Layout lay;
   int rc = make_layout(net, &lay);
   if (rc) return rc;
   if (!n_floats) return fail(TPX_E_ARG, "n_floats is NULL");
-  *n_floats = lay.total();
+  *n_floats = tc_image_offset(lay) + (tc_net_supported(net) ? tc_packed_floats(net) : 0);
   return 0;
 }
 
@@ -208,6 +214,9 @@ int tpx_fcn_pack(const tpx_fcn_desc* net, const void* const* params_host, float*
   if (blocks > 1184) blocks = 1184;
   pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(lay, pa, packed);
   if (cudaGetLastError() != cudaSuccess) return cuda_fail("pack_kernel");
+  if (tc_net_supported(net)) {
+    if (tc_pack(net, params_host, packed + tc_image_offset(lay), (cudaStream_t)stream)) return cuda_fail("tc_pack");
+  }
   return 0;
 }
 
@@ -236,6 +245,11 @@ int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   if (jet->lap && !lap) return fail(TPX_E_ARG, "lap is NULL but lap requested");
   a.packed = packed; a.x = x; a.n = n; a.u = u; a.du = du; a.lapo = lap;
   a.stream = (cudaStream_t)stream;
+  if (tc_supported(net, jet->nd, a.lap)) {
+    rc = tc_forward(net, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, u, du, lap, a.sm_count, a.stream);
+    if (rc) return cuda_fail("tc_fwd_kernel");
+    return 0;
+  }
   switch (a.lay.HP) {
     case 32: rc = launch_fwd<32>(a); break;
     case 64: rc = launch_fwd<64>(a); break;

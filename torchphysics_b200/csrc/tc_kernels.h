@@ -1,0 +1,18 @@
+// Host-side interface of the tensor-core (tcgen05) jet kernels, used by api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/tpx.h"
+#include "fcn_common.cuh"
+
+namespace tpx {
+bool tc_net_supported(const tpx_fcn_desc* net);                 // network shape has a tensor-core kernel
+bool tc_supported(const tpx_fcn_desc* net, int nd, int lap);    // ... and so has this jet
+size_t tc_packed_floats(const tpx_fcn_desc* net);
+int tc_pack(const tpx_fcn_desc* net, const void* const* params_host, float* img, cudaStream_t stream);
+int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float* img, const float* x, int64_t n,
+               float* u, float* du, float* lapo, int sm_count, cudaStream_t stream);
+extern long long* g_tc_debug;   // development: device buffer of >= 512 int64 timestamps, or NULL
+}  // namespace tpx
