@@ -173,6 +173,9 @@ def test_linearity_of_reverse_at_scale():
     a = eng.backward_raw(packed, x[: N // 3].contiguous(), spec, None, None, g[: N // 3].contiguous())
     b = eng.backward_raw(packed, x[N // 3:].contiguous(), spec, None, None, g[N // 3:].contiguous())
     twice = eng.backward_raw(packed, x, spec, None, None, 2 * g)
+    # random-sign adjoints are the worst case for a float32 sum over 2^20 points: the result is ~sqrt(N) while the
+    # summed magnitudes are ~N, so 2e-4 of the result is ~2e-7 of what was actually added up (the tensor-core
+    # path accumulates dW in fp32 TMEM accumulators per CTA before the float64 reduction over CTAs)
     den = full.abs().max()
-    assert ((a + b - full).abs().max() / den) < 1e-6
+    assert ((a + b - full).abs().max() / den) < 2e-4
     assert ((twice - 2 * full).abs().max() / den) < 1e-6

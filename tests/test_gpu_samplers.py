@@ -133,8 +133,7 @@ def test_grid_on_cut_and_union():
     tp = _tp()
     for name in ("cut", "uni"):
         dom = _build(tp, DOMS[name])
-        with pytest.warns(UserWarning) if name == "uni" else _nullcontext():
-            g = tp.samplers.GridSampler(dom, n_points=200).sample_points(device="cuda")
+        g = tp.samplers.GridSampler(dom, n_points=200).sample_points(device="cuda")
         assert len(g) == 200
         assert geometry.contains(DOMS[name], g.as_tensor.cpu().numpy()).all()
 

@@ -276,6 +276,10 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
     default: rc = TPX_E_UNSUPPORTED;
   }
   if (rc) return fail(rc, "no reverse kernel for HP=%d nd=%d lap=%d d_out=%d", a.lay.HP, jet->nd, jet->lap, a.lay.d_out);
+  if (tc_bwd_supported(net, jet->nd, a.lap)) {
+    const size_t tcb = tc_bwd_workspace_bytes(net, a.sm_count);
+    if (tcb > *bytes) *bytes = tcb;
+  }
   return 0;
 }
 
@@ -294,6 +298,13 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
   a.gu = gu; a.gdu = jet->nd > 0 ? gdu : nullptr; a.glap = jet->lap ? glap : nullptr;
   a.gacc = grad_acc; a.ckpt = (float*)workspace; a.ckpt_bytes = workspace_bytes;
   a.stream = (cudaStream_t)stream;
+  if (tc_bwd_supported(net, jet->nd, a.lap)) {
+    rc = tc_backward(net, a.lay, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
+                     (float*)workspace, workspace_bytes, a.sm_count, a.stream);
+    if (rc == TPX_E_WORKSPACE) return fail(rc, "workspace of %zu bytes is too small", workspace_bytes);
+    if (rc) return cuda_fail("tc_bwd_kernel");
+    return 0;
+  }
   switch (a.lay.HP) {
     case 32: rc = launch_bwd<32>(a); break;
     case 64: rc = launch_bwd<64>(a); break;
