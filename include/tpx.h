@@ -97,6 +97,19 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
                          const float* glap, double* grad_acc, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Activation-jet checkpoints.  When a forward evaluation is followed by loss.backward() on the same points
+ * (the normal training step: condition.py:293-304 then solver.py:100-109), the forward kernel can save the
+ * per-layer jets (8 KB per point for a 4x64 net; HBM is 180 GB) and the reverse kernel reads them instead of
+ * re-running the forward sweep.  *bytes = 0 when this network / jet has no saving kernel. */
+int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_t n, size_t* bytes);
+int tpx_fcn_jet_forward_save(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                             const float* x, int64_t n, float* u, float* du, float* lap, void* saved,
+                             size_t saved_bytes, void* stream);
+int tpx_fcn_jet_backward_saved(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                               const float* x, int64_t n, const float* gu, const float* gdu,
+                               const float* glap, double* grad_acc, const void* saved, size_t saved_bytes,
+                               void* stream);
+
 /* float64 packed accumulator -> per-parameter float32 gradients (layout of nn.Linear).
  * grads_host: HOST array of 2*(n_hidden+1) device pointers (entries may be NULL).
  * accumulate != 0 adds to the existing gradient (PyTorch .grad semantics). */

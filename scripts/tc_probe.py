@@ -37,11 +37,48 @@ def main():
         print(f"fwd N={N}: {tf:.3f} ms  {N / tf * 1e3:.3e} pts/s", flush=True)
     if "b" in what:
         tb = timeit(lambda: eng.backward_raw(packed, x, spec, None, None, glap))
-        print(f"bwd N={N}: {tb:.3f} ms  {N / tb * 1e3:.3e} pts/s", flush=True)
+        print(f"bwd (recompute) N={N}: {tb:.3f} ms  {N / tb * 1e3:.3e} pts/s", flush=True)
+    if "s" in what:
+        nbytes = eng.saved_bytes(spec, N)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        tf = timeit(lambda: eng.forward_raw(packed, x, spec, saved))
+        tb = timeit(lambda: eng.backward_raw(packed, x, spec, None, None, glap, saved))
+        print(f"saved mode N={N} ({nbytes / 2**30:.2f} GiB): fwd {tf:.3f} ms  bwd {tb:.3f} ms  "
+              f"fwd+bwd {N / (tf + tb) * 1e3:.3e} pts/s", flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 2 and sys.argv[2].startswith("dbg")):
     main()
+
+
+def debug_bwd(N=1 << 18):
+    import ctypes
+    from torchphysics_b200 import _lib
+    torch.manual_seed(0)
+    seq = ref_autograd.build_fcn(2, 1, (64,) * 4).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    spec = JetSpec((0, 1), (1.0, 1.0))
+    x = torch.rand(N, 2, device="cuda")
+    packed = eng.packed(eng.params())
+    glap = torch.randn(N, 1, device="cuda")
+    saved = torch.empty(eng.saved_bytes(spec, N), dtype=torch.uint8, device="cuda")
+    eng.forward_raw(packed, x, spec, saved)
+    buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
+    lib = _lib.lib()
+    lib.tpx_debug_set_timestamps(ctypes.c_void_p(buf.data_ptr()))
+    eng.backward_raw(packed, x, spec, None, None, glap, saved)
+    torch.cuda.synchronize()
+    lib.tpx_debug_set_timestamps(ctypes.c_void_p(0))
+    t = buf.cpu().numpy()
+    t0 = t[t > 0].min()
+    names = ["enter", "d_ready", "c0:A", "c0:B", "c0:putA", "c0:f", "c0:Zt", "c0:At", "c1:A", "c1:B", "c1:putA", "c1:f", "c1:Zt", "c1:At", "done"]
+    for l in (3, 2, 1, 0):
+        for q in range(4):
+            row = t[(q * 8 + l) * 16:(q * 8 + l) * 16 + 15]
+            print(f"l{l} q{q}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
+    for g in range(3):
+        r = t[1024 + g * 4:1024 + g * 4 + 3]
+        print(f"mma phase {g}: a_ready={int(r[0]-t0)} w_ready={int(r[1]-t0)} issued={int(r[2]-t0)}")
 
 
 def debug_timestamps(N=1 << 18):
@@ -72,3 +109,5 @@ def debug_timestamps(N=1 << 18):
 
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbg":
     debug_timestamps()
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbgb":
+    debug_bwd()

@@ -31,6 +31,9 @@ EXPORTS = (
     "tpx_fcn_backward_workspace_bytes",
     "tpx_fcn_jet_backward",
     "tpx_fcn_unpack_grads",
+    "tpx_fcn_saved_bytes",
+    "tpx_fcn_jet_forward_save",
+    "tpx_fcn_jet_backward_saved",
     "tpx_region_contains",
     "tpx_sample_uniform",
     "tpx_sample_reject_workspace_bytes",

@@ -232,8 +232,8 @@ static int fill_launch(const tpx_fcn_desc* net, const tpx_jet_desc* jet, LaunchA
   return 0;
 }
 
-int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
-                        const float* x, int64_t n, float* u, float* du, float* lap, void* stream) {
+static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                       const float* x, int64_t n, float* u, float* du, float* lap, float* saved, void* stream) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
   int rc = fill_launch(net, jet, &a);
@@ -246,7 +246,7 @@ int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   a.packed = packed; a.x = x; a.n = n; a.u = u; a.du = du; a.lapo = lap;
   a.stream = (cudaStream_t)stream;
   if (tc_supported(net, jet->nd, a.lap)) {
-    rc = tc_forward(net, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, u, du, lap, a.sm_count, a.stream);
+    rc = tc_forward(net, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, u, du, lap, saved, a.sm_count, a.stream);
     if (rc) return cuda_fail("tc_fwd_kernel");
     return 0;
   }
@@ -260,6 +260,34 @@ int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   if (rc == TPX_E_UNSUPPORTED) return fail(rc, "no forward kernel for HP=%d nd=%d lap=%d", a.lay.HP, jet->nd, jet->lap);
   if (rc) return cuda_fail("fcn_fwd_kernel");
   return 0;
+}
+
+int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                        const float* x, int64_t n, float* u, float* du, float* lap, void* stream) {
+  return jet_forward(net, jet, packed, x, n, u, du, lap, nullptr, stream);
+}
+
+int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_t n, size_t* bytes) {
+  Layout lay;
+  int rc = make_layout(net, &lay);
+  if (rc) return rc;
+  JetArgs ja;
+  rc = check_jet(net, jet, &ja);
+  if (rc) return rc;
+  if (!bytes || n < 0) return fail(TPX_E_ARG, "bad argument");
+  *bytes = tc_bwd_supported(net, jet->nd, jet->lap ? 1 : 0) ? tc_saved_bytes(net, n) : 0;
+  return 0;
+}
+
+int tpx_fcn_jet_forward_save(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                             const float* x, int64_t n, float* u, float* du, float* lap, void* saved,
+                             size_t saved_bytes, void* stream) {
+  size_t need = 0;
+  int rc = tpx_fcn_saved_bytes(net, jet, n, &need);
+  if (rc) return rc;
+  if (need == 0) return fail(TPX_E_UNSUPPORTED, "this network / jet has no checkpoint-saving forward kernel");
+  if (!saved || saved_bytes < need) return fail(TPX_E_WORKSPACE, "saved buffer of %zu bytes < %zu", saved_bytes, need);
+  return jet_forward(net, jet, packed, x, n, u, du, lap, (float*)saved, stream);
 }
 
 int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, size_t* bytes) {
@@ -283,10 +311,10 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
   return 0;
 }
 
-int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
-                         const float* x, int64_t n, const float* gu, const float* gdu,
-                         const float* glap, double* grad_acc, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                        const float* x, int64_t n, const float* gu, const float* gdu,
+                        const float* glap, double* grad_acc, void* workspace,
+                        size_t workspace_bytes, int saved, void* stream) {
   LaunchArgs a;
   memset(&a, 0, sizeof(a));
   int rc = fill_launch(net, jet, &a);
@@ -298,9 +326,10 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
   a.gu = gu; a.gdu = jet->nd > 0 ? gdu : nullptr; a.glap = jet->lap ? glap : nullptr;
   a.gacc = grad_acc; a.ckpt = (float*)workspace; a.ckpt_bytes = workspace_bytes;
   a.stream = (cudaStream_t)stream;
+  if (saved && !tc_bwd_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel that reads saved checkpoints");
   if (tc_bwd_supported(net, jet->nd, a.lap)) {
     rc = tc_backward(net, a.lay, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
-                     (float*)workspace, workspace_bytes, a.sm_count, a.stream);
+                     (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);
     if (rc == TPX_E_WORKSPACE) return fail(rc, "workspace of %zu bytes is too small", workspace_bytes);
     if (rc) return cuda_fail("tc_bwd_kernel");
     return 0;
@@ -316,6 +345,20 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
   if (rc == TPX_E_WORKSPACE) return fail(rc, "workspace of %zu bytes is too small", workspace_bytes);
   if (rc) return cuda_fail("fcn_bwd_kernel");
   return 0;
+}
+
+int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                         const float* x, int64_t n, const float* gu, const float* gdu,
+                         const float* glap, double* grad_acc, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return jet_backward(net, jet, packed, x, n, gu, gdu, glap, grad_acc, workspace, workspace_bytes, 0, stream);
+}
+
+int tpx_fcn_jet_backward_saved(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                               const float* x, int64_t n, const float* gu, const float* gdu,
+                               const float* glap, double* grad_acc, const void* saved, size_t saved_bytes,
+                               void* stream) {
+  return jet_backward(net, jet, packed, x, n, gu, gdu, glap, grad_acc, (void*)saved, saved_bytes, 1, stream);
 }
 
 int tpx_fcn_unpack_grads(const tpx_fcn_desc* net, const double* grad_acc, void* const* grads_host,

@@ -114,6 +114,7 @@ struct FwdArgs {
   const float* x;
   int64_t n;
   float *u, *du, *lap;
+  float* ckpt;      // optional: [tile][layer][8 arrays][64][32] activation-jet checkpoints for the reverse kernel
   long long* dbg;   // optional timestamps (development)
 };
 
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
       for (int l = 0; l < L; ++l) {
         const float* bias = sm + so.small + lay.bias(l);
         const bool last = (l == L - 1);
+        float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (8 * HP * TILE) : nullptr;
         const bool dbg_on = a.dbg && blockIdx.x == 0 && pair == blockIdx.x + gridDim.x && lane == 0 && half == 0 && slot == 0;
         if (dbg_on) a.dbg[(q * 8 + l) * 8 + 0] = clock64();
         if (l > 0) {
@@ -272,6 +274,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             for (int i = 0; i < CH; ++i) w[i] = tanh_fast(w[i]);
 #pragma unroll
             for (int i = 0; i < CH; ++i) ex_z[(j0 + c * CH + i) * TILE + lane] = w[i];
+            if (ckl) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) ckl[(j0 + c * CH + i) * TILE + lane] = w[i];
+            }
           }
         } else if (is_dk && LAP) {
           float* dst = ex_dz + (q - 1) * HP * TILE;
@@ -327,10 +333,18 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             const int jc = j0 + c * CH;
             float w[CH];
             own(jc, w);
+            if (ckl) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 0) * HP + jc + i) * TILE + lane] = w[i];
+            }
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const float t = ex_z[(jc + i) * TILE + lane];
               w[i] *= fmaf(-t, t, 1.0f);
+            }
+            if (ckl) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 1) * HP + jc + i) * TILE + lane] = w[i];
             }
             emit(jc, w);
           }
@@ -340,6 +354,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             const int jc = j0 + c * CH;
             float w[CH];
             own(jc, w);
+            if (ckl) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 0) * HP + jc + i) * TILE + lane] = w[i];
+            }
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
               const float t = ex_z[(jc + i) * TILE + lane];
@@ -351,6 +369,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
                 qq = fmaf(lapw[k] * dz, dz, qq);
               }
               w[i] = fmaf(-2.0f * t * s1, qq, s1 * w[i]);
+            }
+            if (ckl) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 1) * HP + jc + i) * TILE + lane] = w[i];
             }
             emit(jc, w);
           }
@@ -462,11 +484,12 @@ static int launch_tc_fwd(const FwdArgs& a, int sm_count, cudaStream_t stream) {
 }
 
 int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float* img, const float* x, int64_t n,
-               float* u, float* du, float* lapo, int sm_count, cudaStream_t stream) {
+               float* u, float* du, float* lapo, float* saved, int sm_count, cudaStream_t stream) {
   FwdArgs a;
   a.lay = TcLayout{net->n_hidden, net->d_in, net->d_out};
   a.jet = jet;
   a.img = img; a.x = x; a.n = n; a.u = u; a.du = du; a.lap = lapo;
+  a.ckpt = saved;
   a.dbg = g_tc_debug;
   switch (jet.nd * 2 + lap) {
     case 0: return launch_tc_fwd<0, 0>(a, sm_count, stream);

@@ -13,11 +13,12 @@ bool tc_supported(const tpx_fcn_desc* net, int nd, int lap);    // ... and so ha
 size_t tc_packed_floats(const tpx_fcn_desc* net);
 int tc_pack(const tpx_fcn_desc* net, const void* const* params_host, float* img, cudaStream_t stream);
 int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float* img, const float* x, int64_t n,
-               float* u, float* du, float* lapo, int sm_count, cudaStream_t stream);
+               float* u, float* du, float* lapo, float* saved, int sm_count, cudaStream_t stream);
 bool tc_bwd_supported(const tpx_fcn_desc* net, int nd, int lap);
 size_t tc_bwd_workspace_bytes(const tpx_fcn_desc* net, int sm_count);
 int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet, int lap, const float* img, const float* x,
                 int64_t n, const float* gu, const float* gdu, const float* glap, double* gacc, float* ckpt, size_t ckpt_bytes,
-                int sm_count, cudaStream_t stream);
+                int saved, int sm_count, cudaStream_t stream);
+size_t tc_saved_bytes(const tpx_fcn_desc* net, int64_t n);   // activation-jet checkpoints of n points
 extern long long* g_tc_debug;   // development: device buffer of >= 512 int64 timestamps, or NULL
 }  // namespace tpx

@@ -134,23 +134,43 @@ class FcnEngine:
         return ws
 
     # ---- raw kernels -----------------------------------------------------------------
-    def forward_raw(self, packed, x, spec):
+    def saved_bytes(self, spec, n):
+        """bytes of activation-jet checkpoints the forward can save for the reverse (0: not available)."""
+        nbytes = ctypes.c_size_t(0)
+        j = spec.c_struct()
+        _lib.check(_lib.lib().tpx_fcn_saved_bytes(ctypes.byref(self.desc), ctypes.byref(j), ctypes.c_int64(n),
+                                                  ctypes.byref(nbytes)))
+        return nbytes.value
+
+    def forward_raw(self, packed, x, spec, saved=None):
         n = x.shape[0]
         u = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device)
         du = torch.empty((n, self.d_out, spec.nd), dtype=torch.float32, device=x.device) if spec.nd else None
         lap = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device) if spec.lap else None
         j = spec.c_struct()
-        _lib.check(_lib.lib().tpx_fcn_jet_forward(
-            ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
-            _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.stream_ptr()))
+        if saved is None:
+            _lib.check(_lib.lib().tpx_fcn_jet_forward(
+                ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+                _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.stream_ptr()))
+        else:
+            _lib.check(_lib.lib().tpx_fcn_jet_forward_save(
+                ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+                _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.ptr(saved), ctypes.c_size_t(saved.numel()),
+                _lib.stream_ptr()))
         return u, du, lap
 
-    def backward_raw(self, packed, x, spec, gu, gdu, glap):
+    def backward_raw(self, packed, x, spec, gu, gdu, glap, saved=None):
         """returns the float64 packed gradient accumulator."""
         n = x.shape[0]
         gacc = torch.zeros(self.packed_floats, dtype=torch.float64, device=x.device)
-        ws = self.workspace(spec, x.device)
         j = spec.c_struct()
+        if saved is not None:
+            _lib.check(_lib.lib().tpx_fcn_jet_backward_saved(
+                ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+                _lib.ptr(gu), _lib.ptr(gdu), _lib.ptr(glap), _lib.ptr(gacc), _lib.ptr(saved),
+                ctypes.c_size_t(saved.numel()), _lib.stream_ptr()))
+            return gacc
+        ws = self.workspace(spec, x.device)
         _lib.check(_lib.lib().tpx_fcn_jet_backward(
             ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
             _lib.ptr(gu), _lib.ptr(gdu), _lib.ptr(glap), _lib.ptr(gacc), _lib.ptr(ws),
@@ -178,12 +198,27 @@ class FcnEngine:
         return _FcnJetFn.apply(self, x, spec, *params)
 
 
+def save_budget_bytes(device):
+    """how much HBM one evaluation may spend on activation-jet checkpoints (TPX_SAVE_GB overrides; 0 disables)."""
+    import os
+    env = os.environ.get("TPX_SAVE_GB")
+    if env is not None:
+        return int(float(env) * 2 ** 30)
+    free, _total = torch.cuda.mem_get_info(device)
+    return int(0.3 * free)
+
+
 class _FcnJetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, spec, *params):
         packed = engine.packed(params)
-        u, du, lap = engine.forward_raw(packed, x, spec)
-        ctx.engine, ctx.spec, ctx.x, ctx.packed = engine, spec, x, packed
+        saved = None
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params) and x.shape[0] > 0:
+            nbytes = engine.saved_bytes(spec, x.shape[0])
+            if 0 < nbytes <= save_budget_bytes(x.device):
+                saved = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        u, du, lap = engine.forward_raw(packed, x, spec, saved)
+        ctx.engine, ctx.spec, ctx.x, ctx.packed, ctx.saved = engine, spec, x, packed, saved
         ctx.params = params
         ctx.set_materialize_grads(False)
         outs = [u]
@@ -212,7 +247,8 @@ class _FcnJetFn(torch.autograd.Function):
             glap = None
         if gu is None and gdu is None and glap is None:
             return (None, None, None) + (None,) * len(needs)
-        gacc = engine.backward_raw(ctx.packed, ctx.x, spec, gu, gdu, glap)
+        gacc = engine.backward_raw(ctx.packed, ctx.x, spec, gu, gdu, glap, ctx.saved)
+        ctx.saved = None
         # reference parity: a parameter the loss does not depend on keeps grad None;
         # that is exactly the output bias when the value stream carries no adjoint.
         grads = engine.unpack(gacc, ctx.params, skip_last_bias=(gu is None))
