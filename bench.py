@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--points", type=int, default=1 << 22, help="collocation points per GPU per step")
+    ap.add_argument("--points", type=int, default=1 << 21, help="collocation points per GPU per step")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -176,16 +176,19 @@ def run_native(args):
     fs = [source(x) for x in xs]
     flat = torch.zeros(n_theta + 1, dtype=torch.float32, device=dev)
     launches = {"n": 0}
+    # activation-jet checkpoints: the forward kernel saves them (8 KB / point), the reverse kernel reads them
+    saved_bytes = eng.saved_bytes(spec, N)
+    saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev) if saved_bytes else None
 
     def step_resident(i):
         """forward jet + residual + loss + reverse + flat gradient (+ all-reduce)."""
         x, f = xs[i % n_batches], fs[i % n_batches]
         packed = eng.packed(params)
-        u, du, lap = eng.forward_raw(packed, x, spec)
+        u, du, lap = eng.forward_raw(packed, x, spec, saved)
         r = lap + f
         loss = torch.mean(r * r)
         glap = r * (2.0 / N)
-        gacc = eng.backward_raw(packed, x, spec, None, None, glap)
+        gacc = eng.backward_raw(packed, x, spec, None, None, glap, saved)
         grads = eng.unpack(gacc, params, skip_last_bias=True)
         off = 0
         for g in grads:
@@ -260,9 +263,10 @@ def run_native(args):
     packed = eng.packed(params)
     glap = torch.randn(N, 1, device=dev) / N
     def bwd_only(i):
-        eng.backward_raw(packed, xs[i % n_batches], spec, None, None, glap)
+        eng.backward_raw(packed, xs[i % n_batches], spec, None, None, glap, saved)
     def fwd_only(i):
-        eng.forward_raw(packed, xs[i % n_batches], spec)
+        eng.forward_raw(packed, xs[i % n_batches], spec, saved)
+    fwd_only(0)
     ms_bwd = timed(bwd_only, 10, 3)
     ms_fwd = timed(fwd_only, 10, 3)
 
@@ -275,6 +279,8 @@ def run_native(args):
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         achieved = N * 2 * F_FWD / (ms_bwd * 1e-3) / 1e12
+        kernel_name = "tc_bwd_kernel (tcgen05 reverse sweep: adjoint + dW products, saved checkpoints)" if saved is not None \
+            else "fcn_bwd_kernel (reverse sweep incl. forward recompute)"
         line = {
             "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -288,13 +294,16 @@ def run_native(args):
                     "h2d_bytes_per_step": N * D_IN * 4, "d2h_bytes_per_step": 4,
                     "path": "tp.conditions.PINNCondition.forward + loss.backward(), x from pinned host memory"},
             "gpu_launches": n_launch,
-            "roofline": {"bound": "tensor", "kernel": "fcn_bwd_kernel (reverse sweep incl. forward recompute)",
+            "roofline": {"bound": "tensor", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_flop_per_point": 2 * F_FWD, "ms_per_launch": ms_bwd,
                          "forward_kernel_ms": ms_fwd,
-                         "note": "fp32 CUDA-core kernel in this round; FLOP = GEMM FLOP of SURVEY 8(d) "
-                                 "(reverse = 2 x forward), recompute not counted"},
+                         "tf32_issue_factor": 3,
+                         "note": "FLOP = algorithmic GEMM FLOP of SURVEY 8(d) (reverse = 2 x forward); the kernel "
+                                 "issues 3 tf32 products per algorithmic product (fp32-accurate split) and tf32 runs at "
+                                 "half the bf16 rate (1.10 PFLOP/s measured with scripts/umma_probe2.cu), so frac = 1 "
+                                 "would need 6x the bf16 peak; the tensor-pipe share is in profiles/"},
             "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:

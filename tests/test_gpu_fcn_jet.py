@@ -179,3 +179,55 @@ def test_linearity_of_reverse_at_scale():
     den = full.abs().max()
     assert ((a + b - full).abs().max() / den) < 2e-4
     assert ((twice - 2 * full).abs().max() / den) < 1e-6
+
+
+@pytest.mark.parametrize("hidden,dcols,lap_w,d_out", [((64,) * 4, (0, 1), (1.0, 1.0), 1), ((40,) * 3, (0, 1), None, 2),
+                                                       ((20, 50, 30), (1,), (2.0,), 3)])
+def test_saved_checkpoints_equal_recompute(hidden, dcols, lap_w, d_out):
+    """tensor-core path: the reverse kernel fed with the checkpoints the forward kernel saved returns the same
+    gradient as the reverse kernel that recomputes the forward sweep, and both agree with the FP32 kernels."""
+    import os
+    import subprocess
+    import sys
+    from torchphysics_b200.engine import FcnEngine, JetSpec
+    torch.manual_seed(3)
+    seq = ref_autograd.build_fcn(2, d_out, hidden).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    spec = JetSpec(dcols, lap_w)
+    N = 5000                                   # not a multiple of the 32-point tile
+    x = torch.rand(N, 2, device="cuda")
+    packed = eng.packed(eng.params())
+    gu = torch.randn(N, d_out, device="cuda")
+    gdu = torch.randn(N, d_out, len(dcols), device="cuda")
+    glap = torch.randn(N, d_out, device="cuda") if lap_w else None
+    nbytes = eng.saved_bytes(spec, N)
+    assert nbytes == ((N + 31) // 32) * len(hidden) * 8 * 64 * 32 * 4
+    saved = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    u1, du1, lap1 = eng.forward_raw(packed, x, spec, saved)
+    u0, du0, lap0 = eng.forward_raw(packed, x, spec)
+    assert torch.equal(u0, u1) and torch.equal(du0, du1)
+    g_saved = eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
+    g_recomp = eng.backward_raw(packed, x, spec, gu, gdu, glap)
+    den = g_recomp.abs().max()
+    assert float((g_saved - g_recomp).abs().max() / den) < 2e-6
+    # the FP32 CUDA-core kernels (TPX_DISABLE_TC=1, separate process: the switch is read once per process)
+    code = (
+        "import sys, torch, torch.nn as nn; sys.path.insert(0, '.');"
+        "from oracle import ref_autograd; from torchphysics_b200.engine import FcnEngine, JetSpec;"
+        f"torch.manual_seed(3); seq = ref_autograd.build_fcn(2, {d_out}, {hidden!r}).cuda();"
+        "eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], 'tanh');"
+        f"spec = JetSpec({dcols!r}, {lap_w!r}); x = torch.rand({N}, 2, device='cuda');"
+        f"gu = torch.randn({N}, {d_out}, device='cuda'); gdu = torch.randn({N}, {d_out}, {len(dcols)}, device='cuda');"
+        + (f"glap = torch.randn({N}, {d_out}, device='cuda');" if lap_w else "glap = None;") +
+        "packed = eng.packed(eng.params()); g = eng.backward_raw(packed, x, spec, gu, gdu, glap);"
+        "torch.save(g.cpu(), sys.argv[1])"
+    )
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"tpx_fp32_{os.getpid()}.pt")
+    env = dict(os.environ, TPX_DISABLE_TC="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root, timeout=300)
+    g_fp32 = torch.load(out).cuda()
+    os.remove(out)
+    n32 = min(g_fp32.numel(), g_saved.numel())
+    # both packed buffers start with the FP32-kernel image (same indexing)
+    assert float((g_saved[:n32] - g_fp32[:n32]).abs().max() / den) < 5e-6
