@@ -213,7 +213,7 @@ class _FcnJetFn(torch.autograd.Function):
     def forward(ctx, engine, x, spec, *params):
         packed = engine.packed(params)
         saved = None
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params) and x.shape[0] > 0:
+        if any(ctx.needs_input_grad[3:]) and x.shape[0] > 0:     # a reverse sweep will follow
             nbytes = engine.saved_bytes(spec, x.shape[0])
             if 0 < nbytes <= save_budget_bytes(x.device):
                 saved = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
