@@ -71,14 +71,12 @@ def debug_bwd(N=1 << 18):
     lib.tpx_debug_set_timestamps(ctypes.c_void_p(0))
     t = buf.cpu().numpy()
     t0 = t[t > 0].min()
-    names = ["enter", "d_ready", "c0:A", "c0:B", "c0:putA", "c0:f", "c0:Zt", "c0:At", "c1:A", "c1:B", "c1:putA", "c1:f", "c1:Zt", "c1:At", "done"]
+    names = ["enter", "d_ready", "loaded", "computed", "A_free", "f_free", "stored", "signalled"]
     for l in (3, 2, 1, 0):
-        for q in range(4):
-            row = t[(q * 8 + l) * 16:(q * 8 + l) * 16 + 15]
-            print(f"l{l} q{q}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
-    for g in range(3):
-        r = t[1024 + g * 4:1024 + g * 4 + 3]
-        print(f"mma phase {g}: a_ready={int(r[0]-t0)} w_ready={int(r[1]-t0)} issued={int(r[2]-t0)}")
+        for s in range(2):
+            for q in range(4):
+                row = t[((s * 4 + q) * 8 + l) * 8:((s * 4 + q) * 8 + l) * 8 + 8]
+                print(f"l{l} s{s} q{q}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
 
 
 def debug_timestamps(N=1 << 18):

@@ -330,9 +330,7 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   if (tc_bwd_supported(net, jet->nd, a.lap)) {
     rc = tc_backward(net, a.lay, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
                      (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);
-    if (rc == TPX_E_WORKSPACE) return fail(rc, "workspace of %zu bytes is too small", workspace_bytes);
-    if (rc) return cuda_fail("tc_bwd_kernel");
-    return 0;
+    return rc;                       // the launcher recorded the message
   }
   switch (a.lay.HP) {
     case 32: rc = launch_bwd<32>(a); break;

@@ -592,15 +592,19 @@ size_t tc_saved_bytes(const tpx_fcn_desc* net, int64_t n) {
 template <int ND, int LAP, bool RECOMP>
 static int launch_tc_bwd(const BwdArgs& a, int sm_count, size_t ws_bytes, cudaStream_t stream) {
   const size_t smem = (size_t)bwd_smem(a.lay).total * sizeof(float) + 1024;
-  if (smem > 227 * 1024) return TPX_E_UNSUPPORTED;
+  if (smem > 227 * 1024) return fail(TPX_E_UNSUPPORTED, "tc_bwd_kernel needs %zu bytes of shared memory", smem);
   const int64_t ntiles = (a.n + TILE - 1) / TILE;
   const int64_t grid = sm_count < ntiles ? sm_count : ntiles;
   if (grid < 1) return 0;
   const int64_t units = RECOMP ? grid : ntiles;
-  if (ws_bytes < (size_t)units * ckpt_floats_per_cta(a.lay.L) * sizeof(float)) return TPX_E_WORKSPACE;
-  if (cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TPX_E_CUDA;
+  if (ws_bytes < (size_t)units * ckpt_floats_per_cta(a.lay.L) * sizeof(float))
+    return fail(TPX_E_WORKSPACE, "checkpoint buffer of %zu bytes is too small (%zu needed)", ws_bytes, (size_t)units * ckpt_floats_per_cta(a.lay.L) * sizeof(float));
+  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel: shared memory attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
   tc_bwd_kernel<ND, LAP, RECOMP><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : TPX_E_CUDA;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel launch (%lld CTAs x %d threads, %zu bytes smem): %s", (long long)grid, B_THREADS, smem, cudaGetErrorString(e));
+  return 0;
 }
 
 int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet, int lap, const float* img, const float* x,
