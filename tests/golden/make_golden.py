@@ -161,20 +161,23 @@ def deep_ritz(hidden, n, name):
 
 
 # ---------------------------------------------------------------------------- config 4
-def deeponet(n_fn, n_pts, p, name):
+def deeponet(n_fn, n_pts, p, name, trunk_hidden=(32, 32), branch_hidden=(24, 24), n_sensors=10):
+    """physics-informed DeepONet for u'' + f = 0 (reference deeponet_condition.py:52-151,
+    deeponet.py:71-110, trunknets.py:145-154, branchnets.py:188-194)."""
     torch.manual_seed(8)
     T, U, Fs, K = tp.spaces.R1("t"), tp.spaces.R1("u"), tp.spaces.R1("f"), tp.spaces.R1("k")
-    trunk = tp.models.FCTrunkNet(T, hidden=(32, 32))
-    branch = tp.models.FCBranchNet(tp.spaces.FunctionSpace(T, Fs), hidden=(24, 24),
-                                   grid=tp.samplers.GridSampler(tp.domains.Interval(T, 0, 1), n_points=10).sample_points())
-    net = tp.models.DeepONet(trunk, branch, U, output_neurons=p)
     int_t = tp.domains.Interval(T, 0, 1)
+    fspace = tp.spaces.FunctionSpace(T, Fs)
+    grid = tp.samplers.GridSampler(int_t, n_points=n_sensors).sample_points()
+    trunk = tp.models.FCTrunkNet(T, hidden=trunk_hidden, default_trunk_input=grid)
+    branch = tp.models.FCBranchNet(fspace, hidden=branch_hidden, grid=grid)
+    net = tp.models.DeepONet(trunk, branch, U, output_neurons=p)
 
     def fn(k, t):
         return k * torch.sin(math.pi * t)
 
     param_sampler = tp.samplers.RandomUniformSampler(tp.domains.Interval(K, -1, 1), n_points=n_fn)
-    fset = tp.domains.CustomFunctionSet(tp.spaces.FunctionSpace(T, Fs), param_sampler, fn)
+    fset = tp.domains.CustomFunctionSet(fspace, param_sampler, fn)
     fsampler = tp.samplers.FunctionSamplerRandomUniform(n_fn, fset, function_creation_interval=1)
     torch.manual_seed(9)
     tsampler = tp.samplers.RandomUniformSampler(int_t, n_points=n_pts).make_static()
@@ -183,6 +186,7 @@ def deeponet(n_fn, n_pts, p, name):
 
     def residual(u, t, f):
         captured["u"] = u
+        captured["ut"] = tp.utils.grad(u, t)
         captured["lap"] = tp.utils.laplacian(u, t)
         captured["f"] = f
         return captured["lap"] + f
@@ -192,17 +196,16 @@ def deeponet(n_fn, n_pts, p, name):
     torch.manual_seed(10)
     loss = cond(device="cpu")
     loss.backward()
-    # branch input actually used in this call
-    binp = captured["f"]
-    trunk_params = [q.detach().numpy().copy() for q in trunk.parameters()]
-    branch_params = [q.detach().numpy().copy() for q in branch.parameters()]
-    save(name, t=tt, fvals=captured["f"], u=captured["u"], lap=captured["lap"], loss=loss,
-         trunk_params=trunk_params, branch_params=branch_params,
-         branch_in=net.branch.current_out.detach() if False else np.zeros(0),
+    k_used = fset.param_samples.as_tensor[fsampler.current_indices].clone()      # (F, 1) in sampled order
+    branch_in = fn(k_used.unsqueeze(1), grid.as_tensor.unsqueeze(0))            # (F, sensors, 1)
+    save(name, t=tt, k=k_used, sensors=grid.as_tensor, branch_in=branch_in, fvals=captured["f"], u=captured["u"],
+         ut=captured["ut"], lap=captured["lap"], loss=loss,
+         trunk_params=[q.detach().numpy().copy() for q in trunk.parameters()],
+         branch_params=[q.detach().numpy().copy() for q in branch.parameters()],
          branch_out=net.branch.current_out.detach(),
          trunk_dtheta=[None if q.grad is None else q.grad.numpy().copy() for q in trunk.parameters()],
          branch_dtheta=[None if q.grad is None else q.grad.numpy().copy() for q in branch.parameters()],
-         p=np.array(p))
+         p=np.array(p), trunk_hidden=np.array(trunk_hidden), branch_hidden=np.array(branch_hidden))
 
 
 # ---------------------------------------------------------------------------- domains
@@ -252,4 +255,6 @@ if __name__ == "__main__":
     heat((48, 48, 48), 193, "heat_3x48")
     navier_stokes((32, 32, 32), 130, "ns_3x32")
     deep_ritz((40, 40, 40, 40), 150, "ritz_4x40")
+    deeponet(6, 40, 16, "deeponet_2x32")
+    deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50)
     domains()

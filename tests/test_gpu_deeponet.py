@@ -1,0 +1,66 @@
+"""SURVEY 8(a) rows a12/a13 on the GPU: PIDeepONetCondition through the native trunk jets
+(value / d_t / Laplacian streams of the trunk, one GEMM per stream against the branch
+coefficients, one native reverse launch) against the golden outputs of the real reference.
+Tolerance 1e-5 max-norm relative (BASELINE.json)."""
+import pytest
+import torch
+
+from tests.golden_io import load, relerr
+from tests.test_host_deeponet import build_deeponet, check_deeponet_step
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("name", ["deeponet_2x32", "deeponet_4x64"])
+def test_pideeponet_condition_matches_reference(name):
+    import torchphysics_b200 as tp
+    G = load(name)
+    net, trunk, branch, fsampler, tsampler = build_deeponet(tp, G, device="cuda")
+    check_deeponet_step(tp, G, net, trunk, branch, fsampler, tsampler, "cuda", TOL)
+    from torchphysics_b200.engine import FcnEngine
+    assert isinstance(trunk._native_engine(), FcnEngine)        # the kernels ran, not a torch fallback
+
+
+def test_deeponet_forward_shapes_and_fixed_branch():
+    """reference tests/tests_models/test_deep_o_net.py:113-154 (shapes), on the native trunk."""
+    import torchphysics_b200 as tp
+    T = tp.spaces.R1("t")
+    fspace = tp.spaces.FunctionSpace(T, tp.spaces.R1("f"))
+    grid = torch.rand((1, 100, 1))
+    for out_space, width in ((tp.spaces.R1("u"), 1), (tp.spaces.R2("u"), 2)):
+        trunk = tp.models.FCTrunkNet(T, default_trunk_input=grid)
+        branch = tp.models.FCBranchNet(fspace, grid=grid)
+        net = tp.models.DeepONet(trunk, branch, output_space=out_space, output_neurons=20).cuda()
+        pts = tp.spaces.Points(torch.tensor([[[2.0], [0.0], [3.4], [2.9]]]).cuda(), T)
+        out = net(pts, lambda t: 20 * t, device="cuda")
+        assert "u" in out.space and out.as_tensor.shape == (1, 4, width)
+        # value equals the torch-op definition of the same modules
+        want = net._generic(pts)
+        assert relerr(out.as_tensor.detach().cpu().numpy(), want.detach().cpu().numpy()) < TOL
+        net.fix_branch_input(torch.sin, device="cuda")
+        assert net(pts).as_tensor.shape == (1, 4, width)
+        assert net().as_tensor.shape == (1, 100, width)            # default trunk input
+        assert trunk(pts).shape == (1, 4, width, 20)
+
+
+def test_deeponet_uncopied_trunk_input():
+    """trunk_input_copied=False: every function has its own trunk points (plain nn.Linear trunk)."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(3)
+    T, U = tp.spaces.R1("t"), tp.spaces.R1("u")
+    fspace = tp.spaces.FunctionSpace(T, tp.spaces.R1("f"))
+    grid = torch.rand((1, 12, 1))
+    trunk = tp.models.FCTrunkNet(T, default_trunk_input=grid, hidden=(16, 16), trunk_input_copied=False)
+    branch = tp.models.FCBranchNet(fspace, grid=grid, hidden=(8,))
+    net = tp.models.DeepONet(trunk, branch, U, output_neurons=8).cuda()
+    net.fix_branch_input(torch.rand(3, 12, 1).cuda())
+    pts = tp.spaces.Points(torch.rand(3, 7, 1).cuda(), T)
+    coords, pts = pts.track_coord_gradients()
+    out = net(pts).as_tensor
+    lap = tp.utils.laplacian(out, coords["t"])
+    gen = net._generic(pts)
+    g = torch.autograd.grad(gen.sum(), coords["t"], create_graph=True)[0]
+    lap_ref = torch.autograd.grad(g.sum(), coords["t"])[0]
+    assert relerr(out.detach().cpu().numpy(), gen.detach().cpu().numpy()) < TOL
+    assert relerr(lap.detach().cpu().numpy(), lap_ref.cpu().numpy()) < TOL

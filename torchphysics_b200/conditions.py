@@ -117,3 +117,84 @@ class PINNCondition(SingleModuleCondition):
         super().__init__(module, sampler, residual_fn, error_fn=SquaredError(), reduce_fn=torch.mean,
                          name=name, track_gradients=track_gradients, data_functions=data_functions,
                          parameter=parameter, weight=weight)
+
+
+class DeepONetSingleModuleCondition(Condition):
+    """reference ``deeponet_condition.py:9-108``: trunk points are sampled once and repeated for
+    every branch function, the branch functions are discretised on the branch grid, the
+    residual sees model output, trunk coordinates, parameters, data functions and (when it
+    names them) the branch functions evaluated at the trunk points."""
+
+    def __init__(self, deeponet_model, branch_function_sampler, trunk_points_sampler, residual_fn, error_fn,
+                 data_sampler=None, reduce_fn=torch.mean, name="singlemodulecondition", track_gradients=True,
+                 data_functions={}, parameter=None, weight=1.0):
+        super().__init__(name=name, weight=weight, track_gradients=track_gradients)
+        self.net = deeponet_model
+        self.branch_function_sampler = branch_function_sampler
+        self.data_sampler = data_sampler
+        self.parameter = _empty_parameter() if parameter is None else parameter
+        if isinstance(self.parameter, Parameter):
+            self.register_parameter(name + "_params", self.parameter.as_tensor)
+        self.trunk_points_sampler = trunk_points_sampler
+        self.residual_fn = UserFunction(residual_fn)
+        self.error_fn = error_fn
+        self.reduce_fn = reduce_fn
+        self.data_functions = self._setup_data_functions(data_functions, self.trunk_points_sampler)
+        fn_out = self.branch_function_sampler.function_set.function_space.output_space.variables
+        self.eval_function_set_for_residual = (len(fn_out & set(self.residual_fn.args)) > 0
+                                               or self.data_sampler is not None)
+        if self.trunk_points_sampler.is_adaptive:
+            self.last_unreduced_loss = None
+
+    def forward(self, device="cpu", iteration=None):
+        if self.trunk_points_sampler.is_adaptive:
+            trunk_points = self.trunk_points_sampler.sample_points(unreduced_loss=self.last_unreduced_loss,
+                                                                   device=device)
+            self.last_unreduced_loss = None
+        else:
+            trunk_points = self.trunk_points_sampler.sample_points(device=device)
+        # the F copies are a broadcast view: the trunk kernel evaluates the N points once
+        base = trunk_points.as_tensor
+        n_fn = self.branch_function_sampler.n_functions
+        trunk_points = Points(base.unsqueeze(0).expand(n_fn, *base.shape), trunk_points.space)
+        trunk_coordinates, trunk_points = trunk_points.track_coord_gradients()
+
+        branch_functions = self.branch_function_sampler.sample_functions(device)
+        if callable(branch_functions):
+            branch_function_input = branch_functions(self.net.branch.grid)
+        else:
+            branch_function_input = branch_functions
+
+        data = None
+        if self.eval_function_set_for_residual:
+            if self.data_sampler is not None:
+                data = self.data_sampler.sample_functions(device)
+                if callable(data):
+                    data = data(trunk_points)
+            elif callable(branch_functions):
+                data = branch_functions(trunk_points)
+            else:
+                data = branch_functions
+
+        with jets.scope(id(self)):
+            model_out = self.net(trunk_points, branch_function_input, device=device)
+            data_fn = {name: self.data_functions[name](trunk_coordinates) for name in self.data_functions}
+            input_dict = {**model_out.coordinates, **trunk_coordinates, **self.parameter.coordinates, **data_fn}
+            if data is not None:
+                input_dict = {**input_dict, **data.coordinates}
+            unreduced_loss = self.error_fn(self.residual_fn(input_dict))
+        if self.trunk_points_sampler.is_adaptive:
+            self.last_unreduced_loss = unreduced_loss
+        return self.reduce_fn(unreduced_loss)
+
+
+class PIDeepONetCondition(DeepONetSingleModuleCondition):
+    """mean over functions of the summed squared residual (reference ``deeponet_condition.py:110-151``)."""
+
+    def __init__(self, deeponet_model, branch_function_sampler, trunk_points_sampler, residual_fn,
+                 data_sampler=None, name="pi_deeponet_condition", track_gradients=True, data_functions={},
+                 parameter=None, weight=1.0):
+        super().__init__(deeponet_model, branch_function_sampler, trunk_points_sampler, residual_fn=residual_fn,
+                         data_sampler=data_sampler, error_fn=SquaredError(), reduce_fn=torch.mean, name=name,
+                         track_gradients=track_gradients, data_functions=data_functions, parameter=parameter,
+                         weight=weight)

@@ -660,3 +660,7 @@ class ProductDomain(Domain):
     def sample_grid(self, n=None, d=None, params=Points.empty(), device="cpu"):
         raise NotImplementedError("Grid sampling on a product domain is not implmented. Use a product "
                                   "sampler instead.")
+
+
+# function sets / function samplers live in the same namespaces as in the reference
+from .functionsets import FunctionSet, CustomFunctionSet, FunctionSetCollection  # noqa: E402,F401

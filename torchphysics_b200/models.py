@@ -68,7 +68,7 @@ class Model(nn.Module):
         self.load_state_dict(torch.load(path))
 
 
-def _fc_layers(hidden, input_dim, output_dim, activations, xavier_gains):
+def _fc_layers(hidden, input_dim, output_dim, activations, xavier_gains, linear_cls=nn.Linear):
     if not isinstance(activations, (list, tuple)):
         activations = len(hidden) * [activations]
     if not isinstance(xavier_gains, (list, tuple)):
@@ -76,10 +76,10 @@ def _fc_layers(hidden, input_dim, output_dim, activations, xavier_gains):
     widths = [input_dim] + list(hidden)
     layers = []
     for i in range(len(hidden)):
-        lin = nn.Linear(widths[i], widths[i + 1])
+        lin = linear_cls(widths[i], widths[i + 1])
         nn.init.xavier_normal_(lin.weight, gain=xavier_gains[i])
         layers += [lin, activations[i]]
-    out = nn.Linear(widths[-1], output_dim)
+    out = linear_cls(widths[-1], output_dim)
     nn.init.xavier_normal_(out.weight, gain=1)
     layers.append(out)
     return layers

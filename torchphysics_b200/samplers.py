@@ -330,3 +330,7 @@ class LHSSampler(PointSampler):
                                           ctypes.c_uint64(0), ctypes.c_int64(n), _lib.ptr(out), ctypes.c_int32(d),
                                           ctypes.c_int32(0), _lib.stream_ptr()))
         return Points(out.to(device), self.domain.space)
+
+
+# function sets / function samplers live in the same namespaces as in the reference
+from .functionsets import FunctionSampler, FunctionSamplerRandomUniform, FunctionSamplerOrdered, FunctionSamplerCoupled  # noqa: E402,F401
