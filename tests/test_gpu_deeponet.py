@@ -38,7 +38,7 @@ def test_deeponet_forward_shapes_and_fixed_branch():
         # value equals the torch-op definition of the same modules
         want = net._generic(pts)
         assert relerr(out.as_tensor.detach().cpu().numpy(), want.detach().cpu().numpy()) < TOL
-        net.fix_branch_input(torch.sin, device="cuda")
+        net.fix_branch_input(lambda t: torch.sin(t), device="cuda")
         assert net(pts).as_tensor.shape == (1, 4, width)
         assert net().as_tensor.shape == (1, 100, width)            # default trunk input
         assert trunk(pts).shape == (1, 4, width, 20)

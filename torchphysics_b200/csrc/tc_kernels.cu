@@ -89,12 +89,23 @@ __global__ void tc_pack_fill_kernel(TcLayout lay, TcPackArgs pa, float* __restri
 // ------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------
+// Activation step of one layer for a group of 4 warps (one per TMEM quadrant = stream) and 32 neurons:
+//   in      the OWNER warp of stream s reads its rows of D (tcgen05.ld, lane = point) and writes them to the
+//           group's exchange buffer  ex[s][p][neuron]  (row padded to 36 floats: 128-bit accesses, no conflicts)
+//   compute warp w takes neurons [8 w, 8 w + 8) of the group for ALL streams of its 32 points: tanh and the jet
+//           formulas are thread-local (no role divergence, every scheduler does a quarter of the tanh work),
+//           checkpoints go to HBM from here, results overwrite ex in place
+//   out     the owner reads its stream's 32 neurons back, splits hi / lo and writes the next A operand to TMEM
+constexpr int EXP = 36;                       // padded neuron extent of one (stream, point) row
+constexpr int EX_GROUP = 4 * TILE * EXP;      // floats of one group's exchange buffer
+constexpr int OC = 2;                         // output columns per reduction pass of the output layer
+
 struct FwdSmem {
   // offsets in floats from the 1024-byte aligned base
   int mats;      // (L-1) * 2 * 4096   W_hi, W_lo per hidden layer
   int small;     // copy of the small block
-  int ex;        // SLOTS * 3 * HP * TILE exchange buffers
-  int part;      // SLOTS * 4 * 8 * TILE partial output sums
+  int ex;        // SLOTS * HALVES exchange buffers
+  int part;      // SLOTS * SLOT_WARPS * 4 * OC * TILE partial output sums
   int total;
 };
 __host__ __device__ inline FwdSmem fwd_smem(const TcLayout& lay) {
@@ -102,8 +113,8 @@ __host__ __device__ inline FwdSmem fwd_smem(const TcLayout& lay) {
   s.mats = 0;
   s.small = (lay.L - 1) * 2 * 4096;
   s.ex = s.small + (int)lay.small();
-  s.part = s.ex + SLOTS * 3 * HP * TILE;
-  s.total = s.part + SLOTS * 4 * 8 * TILE;
+  s.part = s.ex + SLOTS * HALVES * EX_GROUP;
+  s.total = s.part + SLOTS * SLOT_WARPS * 4 * OC * TILE;
   return s;
 }
 
@@ -115,12 +126,12 @@ struct FwdArgs {
   int64_t n;
   float *u, *du, *lap;
   float* ckpt;      // optional: [tile][layer][8 arrays][64][32] activation-jet checkpoints for the reverse kernel
-  long long* dbg;   // optional timestamps (development)
 };
 
 template <int ND, int LAP>
 __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
   constexpr int S = 1 + ND + LAP;
+  constexpr int NDX = ND > 0 ? ND : 1;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_a[SLOTS], bar_d[SLOTS];
   __shared__ uint32_t tmem_slot;
@@ -168,8 +179,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           mbar_wait(&bar_a[s], ph[s]);
           ph[s] ^= 1;
           fence_after();
-          const bool dbg_on = a.dbg && blockIdx.x == 0 && pair == blockIdx.x + gridDim.x && s == 0;
-          if (dbg_on && lane == 0) a.dbg[256 + l * 4 + 0] = clock64();
           if (elect_one()) {
             const uint32_t tD = tmem + s * SLOT_COLS, tAh = tD + 64, tAl = tD + 128;
             const uint32_t wh = wbase + (uint32_t)((l - 1) * 2) * 16384u, wl = wh + 16384u;
@@ -185,231 +194,197 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             mma_commit(&bar_d[s]);
           }
           __syncwarp();
-          if (dbg_on && lane == 0) a.dbg[256 + l * 4 + 1] = clock64();
         }
       }
     }
   } else {
     // =========================== activation warps ===========================
-    // warp = slot * 8 + half * 4 + q : quadrant q (= stream q) of the slot's tile, neurons [NB half, NB half + NB)
-    const int slot = warp / SLOT_WARPS, half = (warp % SLOT_WARPS) >> 2, q = warp & 3;
-    const int j0 = half * NB;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // warp = slot * 8 + half * 4 + quad: TMEM quadrant quad (= stream quad) of the slot's tile; the group
+    // (slot, half) shares neurons [NB half, NB half + NB)
+    const int slot = warp / SLOT_WARPS, half = (warp % SLOT_WARPS) >> 2, quad = warp & 3;
+    const int j0 = half * NB;                 // first neuron of the group
+    const int jw = j0 + quad * 8;             // compute phase: neurons [jw, jw + 8), all streams
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t tD = tmem + slot * SLOT_COLS + lane_base, tAh = tD + 64, tAl = tD + 128;
-    float* ex_z = sm + so.ex + slot * 3 * HP * TILE;       // [j][p]   tanh(z) of the value stream
-    float* ex_dz = ex_z + HP * TILE;                       // [k][j][p] pre-activation of the derivative streams
+    float* ex = sm + so.ex + (slot * HALVES + half) * EX_GROUP;
+    float* ex_own = ex + (quad * TILE + lane) * EXP;            // owner view: stream quad, the group's 32 neurons
+    float* ex_cmp = ex + lane * EXP + quad * 8;                 // compute view of stream s: + s * TILE * EXP
+    float* part = sm + so.part + slot * (SLOT_WARPS * 4 * OC * TILE);
     const float* W0 = sm + so.small + lay.w0();
     const float* WL = sm + so.small + lay.wl();
     const float* bL = sm + so.small + lay.bl();
     const int barid = 1 + slot * HALVES + half;
+    const int slot_bar = 1 + SLOTS * HALVES + slot;
+    const bool owner = quad < S;              // this warp's TMEM rows carry a stream
     uint32_t ph_d = 0;
-    const bool is_val = (q == 0), is_dk = (q >= 1 && q <= ND), is_lap = (LAP && q == ND + 1), idle = (q >= S);
-    const int dcol = is_dk ? a.jet.dcol[q - 1] : 0;
-    float lapw[ND > 0 ? ND : 1];
+    float lapw[NDX];
+    int dcol[NDX];
 #pragma unroll
-    for (int k = 0; k < ND; ++k) lapw[k] = a.jet.lap_w[k];
+    for (int k = 0; k < NDX; ++k) {
+      lapw[k] = (k < ND) ? a.jet.lap_w[k] : 0.0f;
+      dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
+    }
+    if (!owner) {                              // rows of an unused quadrant: a zero A operand, written once
+      float zero[CH];
+#pragma unroll
+      for (int i = 0; i < CH; ++i) zero[i] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < NB / CH; ++c) {
+        tmem_st16(tAh + j0 + c * CH, zero);
+        tmem_st16(tAl + j0 + c * CH, zero);
+      }
+      tmem_wait_st();
+    }
 
     for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
       const int64_t tile = pair * SLOTS + slot;
       if (tile >= ntiles) continue;
       const int64_t gp = tile * TILE + lane;
       const bool valid = gp < a.n;
-      float outacc[8];
+      float xr[TPX_MAX_DIN];
 #pragma unroll
-      for (int o = 0; o < 8; ++o) outacc[o] = 0.0f;
+      for (int cc = 0; cc < TPX_MAX_DIN; ++cc) xr[cc] = (valid && cc < d_in) ? __ldg(a.x + gp * d_in + cc) : 0.0f;
 
       for (int l = 0; l < L; ++l) {
-        const float* bias = sm + so.small + lay.bias(l);
+        const float* bias = sm + so.small + lay.bias(l) + jw;
         const bool last = (l == L - 1);
-        float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (8 * HP * TILE) : nullptr;
-        const bool dbg_on = a.dbg && blockIdx.x == 0 && pair == blockIdx.x + gridDim.x && lane == 0 && half == 0 && slot == 0;
-        if (dbg_on) a.dbg[(q * 8 + l) * 8 + 0] = clock64();
-        if (l > 0) {
+        float z[S][8];                         // pre-activation streams, then activation streams, of 8 neurons
+        if (l == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[0][i] = bias[i];
+#pragma unroll
+          for (int cc = 0; cc < TPX_MAX_DIN; ++cc)
+            if (cc < d_in) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) z[0][i] = fmaf(W0[cc * HP + jw + i], xr[cc], z[0][i]);
+            }
+#pragma unroll
+          for (int k = 0; k < ND; ++k)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[1 + k][i] = W0[dcol[k] * HP + jw + i];
+          if (LAP) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[S - 1][i] = 0.0f;
+          }
+        } else {
+          // ---- in: D rows of this warp's stream -> exchange buffer
           mbar_wait(&bar_d[slot], ph_d);
           ph_d ^= 1;
           fence_after();
-        }
-        if (dbg_on) a.dbg[(q * 8 + l) * 8 + 1] = clock64();
-        float xr[TPX_MAX_DIN];
-        if (l == 0 && is_val) {
+          if (owner) {
 #pragma unroll
-          for (int cc = 0; cc < TPX_MAX_DIN; ++cc) xr[cc] = (valid && cc < d_in) ? __ldg(a.x + gp * d_in + cc) : 0.0f;
-        }
-        // own pre-activation values of neurons [jc, jc + CH)
-        auto own = [&](int jc, float (&w)[CH]) {
-          if (l == 0) {
-            if (is_val) {
+            for (int c = 0; c < NB / CH; ++c) {
+              float w[CH];
+              tmem_ld16(tD + j0 + c * CH, w);
 #pragma unroll
-              for (int i = 0; i < CH; ++i) w[i] = bias[jc + i];
-#pragma unroll
-              for (int cc = 0; cc < TPX_MAX_DIN; ++cc) {
-                if (cc < d_in) {
-#pragma unroll
-                  for (int i = 0; i < CH; ++i) w[i] = fmaf(W0[cc * HP + jc + i], xr[cc], w[i]);
-                }
-              }
-            } else if (is_dk) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) w[i] = W0[dcol * HP + jc + i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) w[i] = 0.0f;
-            }
-          } else {
-            tmem_ld16(tD + jc, w);
-            if (is_val) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) w[i] += bias[jc + i];
+              for (int v = 0; v < CH / 4; ++v)
+                *reinterpret_cast<float4*>(ex_own + c * CH + 4 * v) = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
             }
           }
-        };
-        // ---- phase 1: publish what the other streams of the point need: tanh(z) and d_k z
-        // (one straight-line loop per role so that the 16 independent chains of a chunk interleave)
-        if (is_val) {
-#pragma unroll 1
-          for (int c = 0; c < NB / CH; ++c) {
-            float w[CH];
-            own(j0 + c * CH, w);
+          named_bar_sync(barid, 128);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) w[i] = tanh_fast(w[i]);
+          for (int s = 0; s < S; ++s) {
+            const float4 lo4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * EXP);
+            const float4 hi4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * EXP + 4);
+            z[s][0] = lo4.x; z[s][1] = lo4.y; z[s][2] = lo4.z; z[s][3] = lo4.w;
+            z[s][4] = hi4.x; z[s][5] = hi4.y; z[s][6] = hi4.z; z[s][7] = hi4.w;
+          }
 #pragma unroll
-            for (int i = 0; i < CH; ++i) ex_z[(j0 + c * CH + i) * TILE + lane] = w[i];
+          for (int i = 0; i < 8; ++i) z[0][i] += bias[i];
+        }
+        // ---- compute: thread-local jets of 8 neurons (all streams of this point)
+        float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (8 * HP * TILE) + jw * TILE + lane : nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = tanh_fast(z[0][i]);
+          const float s1 = fmaf(-t, t, 1.0f);
+          z[0][i] = t;
+          if (ckl) ckl[(0 * HP + i) * TILE] = t;
+          float qq = 0.0f;
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            const float dz = z[1 + k][i];
+            if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
+            const float dh = s1 * dz;
+            z[1 + k][i] = dh;
             if (ckl) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) ckl[(j0 + c * CH + i) * TILE + lane] = w[i];
+              ckl[(((1 + k) * 2 + 0) * HP + i) * TILE] = dz;
+              ckl[(((1 + k) * 2 + 1) * HP + i) * TILE] = dh;
             }
           }
-        } else if (is_dk && LAP) {
-          float* dst = ex_dz + (q - 1) * HP * TILE;
-#pragma unroll 1
-          for (int c = 0; c < NB / CH; ++c) {
-            float w[CH];
-            own(j0 + c * CH, w);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) dst[(j0 + c * CH + i) * TILE + lane] = w[i];
+          if (LAP) {
+            const float lz = z[S - 1][i];
+            const float lh = fmaf(-2.0f * t * s1, qq, s1 * lz);
+            z[S - 1][i] = lh;
+            if (ckl) {
+              ckl[(((S - 1) * 2 + 0) * HP + i) * TILE] = lz;
+              ckl[(((S - 1) * 2 + 1) * HP + i) * TILE] = lh;
+            }
           }
         }
-        if (dbg_on) a.dbg[(q * 8 + l) * 8 + 2] = clock64();
-        named_bar_sync(barid, 128);
-        if (dbg_on) a.dbg[(q * 8 + l) * 8 + 3] = clock64();
-        // ---- phase 2: this stream's activation output
-        auto emit = [&](int jc, float (&w)[CH]) {
-          if (!last) {
-            float lo[CH];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              const float hi = tf32_hi(w[i]);
-              lo[i] = w[i] - hi;
-              w[i] = hi;
-            }
-            tmem_st16(tAh + jc, w);
-            tmem_st16(tAl + jc, lo);
-          } else {
-#pragma unroll
-            for (int o = 0; o < 8; ++o) {
-              if (o < d_out) {
-                float acc = outacc[o];
-#pragma unroll
-                for (int i = 0; i < CH; ++i) acc = fmaf(WL[o * HP + jc + i], w[i], acc);
-                outacc[o] = acc;
-              }
-            }
-          }
-        };
-#pragma unroll
-        for (int o = 0; o < 8; ++o) outacc[o] = 0.0f;
-        if (is_val) {
-#pragma unroll 1
-          for (int c = 0; c < NB / CH; ++c) {
-            const int jc = j0 + c * CH;
-            float w[CH];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) w[i] = ex_z[(jc + i) * TILE + lane];
-            emit(jc, w);
-          }
-        } else if (is_dk) {
-#pragma unroll 1
-          for (int c = 0; c < NB / CH; ++c) {
-            const int jc = j0 + c * CH;
-            float w[CH];
-            own(jc, w);
-            if (ckl) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 0) * HP + jc + i) * TILE + lane] = w[i];
-            }
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              const float t = ex_z[(jc + i) * TILE + lane];
-              w[i] *= fmaf(-t, t, 1.0f);
-            }
-            if (ckl) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 1) * HP + jc + i) * TILE + lane] = w[i];
-            }
-            emit(jc, w);
-          }
-        } else if (is_lap) {
-#pragma unroll 1
-          for (int c = 0; c < NB / CH; ++c) {
-            const int jc = j0 + c * CH;
-            float w[CH];
-            own(jc, w);
-            if (ckl) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 0) * HP + jc + i) * TILE + lane] = w[i];
-            }
-#pragma unroll
-            for (int i = 0; i < CH; ++i) {
-              const float t = ex_z[(jc + i) * TILE + lane];
-              const float s1 = fmaf(-t, t, 1.0f);
-              float qq = 0.0f;
-#pragma unroll
-              for (int k = 0; k < ND; ++k) {
-                const float dz = ex_dz[(k * HP + jc + i) * TILE + lane];
-                qq = fmaf(lapw[k] * dz, dz, qq);
-              }
-              w[i] = fmaf(-2.0f * t * s1, qq, s1 * w[i]);
-            }
-            if (ckl) {
-#pragma unroll
-              for (int i = 0; i < CH; ++i) ckl[((q * 2 + 1) * HP + jc + i) * TILE + lane] = w[i];
-            }
-            emit(jc, w);
-          }
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < NB / CH; ++c) {
-            float w[CH];
-#pragma unroll
-            for (int i = 0; i < CH; ++i) w[i] = 0.0f;
-            emit(j0 + c * CH, w);
-          }
-        }
-        if (dbg_on) a.dbg[(q * 8 + l) * 8 + 4] = clock64();
         if (!last) {
-          tmem_wait_st();
+          // ---- out: activation streams -> exchange buffer -> owners split hi / lo into the next A operand
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            *reinterpret_cast<float4*>(ex_cmp + s * TILE * EXP) = make_float4(z[s][0], z[s][1], z[s][2], z[s][3]);
+            *reinterpret_cast<float4*>(ex_cmp + s * TILE * EXP + 4) = make_float4(z[s][4], z[s][5], z[s][6], z[s][7]);
+          }
+          named_bar_sync(barid, 128);
+          if (owner) {
+#pragma unroll
+            for (int c = 0; c < NB / CH; ++c) {
+              float hi[CH], lo[CH];
+#pragma unroll
+              for (int v = 0; v < CH / 4; ++v) {
+                const float4 w4 = *reinterpret_cast<const float4*>(ex_own + c * CH + 4 * v);
+                hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
+              }
+#pragma unroll
+              for (int i = 0; i < CH; ++i) {
+                const float h = tf32_hi(hi[i]);
+                lo[i] = hi[i] - h;
+                hi[i] = h;
+              }
+              tmem_st16(tAh + j0 + c * CH, hi);
+              tmem_st16(tAl + j0 + c * CH, lo);
+            }
+            tmem_wait_st();
+          }
           fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_a[slot]);
-        }
-        if (dbg_on) a.dbg[(q * 8 + l) * 8 + 5] = clock64();
-      }
-      // ---- outputs of this stream: the two halves of a row meet through shared memory
-      float* part = sm + so.part + (slot * 4 + q) * (8 * TILE);          // [o][p] partial sums of half 1
-      if (half == 1) {
+        } else {
+          // ---- output layer: every warp holds partial dot products over its 8 neurons for all streams; the 8
+          // warps of the slot meet in shared memory, OC output columns per pass
+          const int w8 = warp % SLOT_WARPS;
+          for (int o0 = 0; o0 < d_out; o0 += OC) {
 #pragma unroll
-        for (int o = 0; o < 8; ++o)
-          if (o < d_out) part[o * TILE + lane] = outacc[o];
-      }
-      named_bar_sync(1 + SLOTS * HALVES + slot, 32 * SLOT_WARPS);
-      if (half == 0 && valid && !idle) {
+            for (int oo = 0; oo < OC; ++oo) {
+              const int o = (o0 + oo < d_out) ? o0 + oo : o0;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          if (o < d_out) {
-            const float r = outacc[o] + part[o * TILE + lane];
-            if (is_val) a.u[gp * d_out + o] = r + bL[o];
-            else if (is_dk) a.du[(gp * d_out + o) * ND + (q - 1)] = r;
-            else a.lap[gp * d_out + o] = r;
+              for (int s = 0; s < S; ++s) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc = fmaf(WL[o * HP + jw + i], z[s][i], acc);
+                part[((w8 * 4 + s) * OC + oo) * TILE + lane] = acc;
+              }
+            }
+            named_bar_sync(slot_bar, 32 * SLOT_WARPS);
+            if (half == 0 && owner && valid) {
+#pragma unroll
+              for (int oo = 0; oo < OC; ++oo) {
+                const int o = o0 + oo;
+                if (o < d_out) {
+                  float r = 0.0f;
+#pragma unroll
+                  for (int w = 0; w < SLOT_WARPS; ++w) r += part[((w * 4 + quad) * OC + oo) * TILE + lane];
+                  if (quad == 0) a.u[gp * d_out + o] = r + bL[o];
+                  else if (quad <= ND) a.du[(gp * d_out + o) * ND + (quad - 1)] = r;
+                  else a.lap[gp * d_out + o] = r;
+                }
+              }
+            }
+            if (o0 + OC < d_out) named_bar_sync(slot_bar, 32 * SLOT_WARPS);   // part is reused by the next pass
           }
         }
       }
@@ -490,7 +465,6 @@ int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float
   a.jet = jet;
   a.img = img; a.x = x; a.n = n; a.u = u; a.du = du; a.lap = lapo;
   a.ckpt = saved;
-  a.dbg = g_tc_debug;
   switch (jet.nd * 2 + lap) {
     case 0: return launch_tc_fwd<0, 0>(a, sm_count, stream);
     case 2: return launch_tc_fwd<1, 0>(a, sm_count, stream);
