@@ -201,7 +201,7 @@ def test_saved_checkpoints_equal_recompute(hidden, dcols, lap_w, d_out):
     gdu = torch.randn(N, d_out, len(dcols), device="cuda")
     glap = torch.randn(N, d_out, device="cuda") if lap_w else None
     nbytes = eng.saved_bytes(spec, N)
-    assert nbytes == ((N + 31) // 32) * len(hidden) * 8 * 64 * 32 * 4
+    assert nbytes == ((N + 31) // 32) * len(hidden) * 4 * 64 * 32 * 4
     saved = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     u1, du1, lap1 = eng.forward_raw(packed, x, spec, saved)
     u0, du0, lap0 = eng.forward_raw(packed, x, spec)

@@ -1,7 +1,8 @@
-// Tensor-core (tcgen05 / TMEM) reverse kernel for hidden width <= 64, tanh, <= 4 streams:
-// per tile of 32 points it re-runs the forward jet (checkpointing the activation jets in a
-// per-CTA, L2-resident scratch), then sweeps the layers backwards.  Rows of every UMMA are
-// (stream q, point p) = TMEM lane 32 q + p, as in the forward kernel (tc_kernels.cu).
+// Tensor-core (tcgen05 / TMEM) reverse kernel for hidden width <= 64, tanh, <= 4 streams.
+//
+// It sweeps the layers of one 32-point tile backwards, reading the activation-jet checkpoints the forward
+// kernel saved (tc_kernels.cu: per tile and layer S arrays [64 neurons][32 points]: tanh(z), d_k z, L z).
+// Rows of every UMMA are (stream q, point p) = TMEM lane 32 q + p, as in the forward kernel.
 //
 // Per hidden matrix l (1 <= l < L) the reverse step issues two products:
 //   adjoint   D[128 x 64] = Zbar_l[128 x 64] W_l            A = Zbar (hi/lo) in TMEM, B = W_l^T image (K-major)
@@ -11,9 +12,19 @@
 //             [hi ; lo] on M = 128 and a_{l-1} as two N = 64 operands hi / lo, so two chains give
 //             hi*hi + lo*hi + hi*lo + lo*lo.  dW_l accumulates in TMEM over ALL tiles of the CTA and is
 //             read out once at the end of the kernel.
-// Everything with a tiny contraction (layer 0, output layer, biases) is reduced over the 32 lanes with a
-// transposing shuffle reduction and accumulated in registers across tiles.
-// Weight images (32 KB per product) stream through a 2-deep ring with cp.async.bulk + mbarrier.
+//
+// Activation step (16 warps = 4 neuron groups x 4 TMEM quadrants, lane = point).  A TMEM quadrant holds ONE
+// stream, but the adjoint formulas couple all streams of a point, so the step is split like the forward's:
+//   in      the OWNER warp of stream s reads its 16 adjoint columns of D and writes them to the group's
+//           exchange buffer ex[s][p][neuron] (rows padded to 20 floats: conflict-free 128-bit accesses)
+//   compute warp w of the group takes neurons [4 w, 4 w + 4) for ALL streams of its 32 points: adjoints of the
+//           pre-activation streams, the activation jets a_{l-1} of the previous layer (from its checkpoints,
+//           kept in registers for the next step) -- all thread-local, identical work on every scheduler;
+//           it writes the transposed gradient-product operands (Zt, At) itself and hands Zbar back through ex
+//   out     the owner splits its stream's Zbar rows hi / lo into the TMEM A operand of the adjoint product
+// Bias, first-layer and output-layer gradients are reduced over the 32 lanes with a short transposing
+// shuffle reduction and accumulated in shared memory (each entry is owned by one warp).
+// Weight images (32 KB per product) are fetched with cp.async.bulk + mbarrier behind the activation work.
 #include <cstdio>
 #include <cstring>
 
@@ -26,26 +37,31 @@
 namespace tpx {
 namespace tc {
 
-constexpr int B_CH = 16;                 // neurons per activation warp
+constexpr int B_CH = 16;                 // neurons per warp group (= columns one owner moves per step)
 constexpr int B_GROUPS = HP / B_CH;      // warp groups: the 4 quadrant warps that share one chunk of neurons
+constexpr int B_NW = B_CH / 4;           // neurons per warp in the compute phase
 constexpr int B_EPI_WARPS = 4 * B_GROUPS;
 constexpr int B_THREADS = 32 * (B_EPI_WARPS + 1);
 constexpr uint32_t B_TMEM_COLS = 512;
 constexpr uint32_t T_D = 0, T_AH = 64, T_AL = 128, T_DW = 192;   // TMEM columns
-constexpr int MAXL = 6;                  // hidden layers supported (dW accumulators: 64 columns each)
-constexpr int MAXIO = 4;                 // d_in, d_out supported by the register accumulators
-constexpr int EX_ARRAYS = 7;             // exchange arrays of 16 x 32 floats per warp group
+constexpr int MAXL = 6;                  // hidden layers supported (dW accumulators: 64 columns each, L - 1 <= 5)
+constexpr int MAXIO = 4;                 // d_in, d_out supported
+constexpr int BXP = 20;                  // padded neuron extent of one (stream, point) row of the exchange buffer
+constexpr int BX_GROUP = 4 * TILE * BXP;
 
 struct BwdSmem {
-  int wring, zt, at, ex, small, total;   // float offsets from the 1 KB aligned base
+  int wring, zt, at, ex, acc, small, total;   // float offsets from the 1 KB aligned base
 };
+// shared accumulators: [db: MAXL x 64][dW0: MAXIO x 64][dWL: MAXIO x 64][dbL: 64 (MAXIO used)]
+constexpr int ACC_DB = 0, ACC_W0 = MAXL * HP, ACC_WL = ACC_W0 + MAXIO * HP, ACC_BL = ACC_WL + MAXIO * HP, ACC_TOTAL = ACC_BL + HP;
 __host__ __device__ inline BwdSmem bwd_smem(const TcLayout& lay) {
   BwdSmem s;
   s.wring = 0;                            // (hi, lo) x 4096: one product image, refetched per phase
   s.zt = 8192;                            // 128 rows x 128 K
   s.at = s.zt + 16384;                    // hi: 64 rows x 128 K, lo: 64 rows x 128 K
   s.ex = s.at + 16384;
-  s.small = s.ex + B_GROUPS * EX_ARRAYS * B_CH * TILE;
+  s.acc = s.ex + B_GROUPS * BX_GROUP;
+  s.small = s.acc + ACC_TOTAL;
   s.total = s.small + (int)lay.small();
   return s;
 }
@@ -59,33 +75,20 @@ struct BwdArgs {
   int64_t n;
   const float *gu, *gdu, *glap;
   double* gacc;
-  float* ckpt;       // RECOMP: per CTA, else per tile: L x 8 arrays x 64 x 32 floats
+  const float* ckpt;   // per tile: L x 4 arrays x 64 x 32 floats
 };
 
-__host__ __device__ inline size_t ckpt_floats_per_cta(int L) { return (size_t)L * 8 * HP * TILE; }
-
-// lane L receives the sum over all 32 lanes of v[L & 15]  (v is destroyed)
-__device__ __forceinline__ float reduce16(float (&v)[B_CH], int lane) {
-#pragma unroll
-  for (int s = 8; s >= 1; s >>= 1) {
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const bool up = (lane & s) != 0;
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
-
-__device__ __forceinline__ float tanh_fast_b(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -2.885390081777927f));
-  const float d = e + 1.0f;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  r = r * fmaf(-d, r, 2.0f);
-  return copysignf((1.0f - e) * r, x);
+// lane receives the sum over all 32 lanes of v[lane & 3]
+__device__ __forceinline__ float reduce4(float v0, float v1, float v2, float v3, int lane) {
+  const bool up2 = (lane & 2) != 0;
+  const float a0 = (up2 ? v2 : v0) + __shfl_xor_sync(0xffffffffu, up2 ? v0 : v2, 2);
+  const float a1 = (up2 ? v3 : v1) + __shfl_xor_sync(0xffffffffu, up2 ? v1 : v3, 2);
+  const bool up1 = (lane & 1) != 0;
+  float b = (up1 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up1 ? a0 : a1, 1);
+  b += __shfl_xor_sync(0xffffffffu, b, 4);
+  b += __shfl_xor_sync(0xffffffffu, b, 8);
+  b += __shfl_xor_sync(0xffffffffu, b, 16);
+  return b;
 }
 
 __device__ __forceinline__ void bulk_load(float* dst_smem, const float* src, uint32_t bytes, uint64_t* bar) {
@@ -94,7 +97,7 @@ __device__ __forceinline__ void bulk_load(float* dst_smem, const float* src, uin
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int ND, int LAP, bool RECOMP>
+template <int ND, int LAP>
 __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
@@ -107,9 +110,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   const BwdSmem so = bwd_smem(lay);
   const int L = lay.L, d_in = lay.d_in, d_out = lay.d_out;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nphase = RECOMP ? 2 * (L - 1) : (L - 1);   // MMA phases per tile: [F1..F(L-1),] R(L-1)..R1
+  const int nphase = L - 1;                 // MMA phases per tile: R(L-1) .. R1
 
   for (int v = tid; v < (int)lay.small(); v += B_THREADS) sm[so.small + v] = __ldg(a.img + v);
+  for (int v = tid; v < ACC_TOTAL; v += B_THREADS) sm[so.acc + v] = 0.0f;
+  for (int v = tid; v < 2 * 16384; v += B_THREADS) sm[so.zt + v] = 0.0f;     // K atoms of unused streams stay zero
   if (warp == B_EPI_WARPS) tmem_alloc(&tmem_slot, B_TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_a, B_EPI_WARPS);
@@ -118,6 +123,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     mbar_init(&bar_w, 1);
     mbar_init_fence();
   }
+  fence_async_smem();
   fence_before();
   __syncthreads();
   fence_after();
@@ -131,21 +137,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     constexpr uint32_t idesc = idesc_tf32(128, HP);
     const int64_t total_phases = my_tiles * nphase;
     uint32_t ph_a = 0, ph_w = 0, ph_d = 0;
-    auto phase_layer = [&](int64_t g, bool& fwd) -> int {
-      const int n = (int)(g % nphase);
-      fwd = RECOMP && n < L - 1;
-      return fwd ? n + 1 : (L - 1) - (RECOMP ? n - (L - 1) : n);
-    };
     auto phase_src = [&](int64_t g) -> const float* {
-      bool fwd;
-      const int l = phase_layer(g, fwd);
-      return a.img + lay.mat(l, fwd ? 0 : 2);
+      const int l = (L - 1) - (int)(g % nphase);
+      return a.img + lay.mat(l, 2);
     };
     if (total_phases > 0 && elect_one()) bulk_load(sm + so.wring, phase_src(0), 32768u, &bar_w);
     __syncwarp();
     for (int64_t g = 0; g < total_phases; ++g) {
-      bool fwd;
-      const int l = phase_layer(g, fwd);
+      const int l = (L - 1) - (int)(g % nphase);
       const bool first_tile = g < nphase;
       mbar_wait(&bar_a, ph_a);
       ph_a ^= 1;
@@ -164,19 +163,17 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
           mma_tf32_ts(tD, tAl + ks * 8, desc_k_sw128(wh + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, 1);
-        mma_commit(&bar_d);                  // the adjoint (or forward) product is all the next epilogue needs ...
-        if (!fwd) {
-          const uint32_t tW = tmem + T_DW + (uint32_t)(l - 1) * 64;
+        mma_commit(&bar_d);                  // the adjoint product is all the next activation step needs ...
+        const uint32_t tW = tmem + T_DW + (uint32_t)(l - 1) * 64;
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks)
-            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 8192 + (ks & 3) * 32),
-                        idesc, (ks > 0 || !first_tile) ? 1u : 0u);
+        for (int ks = 0; ks < 16; ++ks)
+          mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 8192 + (ks & 3) * 32),
+                      idesc, (ks > 0 || !first_tile) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks)
-            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32),
-                        desc_k_sw128(at + 32768u + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, 1);
-          mma_commit(&bar_f);                // ... the gradient product only gates the reuse of its operands
-        }
+        for (int ks = 0; ks < 16; ++ks)
+          mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32),
+                      desc_k_sw128(at + 32768u + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, 1);
+        mma_commit(&bar_f);                  // ... the gradient product only gates the reuse of its operands
       }
       __syncwarp();
       // the weight image is free once this phase's TMEM-operand products are done: fetch the next image
@@ -190,333 +187,238 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     }
   } else {
     // =========================== activation warps ===========================
-    // warp = grp * 4 + q: TMEM quadrant q (= stream q of the tile), neurons [16 grp, 16 grp + 16)
-    const int grp = warp >> 2, q = warp & 3;
-    const int jc = grp * B_CH;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // warp = grp * 4 + quad: TMEM quadrant quad (= stream quad), group neurons [16 grp, 16 grp + 16);
+    // compute phase: neurons jn .. jn + 3, all streams
+    const int grp = warp >> 2, quad = warp & 3;
+    const int jc = grp * B_CH, jn = jc + quad * B_NW;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t tD = tmem + T_D + lane_base, tAh = tmem + T_AH + lane_base, tAl = tmem + T_AL + lane_base;
-    float* ex = sm + so.ex + grp * (EX_ARRAYS * B_CH * TILE);
-    float* X_T = ex;                                  // [16][32] tanh(z)
-    float* X_DZ = ex + 1 * B_CH * TILE;               // [k][16][32]  d_k z           (k < 3)
-    float* X_G = ex + 4 * B_CH * TILE;                // [k][16][32]  adjoint of d_k a (k < 2 with LAP, < 3 without)
-    float* X_LZ = ex + (LAP ? 3 : 6) * B_CH * TILE;   // with LAP: ND <= 2, so array 3 is free for L z
-    float* X_GL = ex + 6 * B_CH * TILE;               // adjoint of L a
+    float* ex = sm + so.ex + grp * BX_GROUP;
+    float* ex_own = ex + (quad * TILE + lane) * BXP;           // owner view: stream quad, the group's 16 neurons
+    float* ex_cmp = ex + lane * BXP + quad * B_NW;             // compute view of stream s: + s * TILE * BXP
+    float* acc = sm + so.acc;
     const float* W0 = sm + so.small + lay.w0();
     const float* WL = sm + so.small + lay.wl();
     const int barid = 1 + grp;
-    const bool is_val = (q == 0), is_dk = (q >= 1 && q <= ND), is_lap = (LAP && q == ND + 1), idle = (q >= S);
-    const int kq = is_dk ? q - 1 : 0;
-    const int dcol = is_dk ? a.jet.dcol[kq] : 0;
+    const bool owner = quad < S;
     float lapw[NDX];
+    int dcol[NDX];
 #pragma unroll
-    for (int k = 0; k < NDX; ++k) lapw[k] = (LAP && k < ND) ? a.jet.lap_w[k] : 0.0f;
+    for (int k = 0; k < NDX; ++k) {
+      lapw[k] = (LAP && k < ND) ? a.jet.lap_w[k] : 0.0f;
+      dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
+    }
     uint32_t ph_d = 0, ph_f = 0;
     bool dw_pending = false;             // a gradient product may still be reading Zt / At
-    // transposed operands: element (row = neuron, K = this thread's row index 32 q + lane); 128-byte swizzle
-    //   offset = (K / 32) * atom + row * 32 + ((((K % 32) / 4) ^ (row % 8)) * 4) + K % 4,   row % 8 == i % 8 (jc % 16 == 0)
-    float* Zt = sm + so.zt + q * 4096 + jc * 32 + (lane & 3);
-    float* At = sm + so.at + q * 2048 + jc * 32 + (lane & 3);
-    int xo[8];
+    // transposed operands: element (row = neuron, K = 32 s + lane); 128-byte swizzle:
+    //   offset = s * atom + row * 32 + ((lane / 4) ^ (row % 8)) * 4 + lane % 4
+    float* Zt = sm + so.zt + jn * 32 + (lane & 3);
+    float* At = sm + so.at + jn * 32 + (lane & 3);
+    int xo[B_NW];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) xo[m] = ((lane >> 2) ^ m) << 2;
-
-    // register accumulators across tiles; lane i (and i + 16) <-> neuron jc + (i & 15)
-    float acc_b[MAXL], acc_w0[MAXIO], acc_wl[MAXIO], acc_bl[MAXIO];
+    for (int i = 0; i < B_NW; ++i) xo[i] = ((lane >> 2) ^ ((jn + i) & 7)) << 2;
+    if (!owner) {                        // rows of an unused quadrant: a zero A operand, written once
+      float zero[B_CH];
 #pragma unroll
-    for (int l = 0; l < MAXL; ++l) acc_b[l] = 0.0f;
-#pragma unroll
-    for (int c = 0; c < MAXIO; ++c) acc_w0[c] = acc_wl[c] = acc_bl[c] = 0.0f;
-    auto add_b = [&](int l, float v) {
-#pragma unroll
-      for (int ll = 0; ll < MAXL; ++ll)
-        if (ll == l) acc_b[ll] += v;
-    };
-
-    auto wait_d = [&]() {
-      mbar_wait(&bar_d, ph_d);
-      ph_d ^= 1;
-      fence_after();
-    };
-    auto signal_a = [&]() {
+      for (int i = 0; i < B_CH; ++i) zero[i] = 0.0f;
+      tmem_st16(tAh + jc, zero);
+      tmem_st16(tAl + jc, zero);
       tmem_wait_st();
-      fence_async_smem();
-      fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_a);
-    };
-    auto put_A = [&](const float (&w)[B_CH]) {
-      float hi[B_CH], lo[B_CH];
+    }
+
+    // activation jets of a layer from its checkpoints (t, d_k z, L z) -> (a, d_k a, L a)
+    auto jets = [&](const float (&c)[S][B_NW], float (&h)[S][B_NW]) {
 #pragma unroll
-      for (int i = 0; i < B_CH; ++i) {
-        hi[i] = tf32_hi(w[i]);
-        lo[i] = w[i] - hi[i];
-      }
-      tmem_st16(tAh + jc, hi);
-      tmem_st16(tAl + jc, lo);
-    };
-    auto put_Zt = [&](const float (&w)[B_CH]) {
+      for (int i = 0; i < B_NW; ++i) {
+        const float t = c[0][i];
+        const float s1 = fmaf(-t, t, 1.0f);
+        h[0][i] = t;
+        float qq = 0.0f;
 #pragma unroll
-      for (int i = 0; i < B_CH; ++i) {
-        const float hi = tf32_hi(w[i]);
-        Zt[i * 32 + xo[i & 7]] = hi;
-        Zt[(64 + i) * 32 + xo[i & 7]] = w[i] - hi;
-      }
-    };
-    auto put_At = [&](const float (&w)[B_CH]) {
-#pragma unroll
-      for (int i = 0; i < B_CH; ++i) {
-        const float hi = tf32_hi(w[i]);
-        At[i * 32 + xo[i & 7]] = hi;
-        At[8192 + i * 32 + xo[i & 7]] = w[i] - hi;
-      }
-    };
-    // output layer gradient: dWL[o][j] += sum_rows g_row[o] a_{L-1,row}[j]
-    auto grad_out = [&](const float (&al)[B_CH], const float (&g)[MAXIO]) {
-#pragma unroll
-      for (int o = 0; o < MAXIO; ++o)
-        if (o < d_out) {
-          float v[B_CH];
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) v[i] = g[o] * al[i];
-          acc_wl[o] += reduce16(v, lane);
+        for (int k = 0; k < ND; ++k) {
+          const float dz = c[1 + k][i];
+          if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
+          h[1 + k][i] = s1 * dz;
         }
+        if (LAP) h[S - 1][i] = fmaf(-2.0f * t * s1, qq, s1 * c[S - 1][i]);
+      }
+    };
+    auto load_ck = [&](const float* ck_tile, int l, float (&c)[S][B_NW]) {
+      const float* base = ck_tile + (size_t)l * 4 * HP * TILE + jn * TILE + lane;
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int i = 0; i < B_NW; ++i) c[s][i] = __ldg(base + (s * HP + i) * TILE);
     };
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gp = tile * TILE + lane;
       const bool valid = gp < a.n;
+      const float* ck_tile = a.ckpt + (size_t)tile * ((size_t)L * 4 * HP * TILE);
+      float ck[S][B_NW], ckp[S][B_NW];       // checkpoints of layer l and of layer l - 1
+      load_ck(ck_tile, L - 1, ck);
+      if (L >= 2) load_ck(ck_tile, L - 2, ckp);
       float xr[MAXIO];
 #pragma unroll
       for (int c = 0; c < MAXIO; ++c) xr[c] = (valid && c < d_in) ? __ldg(a.x + gp * d_in + c) : 0.0f;
-      float g[MAXIO];                      // adjoint of this row's output stream
+      float g[S][MAXIO];                     // adjoints of this point's output streams
 #pragma unroll
       for (int o = 0; o < MAXIO; ++o) {
-        float v = 0.0f;
-        if (valid && o < d_out) {
-          if (is_val) { if (a.gu) v = __ldg(a.gu + gp * d_out + o); }
-          else if (is_dk) { if (a.gdu) v = __ldg(a.gdu + (gp * d_out + o) * ND + kq); }
-          else if (is_lap) { if (a.glap) v = __ldg(a.glap + gp * d_out + o); }
-        }
-        g[o] = v;
+        const bool on = valid && o < d_out;
+        g[0][o] = (on && a.gu) ? __ldg(a.gu + gp * d_out + o) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) g[1 + k][o] = (on && a.gdu) ? __ldg(a.gdu + (gp * d_out + o) * ND + k) : 0.0f;
+        if (LAP) g[S - 1][o] = (on && a.glap) ? __ldg(a.glap + gp * d_out + o) : 0.0f;
       }
-      if (is_val && grp == 0) {
+      if (warp == 0) {                       // output bias: sum of the value-stream adjoints
 #pragma unroll
         for (int o = 0; o < MAXIO; ++o) {
-          float s = g[o];
+          float s = g[0][o];
 #pragma unroll
           for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-          acc_bl[o] += s;
+          if (lane == 0 && o < d_out) acc[ACC_BL + o] += s;
         }
       }
-      // checkpoints: recomputed into the per-CTA scratch, or the ones the forward kernel saved for this tile
-      float* ck = a.ckpt + (size_t)(RECOMP ? (int64_t)blockIdx.x : tile) * ckpt_floats_per_cta(L);
 
-      // ------------------------------------------------------------------ forward with checkpoints
-      if constexpr (RECOMP) {
-        for (int l = 0; l < L; ++l) {
-          const float* bias = sm + so.small + lay.bias(l);
-          const bool last = (l == L - 1);
-          if (l > 0) wait_d();
-          float* ckl = ck + (size_t)l * 8 * HP * TILE + jc * TILE + lane;
-          float w[B_CH];
-          if (l == 0) {
-            if (is_val) {
+      for (int l = L - 1; l >= 0; --l) {
+        float ga[S][B_NW];                   // adjoints of the activation streams of layer l
+        if (l == L - 1) {
+          // output layer: u_s = WL a_s (+ bL): adjoint and gradient are thread-local
+          float al[S][B_NW];
+          jets(ck, al);
 #pragma unroll
-              for (int i = 0; i < B_CH; ++i) w[i] = bias[jc + i];
+          for (int s = 0; s < S; ++s)
 #pragma unroll
-              for (int cc = 0; cc < MAXIO; ++cc)
-                if (cc < d_in) {
+            for (int i = 0; i < B_NW; ++i) ga[s][i] = 0.0f;
 #pragma unroll
-                  for (int i = 0; i < B_CH; ++i) w[i] = fmaf(W0[cc * HP + jc + i], xr[cc], w[i]);
+          for (int o = 0; o < MAXIO; ++o)
+            if (o < d_out) {
+              float wg[B_NW];
+#pragma unroll
+              for (int i = 0; i < B_NW; ++i) wg[i] = 0.0f;
+#pragma unroll
+              for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int i = 0; i < B_NW; ++i) {
+                  ga[s][i] = fmaf(WL[o * HP + jn + i], g[s][o], ga[s][i]);
+                  wg[i] = fmaf(g[s][o], al[s][i], wg[i]);
                 }
-            } else if (is_dk) {
-#pragma unroll
-              for (int i = 0; i < B_CH; ++i) w[i] = W0[dcol * HP + jc + i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < B_CH; ++i) w[i] = 0.0f;
+              const float r = reduce4(wg[0], wg[1], wg[2], wg[3], lane);
+              if (lane < B_NW) acc[ACC_WL + o * HP + jn + lane] += r;
             }
-          } else {
+        } else {
+          // ---- in: adjoint product of the previous step, rows of this warp's stream -> exchange buffer
+          mbar_wait(&bar_d, ph_d);
+          ph_d ^= 1;
+          fence_after();
+          if (owner) {
+            float w[B_CH];
             tmem_ld16(tD + jc, w);
-            if (is_val) {
 #pragma unroll
-              for (int i = 0; i < B_CH; ++i) w[i] += bias[jc + i];
-            }
-          }
-          // stage A: publish + checkpoint the pre-activation jets
-          if (is_val) {
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) w[i] = tanh_fast_b(w[i]);
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) {
-              X_T[i * TILE + lane] = w[i];
-              ckl[(0 * HP + i) * TILE] = w[i];
-            }
-          } else if (is_dk) {
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) {
-              if (LAP) X_DZ[(kq * B_CH + i) * TILE + lane] = w[i];
-              ckl[((q * 2 + 0) * HP + i) * TILE] = w[i];
-            }
-          } else if (is_lap) {
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) ckl[((q * 2 + 0) * HP + i) * TILE] = w[i];
+            for (int v = 0; v < B_CH / 4; ++v)
+              *reinterpret_cast<float4*>(ex_own + 4 * v) = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
           }
           named_bar_sync(barid, 128);
-          // stage B: this stream's activation output
-          if (is_dk) {
 #pragma unroll
-            for (int i = 0; i < B_CH; ++i) {
-              const float t = X_T[i * TILE + lane];
-              w[i] *= fmaf(-t, t, 1.0f);
-              ckl[((q * 2 + 1) * HP + i) * TILE] = w[i];
-            }
-          } else if (is_lap) {
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) {
-              const float t = X_T[i * TILE + lane];
-              const float s1 = fmaf(-t, t, 1.0f);
-              float qq = 0.0f;
-#pragma unroll
-              for (int k = 0; k < ND; ++k) {
-                const float dz = X_DZ[(k * B_CH + i) * TILE + lane];
-                qq = fmaf(lapw[k] * dz, dz, qq);
-              }
-              w[i] = fmaf(-2.0f * t * s1, qq, s1 * w[i]);
-              ckl[((q * 2 + 1) * HP + i) * TILE] = w[i];
-            }
-          } else if (idle) {
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) w[i] = 0.0f;
-          }
-          if (!last) {
-            put_A(w);
-            signal_a();
-          } else if (!idle) {
-            grad_out(w, g);
-          }
-          named_bar_sync(barid, 128);        // the exchange arrays are reused by the next layer
-        }
-      }
-
-      // ------------------------------------------------------------------ reverse sweep
-      for (int l = L - 1; l >= 0; --l) {
-        const float* ckl = ck + (size_t)l * 8 * HP * TILE + jc * TILE + lane;
-        const float* ckp = ck + (size_t)(l > 0 ? l - 1 : 0) * 8 * HP * TILE + jc * TILE + lane;
-        // this row's checkpoints (global): issued before waiting for the adjoint product
-        float cz[B_CH], ap[B_CH];
-#pragma unroll
-        for (int i = 0; i < B_CH; ++i) {
-          cz[i] = idle ? 0.0f : ckl[((q * 2 + 0) * HP + i) * TILE];
-          ap[i] = (idle || l == 0) ? 0.0f : ckp[((q * 2 + (is_val ? 0 : 1)) * HP + i) * TILE];
-        }
-        float ga[B_CH];                    // adjoint of this row's stream of a_l
-        if (l == L - 1) {
-          if constexpr (!RECOMP) {
-            if (!idle) {                   // output layer gradient from the saved jet of the last hidden layer
-              float al[B_CH];
-#pragma unroll
-              for (int i = 0; i < B_CH; ++i) al[i] = ckl[((q * 2 + (is_val ? 0 : 1)) * HP + i) * TILE];
-              grad_out(al, g);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) {
-            float s = 0.0f;
-#pragma unroll
-            for (int o = 0; o < MAXIO; ++o)
-              if (o < d_out) s = fmaf(WL[o * HP + jc + i], g[o], s);
-            ga[i] = s;
-          }
-        } else {
-          wait_d();
-          tmem_ld16(tD + jc, ga);
-        }
-        // stage A: publish
-        if (is_val) {
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) X_T[i * TILE + lane] = cz[i];
-        } else if (is_dk) {
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) {
-            X_DZ[(kq * B_CH + i) * TILE + lane] = cz[i];
-            X_G[(kq * B_CH + i) * TILE + lane] = ga[i];
-          }
-        } else if (is_lap) {
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) {
-            X_LZ[i * TILE + lane] = cz[i];
-            X_GL[i * TILE + lane] = ga[i];
+          for (int s = 0; s < S; ++s) {
+            const float4 v4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * BXP);
+            ga[s][0] = v4.x; ga[s][1] = v4.y; ga[s][2] = v4.z; ga[s][3] = v4.w;
           }
         }
-        named_bar_sync(barid, 128);
-        // stage B: adjoint of this row's pre-activation stream
-        float zb[B_CH];
-        if (is_val) {
+        // ---- compute: adjoints of the pre-activation streams (thread-local)
+        float zb[S][B_NW];
 #pragma unroll
-          for (int i = 0; i < B_CH; ++i) {
-            const float t = cz[i];
-            const float s1 = fmaf(-t, t, 1.0f), s2 = -2.0f * t * s1;
-            float acc = ga[i] * s1, qq = 0.0f;
+        for (int i = 0; i < B_NW; ++i) {
+          const float t = ck[0][i];
+          const float s1 = fmaf(-t, t, 1.0f), s2 = -2.0f * t * s1;
+          float v0 = ga[0][i] * s1, qq = 0.0f;
+          const float gl = LAP ? ga[S - 1][i] : 0.0f;
 #pragma unroll
-            for (int k = 0; k < ND; ++k) {
-              const float dz = X_DZ[(k * B_CH + i) * TILE + lane];
-              acc = fmaf(X_G[(k * B_CH + i) * TILE + lane] * s2, dz, acc);
-              if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
-            }
+          for (int k = 0; k < ND; ++k) {
+            const float dz = ck[1 + k][i];
+            v0 = fmaf(ga[1 + k][i] * s2, dz, v0);
+            float vk = ga[1 + k][i] * s1;
             if (LAP) {
-              const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
-              acc = fmaf(X_GL[i * TILE + lane], fmaf(s3, qq, s2 * X_LZ[i * TILE + lane]), acc);
+              qq = fmaf(lapw[k] * dz, dz, qq);
+              vk = fmaf(2.0f * lapw[k] * gl * s2, dz, vk);
             }
-            zb[i] = acc;
+            zb[1 + k][i] = vk;
           }
-        } else if (is_dk) {
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) {
-            const float t = X_T[i * TILE + lane];
-            const float s1 = fmaf(-t, t, 1.0f);
-            float acc = ga[i] * s1;
-            if (LAP) acc = fmaf(2.0f * lapw[kq] * X_GL[i * TILE + lane] * (-2.0f * t * s1), cz[i], acc);
-            zb[i] = acc;
+          if (LAP) {
+            const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
+            v0 = fmaf(gl, fmaf(s3, qq, s2 * ck[S - 1][i]), v0);
+            zb[S - 1][i] = gl * s1;
           }
-        } else if (is_lap) {
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) {
-            const float t = X_T[i * TILE + lane];
-            zb[i] = ga[i] * fmaf(-t, t, 1.0f);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) zb[i] = 0.0f;
+          zb[0][i] = v0;
+        }
+        {                                    // bias gradient of layer l
+          const float r = reduce4(zb[0][0], zb[0][1], zb[0][2], zb[0][3], lane);
+          if (lane < B_NW) acc[ACC_DB + l * HP + jn + lane] += r;
         }
         if (l > 0) {
-          put_A(zb);
-          if (dw_pending) {                // the previous gradient product must have finished reading Zt / At
+          float ap[S][B_NW];                 // activation jets of layer l - 1 = the other operand of dW_l
+          jets(ckp, ap);
+          if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
             mbar_wait(&bar_f, ph_f);
             ph_f ^= 1;
           }
-          put_Zt(zb);
-          put_At(ap);
-          signal_a();
-          dw_pending = true;
-          if (is_val) add_b(l, reduce16(zb, lane));
-        } else {
-          // layer 0: z = W0 x + b0, d_k z = W0[:, dcol_k]
-          if (is_val) {
 #pragma unroll
-            for (int cc = 0; cc < MAXIO; ++cc)
-              if (cc < d_in) {
-                float v[B_CH];
+          for (int s = 0; s < S; ++s) {
 #pragma unroll
-                for (int i = 0; i < B_CH; ++i) v[i] = zb[i] * xr[cc];
-                acc_w0[cc] += reduce16(v, lane);
-              }
-            acc_b[0] += reduce16(zb, lane);
-          } else if (is_dk) {
-            acc_w0[0] += reduce16(zb, lane);
+            for (int i = 0; i < B_NW; ++i) {
+              const float zh = tf32_hi(zb[s][i]);
+              Zt[s * 4096 + i * 32 + xo[i]] = zh;
+              Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
+              const float ah = tf32_hi(ap[s][i]);
+              At[s * 2048 + i * 32 + xo[i]] = ah;
+              At[8192 + s * 2048 + i * 32 + xo[i]] = ap[s][i] - ah;
+            }
+            *reinterpret_cast<float4*>(ex_cmp + s * TILE * BXP) = make_float4(zb[s][0], zb[s][1], zb[s][2], zb[s][3]);
           }
+          dw_pending = true;
+          named_bar_sync(barid, 128);
+          // ---- out: Zbar rows of this warp's stream -> TMEM A operand (hi / lo)
+          if (owner) {
+            float hi[B_CH], lo[B_CH];
+#pragma unroll
+            for (int v = 0; v < B_CH / 4; ++v) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ex_own + 4 * v);
+              hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < B_CH; ++i) {
+              const float h = tf32_hi(hi[i]);
+              lo[i] = hi[i] - h;
+              hi[i] = h;
+            }
+            tmem_st16(tAh + jc, hi);
+            tmem_st16(tAl + jc, lo);
+            tmem_wait_st();
+          }
+          fence_async_smem();
+          fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_a);
+          // next step: layer l - 1 becomes the current layer; fetch the checkpoints of layer l - 2 behind the MMAs
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int i = 0; i < B_NW; ++i) ck[s][i] = ckp[s][i];
+          if (l >= 2) load_ck(ck_tile, l - 2, ckp);
+        } else {
+          // layer 0: z = W0 x + b0, d_k z = W0[:, dcol_k], L z = 0
+#pragma unroll
+          for (int cc = 0; cc < MAXIO; ++cc)
+            if (cc < d_in) {
+              float r = reduce4(zb[0][0] * xr[cc], zb[0][1] * xr[cc], zb[0][2] * xr[cc], zb[0][3] * xr[cc], lane);
+#pragma unroll
+              for (int k = 0; k < ND; ++k) {
+                const float rk = reduce4(zb[1 + k][0], zb[1 + k][1], zb[1 + k][2], zb[1 + k][3], lane);
+                if (dcol[k] == cc) r += rk;
+              }
+              if (lane < B_NW) acc[ACC_W0 + cc * HP + jn + lane] += r;
+            }
         }
-        named_bar_sync(barid, 128);          // the exchange arrays are reused by the next step
       }
     }
     if (dw_pending) {                        // the last gradient product of this CTA
@@ -526,34 +428,29 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 
     // ------------------------------------------------------------------ flush the accumulators
     const int HP32 = lay32.HP;
-    if (lane < 16) {
-      const int j = jc + lane;
+    __syncwarp();
+    if (lane < B_NW) {
+      const int j = jn + lane;
       if (j < HP32) {
-        if (is_val) {
 #pragma unroll
-          for (int l = 0; l < MAXL; ++l)
-            if (l < L) atomicAdd(a.gacc + (l == 0 ? lay32.b0() : lay32.b(l)) + j, (double)acc_b[l]);
+        for (int l = 0; l < MAXL; ++l)
+          if (l < L) atomicAdd(a.gacc + (l == 0 ? lay32.b0() : lay32.b(l)) + j, (double)acc[ACC_DB + l * HP + j]);
 #pragma unroll
-          for (int cc = 0; cc < MAXIO; ++cc)
-            if (cc < d_in) atomicAdd(a.gacc + lay32.w0() + (size_t)cc * HP32 + j, (double)acc_w0[cc]);
-        } else if (is_dk) {
-          atomicAdd(a.gacc + lay32.w0() + (size_t)dcol * HP32 + j, (double)acc_w0[0]);
-        }
-        if (!idle) {
+        for (int cc = 0; cc < MAXIO; ++cc)
+          if (cc < d_in) atomicAdd(a.gacc + lay32.w0() + (size_t)cc * HP32 + j, (double)acc[ACC_W0 + cc * HP + j]);
 #pragma unroll
-          for (int o = 0; o < MAXIO; ++o)
-            if (o < d_out) atomicAdd(a.gacc + lay32.wl() + (size_t)o * HP32 + j, (double)acc_wl[o]);
-        }
+        for (int o = 0; o < MAXIO; ++o)
+          if (o < d_out) atomicAdd(a.gacc + lay32.wl() + (size_t)o * HP32 + j, (double)acc[ACC_WL + o * HP + j]);
       }
     }
-    if (is_val && grp == 0 && lane == 0) {
+    if (warp == 0 && lane == 0) {
 #pragma unroll
       for (int o = 0; o < MAXIO; ++o)
-        if (o < d_out) atomicAdd(a.gacc + lay32.bl() + o, (double)acc_bl[o]);
+        if (o < d_out) atomicAdd(a.gacc + lay32.bl() + o, (double)acc[ACC_BL + o]);
     }
     // hidden matrices: rows j (hi, quadrants 0-1) and 64 + j (lo, quadrants 2-3) both add into dW[j][i]
     if (my_tiles > 0) {
-      const int j = (q & 1) * 32 + lane;
+      const int j = (quad & 1) * 32 + lane;
       for (int l = 1; l < L; ++l) {
         const uint32_t tW = tmem + T_DW + (uint32_t)(l - 1) * 64 + lane_base;
         float w[B_CH];
@@ -581,30 +478,45 @@ bool tc_bwd_supported(const tpx_fcn_desc* net, int nd, int lap) {
   return true;
 }
 
+static size_t ckpt_floats_per_tile(int L) { return (size_t)L * 4 * HP * TILE; }
+
+// without saved checkpoints the reverse sweep runs in chunks: forward kernel (checkpoints only) into the
+// workspace, then the reverse kernel; a chunk is 16 tiles per SM
+static int64_t chunk_tiles(int sm_count) { return (int64_t)sm_count * 16; }
+
 size_t tc_bwd_workspace_bytes(const tpx_fcn_desc* net, int sm_count) {
-  return (size_t)sm_count * ckpt_floats_per_cta(net->n_hidden) * sizeof(float);
+  return (size_t)chunk_tiles(sm_count) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
 }
 
 size_t tc_saved_bytes(const tpx_fcn_desc* net, int64_t n) {
-  return (size_t)((n + TILE - 1) / TILE) * ckpt_floats_per_cta(net->n_hidden) * sizeof(float);
+  return (size_t)((n + TILE - 1) / TILE) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
 }
 
-template <int ND, int LAP, bool RECOMP>
-static int launch_tc_bwd(const BwdArgs& a, int sm_count, size_t ws_bytes, cudaStream_t stream) {
+template <int ND, int LAP>
+static int launch_tc_bwd(const BwdArgs& a, int sm_count, cudaStream_t stream) {
   const size_t smem = (size_t)bwd_smem(a.lay).total * sizeof(float) + 1024;
   if (smem > 227 * 1024) return fail(TPX_E_UNSUPPORTED, "tc_bwd_kernel needs %zu bytes of shared memory", smem);
   const int64_t ntiles = (a.n + TILE - 1) / TILE;
   const int64_t grid = sm_count < ntiles ? sm_count : ntiles;
   if (grid < 1) return 0;
-  const int64_t units = RECOMP ? grid : ntiles;
-  if (ws_bytes < (size_t)units * ckpt_floats_per_cta(a.lay.L) * sizeof(float))
-    return fail(TPX_E_WORKSPACE, "checkpoint buffer of %zu bytes is too small (%zu needed)", ws_bytes, (size_t)units * ckpt_floats_per_cta(a.lay.L) * sizeof(float));
-  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP, RECOMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel: shared memory attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-  tc_bwd_kernel<ND, LAP, RECOMP><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
+  tc_bwd_kernel<ND, LAP><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel launch (%lld CTAs x %d threads, %zu bytes smem): %s", (long long)grid, B_THREADS, smem, cudaGetErrorString(e));
   return 0;
+}
+
+static int launch_tc_bwd_any(const BwdArgs& a, int nd, int lap, int sm_count, cudaStream_t stream) {
+  switch (nd * 2 + lap) {
+    case 0: return launch_tc_bwd<0, 0>(a, sm_count, stream);
+    case 2: return launch_tc_bwd<1, 0>(a, sm_count, stream);
+    case 3: return launch_tc_bwd<1, 1>(a, sm_count, stream);
+    case 4: return launch_tc_bwd<2, 0>(a, sm_count, stream);
+    case 5: return launch_tc_bwd<2, 1>(a, sm_count, stream);
+    case 6: return launch_tc_bwd<3, 0>(a, sm_count, stream);
+    default: return TPX_E_UNSUPPORTED;
+  }
 }
 
 int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet, int lap, const float* img, const float* x,
@@ -614,19 +526,31 @@ int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet
   a.lay = TcLayout{net->n_hidden, net->d_in, net->d_out};
   a.lay32 = lay32;
   a.jet = jet;
-  a.img = img; a.x = x; a.n = n; a.gu = gu; a.gdu = gdu; a.glap = glap; a.gacc = gacc; a.ckpt = ckpt;
-#define TPX_TC_BWD_CASE(NDV, LAPV) \
-  return saved ? launch_tc_bwd<NDV, LAPV, false>(a, sm_count, ckpt_bytes, stream) : launch_tc_bwd<NDV, LAPV, true>(a, sm_count, ckpt_bytes, stream)
-  switch (jet.nd * 2 + lap) {
-    case 0: TPX_TC_BWD_CASE(0, 0);
-    case 2: TPX_TC_BWD_CASE(1, 0);
-    case 3: TPX_TC_BWD_CASE(1, 1);
-    case 4: TPX_TC_BWD_CASE(2, 0);
-    case 5: TPX_TC_BWD_CASE(2, 1);
-    case 6: TPX_TC_BWD_CASE(3, 0);
-    default: return TPX_E_UNSUPPORTED;
+  a.img = img; a.gacc = gacc; a.ckpt = ckpt;
+  const size_t per_tile = ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
+  if (saved) {
+    const size_t need = (size_t)((n + TILE - 1) / TILE) * per_tile;
+    if (ckpt_bytes < need) return fail(TPX_E_WORKSPACE, "checkpoint buffer of %zu bytes is too small (%zu needed)", ckpt_bytes, need);
+    a.x = x; a.n = n; a.gu = gu; a.gdu = gdu; a.glap = glap;
+    return launch_tc_bwd_any(a, jet.nd, lap, sm_count, stream);
   }
-#undef TPX_TC_BWD_CASE
+  // no saved checkpoints: chunks of (forward kernel writing checkpoints only) + reverse kernel
+  const int64_t ctiles = (int64_t)(ckpt_bytes / per_tile);
+  if (ctiles < 1) return fail(TPX_E_WORKSPACE, "workspace of %zu bytes holds no tile (%zu bytes each)", ckpt_bytes, per_tile);
+  const int64_t cpts = ctiles * TILE;
+  const int d_in = net->d_in, d_out = net->d_out, nd = jet.nd;
+  for (int64_t p0 = 0; p0 < n; p0 += cpts) {
+    const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
+    int rc = tc_forward(net, jet, lap, img, x + p0 * d_in, m, nullptr, nullptr, nullptr, ckpt, sm_count, stream);
+    if (rc) return fail(rc, "tc_fwd_kernel (checkpoint pass of the reverse sweep)");
+    a.x = x + p0 * d_in; a.n = m;
+    a.gu = gu ? gu + p0 * d_out : nullptr;
+    a.gdu = gdu ? gdu + p0 * d_out * nd : nullptr;
+    a.glap = glap ? glap + p0 * d_out : nullptr;
+    rc = launch_tc_bwd_any(a, nd, lap, sm_count, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 }  // namespace tpx

@@ -125,7 +125,7 @@ struct FwdArgs {
   const float* x;
   int64_t n;
   float *u, *du, *lap;
-  float* ckpt;      // optional: [tile][layer][8 arrays][64][32] activation-jet checkpoints for the reverse kernel
+  float* ckpt;      // optional: [tile][layer][4 arrays][64][32] checkpoints for the reverse kernel: tanh(z), d_k z, L z
 };
 
 template <int ND, int LAP>
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           for (int i = 0; i < 8; ++i) z[0][i] += bias[i];
         }
         // ---- compute: thread-local jets of 8 neurons (all streams of this point)
-        float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (8 * HP * TILE) + jw * TILE + lane : nullptr;
+        float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (4 * HP * TILE) + jw * TILE + lane : nullptr;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float t = tanh_fast(z[0][i]);
@@ -305,21 +305,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           for (int k = 0; k < ND; ++k) {
             const float dz = z[1 + k][i];
             if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
-            const float dh = s1 * dz;
-            z[1 + k][i] = dh;
-            if (ckl) {
-              ckl[(((1 + k) * 2 + 0) * HP + i) * TILE] = dz;
-              ckl[(((1 + k) * 2 + 1) * HP + i) * TILE] = dh;
-            }
+            z[1 + k][i] = s1 * dz;
+            if (ckl) ckl[((1 + k) * HP + i) * TILE] = dz;
           }
           if (LAP) {
             const float lz = z[S - 1][i];
-            const float lh = fmaf(-2.0f * t * s1, qq, s1 * lz);
-            z[S - 1][i] = lh;
-            if (ckl) {
-              ckl[(((S - 1) * 2 + 0) * HP + i) * TILE] = lz;
-              ckl[(((S - 1) * 2 + 1) * HP + i) * TILE] = lh;
-            }
+            z[S - 1][i] = fmaf(-2.0f * t * s1, qq, s1 * lz);
+            if (ckl) ckl[((S - 1) * HP + i) * TILE] = lz;
           }
         }
         if (!last) {
@@ -353,8 +345,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_a[slot]);
-        } else {
-          // ---- output layer: every warp holds partial dot products over its 8 neurons for all streams; the 8
+        } else if (a.u != nullptr) {
+          // ---- output layer (skipped by the checkpoint-only pass of the reverse sweep): every warp holds partial dot products over its 8 neurons for all streams; the 8
           // warps of the slot meet in shared memory, OC output columns per pass
           const int w8 = warp % SLOT_WARPS;
           for (int o0 = 0; o0 < d_out; o0 += OC) {
