@@ -71,12 +71,11 @@ def debug_bwd(N=1 << 18):
     lib.tpx_debug_set_timestamps(ctypes.c_void_p(0))
     t = buf.cpu().numpy()
     t0 = t[t > 0].min()
-    names = ["enter", "d_ready", "loaded", "computed", "A_free", "f_free", "stored", "signalled"]
-    for l in (3, 2, 1, 0):
-        for s in range(2):
-            for q in range(4):
-                row = t[((s * 4 + q) * 8 + l) * 8:((s * 4 + q) * 8 + l) * 8 + 8]
-                print(f"l{l} s{s} q{q}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
+    names = ["enter", "d_ready", "in_bar", "computed", "f_free", "stored", "out_bar", "arrived"]
+    for w, off in ((0, 0), (7, 256)):
+        for l in (3, 2, 1, 0):
+            row = t[off + l * 16: off + l * 16 + 8]
+            print(f"warp{w} l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
 
 
 def debug_timestamps(N=1 << 18):

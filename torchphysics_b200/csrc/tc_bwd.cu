@@ -76,6 +76,7 @@ struct BwdArgs {
   const float *gu, *gdu, *glap;
   double* gacc;
   const float* ckpt;   // per tile: L x 4 arrays x 64 x 32 floats
+  long long* dbg;      // development: timestamps of one tile
 };
 
 // lane receives the sum over all 32 lanes of v[lane & 3]
@@ -251,39 +252,134 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         for (int i = 0; i < B_NW; ++i) c[s][i] = __ldg(base + (s * HP + i) * TILE);
     };
 
+    // adjoints of the pre-activation streams of a layer from the adjoints of its activation streams (thread-local)
+    auto zbar = [&](const float (&c)[S][B_NW], const float (&ga)[S][B_NW], float (&zb)[S][B_NW]) {
+#pragma unroll
+      for (int i = 0; i < B_NW; ++i) {
+        const float t = c[0][i];
+        const float s1 = fmaf(-t, t, 1.0f), s2 = -2.0f * t * s1;
+        float v0 = ga[0][i] * s1, qq = 0.0f;
+        const float gl = LAP ? ga[S - 1][i] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          const float dz = c[1 + k][i];
+          v0 = fmaf(ga[1 + k][i] * s2, dz, v0);
+          float vk = ga[1 + k][i] * s1;
+          if (LAP) {
+            qq = fmaf(lapw[k] * dz, dz, qq);
+            vk = fmaf(2.0f * lapw[k] * gl * s2, dz, vk);
+          }
+          zb[1 + k][i] = vk;
+        }
+        if (LAP) {
+          const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
+          v0 = fmaf(gl, fmaf(s3, qq, s2 * c[S - 1][i]), v0);
+          zb[S - 1][i] = gl * s1;
+        }
+        zb[0][i] = v0;
+      }
+    };
+    // in: adjoint product of the previous step, rows of this warp's stream -> exchange buffer -> all streams of
+    // this thread's neurons
+    auto fetch_adjoint = [&](float (&ga)[S][B_NW]) {
+      mbar_wait(&bar_d, ph_d);
+      ph_d ^= 1;
+      fence_after();
+      if (owner) {
+        float w[B_CH];
+        tmem_ld16(tD + jc, w);
+#pragma unroll
+        for (int v = 0; v < B_CH / 4; ++v)
+          *reinterpret_cast<float4*>(ex_own + 4 * v) = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+      }
+      named_bar_sync(barid, 128);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const float4 v4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * BXP);
+        ga[s][0] = v4.x; ga[s][1] = v4.y; ga[s][2] = v4.z; ga[s][3] = v4.w;
+      }
+    };
+    // hand Zbar of layer l >= 1 to the two products: transposed operands of the gradient product (with the
+    // activation jets of layer l - 1), TMEM A operand of the adjoint product
+    auto emit = [&](const float (&zb)[S][B_NW], const float (&cprev)[S][B_NW]) {
+      float ap[S][B_NW];
+      jets(cprev, ap);
+      if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
+        mbar_wait(&bar_f, ph_f);
+        ph_f ^= 1;
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int i = 0; i < B_NW; ++i) {
+          const float zh = tf32_hi(zb[s][i]);
+          Zt[s * 4096 + i * 32 + xo[i]] = zh;
+          Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
+          const float ah = tf32_hi(ap[s][i]);
+          At[s * 2048 + i * 32 + xo[i]] = ah;
+          At[8192 + s * 2048 + i * 32 + xo[i]] = ap[s][i] - ah;
+        }
+        *reinterpret_cast<float4*>(ex_cmp + s * TILE * BXP) = make_float4(zb[s][0], zb[s][1], zb[s][2], zb[s][3]);
+      }
+      dw_pending = true;
+      named_bar_sync(barid, 128);
+      if (owner) {
+        float hi[B_CH], lo[B_CH];
+#pragma unroll
+        for (int v = 0; v < B_CH / 4; ++v) {
+          const float4 w4 = *reinterpret_cast<const float4*>(ex_own + 4 * v);
+          hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < B_CH; ++i) {
+          const float h = tf32_hi(hi[i]);
+          lo[i] = hi[i] - h;
+          hi[i] = h;
+        }
+        tmem_st16(tAh + jc, hi);
+        tmem_st16(tAl + jc, lo);
+        tmem_wait_st();
+      }
+      fence_async_smem();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a);
+    };
+    auto add_bias = [&](int l, const float (&zb)[S][B_NW]) {
+      const float r = reduce4(zb[0][0], zb[0][1], zb[0][2], zb[0][3], lane);
+      if (lane < B_NW) acc[ACC_DB + l * HP + jn + lane] += r;
+    };
+
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gp = tile * TILE + lane;
       const bool valid = gp < a.n;
       const float* ck_tile = a.ckpt + (size_t)tile * ((size_t)L * 4 * HP * TILE);
-      float ck[S][B_NW], ckp[S][B_NW];       // checkpoints of layer l and of layer l - 1
+      float ck[S][B_NW], ckn[S][B_NW];       // checkpoints of the current layer and of the one below (prefetched)
       load_ck(ck_tile, L - 1, ck);
-      if (L >= 2) load_ck(ck_tile, L - 2, ckp);
-      float xr[MAXIO];
+      load_ck(ck_tile, L - 2, ckn);
+      // ------------------------------------------------ output layer + last hidden layer (l = L - 1)
+      {
+        float ga[S][B_NW], zb[S][B_NW];
+        {
+          float g[S][MAXIO];                 // adjoints of this point's output streams
 #pragma unroll
-      for (int c = 0; c < MAXIO; ++c) xr[c] = (valid && c < d_in) ? __ldg(a.x + gp * d_in + c) : 0.0f;
-      float g[S][MAXIO];                     // adjoints of this point's output streams
+          for (int o = 0; o < MAXIO; ++o) {
+            const bool on = valid && o < d_out;
+            g[0][o] = (on && a.gu) ? __ldg(a.gu + gp * d_out + o) : 0.0f;
 #pragma unroll
-      for (int o = 0; o < MAXIO; ++o) {
-        const bool on = valid && o < d_out;
-        g[0][o] = (on && a.gu) ? __ldg(a.gu + gp * d_out + o) : 0.0f;
+            for (int k = 0; k < ND; ++k) g[1 + k][o] = (on && a.gdu) ? __ldg(a.gdu + (gp * d_out + o) * ND + k) : 0.0f;
+            if (LAP) g[S - 1][o] = (on && a.glap) ? __ldg(a.glap + gp * d_out + o) : 0.0f;
+          }
+          if (warp == 0) {                   // output bias: sum of the value-stream adjoints
 #pragma unroll
-        for (int k = 0; k < ND; ++k) g[1 + k][o] = (on && a.gdu) ? __ldg(a.gdu + (gp * d_out + o) * ND + k) : 0.0f;
-        if (LAP) g[S - 1][o] = (on && a.glap) ? __ldg(a.glap + gp * d_out + o) : 0.0f;
-      }
-      if (warp == 0) {                       // output bias: sum of the value-stream adjoints
+            for (int o = 0; o < MAXIO; ++o) {
+              float sum = g[0][o];
 #pragma unroll
-        for (int o = 0; o < MAXIO; ++o) {
-          float s = g[0][o];
-#pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-          if (lane == 0 && o < d_out) acc[ACC_BL + o] += s;
-        }
-      }
-
-      for (int l = L - 1; l >= 0; --l) {
-        float ga[S][B_NW];                   // adjoints of the activation streams of layer l
-        if (l == L - 1) {
-          // output layer: u_s = WL a_s (+ bL): adjoint and gradient are thread-local
+              for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+              if (lane == 0 && o < d_out) acc[ACC_BL + o] += sum;
+            }
+          }
+          // u_s = WL a_s (+ bL): adjoint and gradient are thread-local
           float al[S][B_NW];
           jets(ck, al);
 #pragma unroll
@@ -306,119 +402,43 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
               const float r = reduce4(wg[0], wg[1], wg[2], wg[3], lane);
               if (lane < B_NW) acc[ACC_WL + o * HP + jn + lane] += r;
             }
-        } else {
-          // ---- in: adjoint product of the previous step, rows of this warp's stream -> exchange buffer
-          mbar_wait(&bar_d, ph_d);
-          ph_d ^= 1;
-          fence_after();
-          if (owner) {
-            float w[B_CH];
-            tmem_ld16(tD + jc, w);
-#pragma unroll
-            for (int v = 0; v < B_CH / 4; ++v)
-              *reinterpret_cast<float4*>(ex_own + 4 * v) = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-          }
-          named_bar_sync(barid, 128);
-#pragma unroll
-          for (int s = 0; s < S; ++s) {
-            const float4 v4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * BXP);
-            ga[s][0] = v4.x; ga[s][1] = v4.y; ga[s][2] = v4.z; ga[s][3] = v4.w;
-          }
         }
-        // ---- compute: adjoints of the pre-activation streams (thread-local)
-        float zb[S][B_NW];
+        zbar(ck, ga, zb);
+        add_bias(L - 1, zb);
+        emit(zb, ckn);
+      }
+      // ------------------------------------------------ hidden layers l = L - 2 .. 1 (ck holds layer l)
+      for (int l = L - 2; l >= 1; --l) {
+        float ga[S][B_NW], zb[S][B_NW];
 #pragma unroll
-        for (int i = 0; i < B_NW; ++i) {
-          const float t = ck[0][i];
-          const float s1 = fmaf(-t, t, 1.0f), s2 = -2.0f * t * s1;
-          float v0 = ga[0][i] * s1, qq = 0.0f;
-          const float gl = LAP ? ga[S - 1][i] : 0.0f;
+        for (int s = 0; s < S; ++s)
 #pragma unroll
-          for (int k = 0; k < ND; ++k) {
-            const float dz = ck[1 + k][i];
-            v0 = fmaf(ga[1 + k][i] * s2, dz, v0);
-            float vk = ga[1 + k][i] * s1;
-            if (LAP) {
-              qq = fmaf(lapw[k] * dz, dz, qq);
-              vk = fmaf(2.0f * lapw[k] * gl * s2, dz, vk);
-            }
-            zb[1 + k][i] = vk;
+          for (int i = 0; i < B_NW; ++i) ck[s][i] = ckn[s][i];
+        load_ck(ck_tile, l - 1, ckn);        // behind the wait for the adjoint product
+        fetch_adjoint(ga);
+        zbar(ck, ga, zb);
+        add_bias(l, zb);
+        emit(zb, ckn);
+      }
+      // ------------------------------------------------ first layer: z = W0 x + b0, d_k z = W0[:, dcol_k], L z = 0
+      {
+        float ga[S][B_NW], zb[S][B_NW];
+        fetch_adjoint(ga);
+        zbar(ckn, ga, zb);
+        add_bias(0, zb);
+        float rk[NDX];
+#pragma unroll
+        for (int k = 0; k < ND; ++k) rk[k] = reduce4(zb[1 + k][0], zb[1 + k][1], zb[1 + k][2], zb[1 + k][3], lane);
+#pragma unroll
+        for (int cc = 0; cc < MAXIO; ++cc)
+          if (cc < d_in) {
+            const float xc = valid ? __ldg(a.x + gp * d_in + cc) : 0.0f;
+            float r = reduce4(zb[0][0] * xc, zb[0][1] * xc, zb[0][2] * xc, zb[0][3] * xc, lane);
+#pragma unroll
+            for (int k = 0; k < ND; ++k)
+              if (dcol[k] == cc) r += rk[k];
+            if (lane < B_NW) acc[ACC_W0 + cc * HP + jn + lane] += r;
           }
-          if (LAP) {
-            const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
-            v0 = fmaf(gl, fmaf(s3, qq, s2 * ck[S - 1][i]), v0);
-            zb[S - 1][i] = gl * s1;
-          }
-          zb[0][i] = v0;
-        }
-        {                                    // bias gradient of layer l
-          const float r = reduce4(zb[0][0], zb[0][1], zb[0][2], zb[0][3], lane);
-          if (lane < B_NW) acc[ACC_DB + l * HP + jn + lane] += r;
-        }
-        if (l > 0) {
-          float ap[S][B_NW];                 // activation jets of layer l - 1 = the other operand of dW_l
-          jets(ckp, ap);
-          if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
-            mbar_wait(&bar_f, ph_f);
-            ph_f ^= 1;
-          }
-#pragma unroll
-          for (int s = 0; s < S; ++s) {
-#pragma unroll
-            for (int i = 0; i < B_NW; ++i) {
-              const float zh = tf32_hi(zb[s][i]);
-              Zt[s * 4096 + i * 32 + xo[i]] = zh;
-              Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
-              const float ah = tf32_hi(ap[s][i]);
-              At[s * 2048 + i * 32 + xo[i]] = ah;
-              At[8192 + s * 2048 + i * 32 + xo[i]] = ap[s][i] - ah;
-            }
-            *reinterpret_cast<float4*>(ex_cmp + s * TILE * BXP) = make_float4(zb[s][0], zb[s][1], zb[s][2], zb[s][3]);
-          }
-          dw_pending = true;
-          named_bar_sync(barid, 128);
-          // ---- out: Zbar rows of this warp's stream -> TMEM A operand (hi / lo)
-          if (owner) {
-            float hi[B_CH], lo[B_CH];
-#pragma unroll
-            for (int v = 0; v < B_CH / 4; ++v) {
-              const float4 w4 = *reinterpret_cast<const float4*>(ex_own + 4 * v);
-              hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < B_CH; ++i) {
-              const float h = tf32_hi(hi[i]);
-              lo[i] = hi[i] - h;
-              hi[i] = h;
-            }
-            tmem_st16(tAh + jc, hi);
-            tmem_st16(tAl + jc, lo);
-            tmem_wait_st();
-          }
-          fence_async_smem();
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_a);
-          // next step: layer l - 1 becomes the current layer; fetch the checkpoints of layer l - 2 behind the MMAs
-#pragma unroll
-          for (int s = 0; s < S; ++s)
-#pragma unroll
-            for (int i = 0; i < B_NW; ++i) ck[s][i] = ckp[s][i];
-          if (l >= 2) load_ck(ck_tile, l - 2, ckp);
-        } else {
-          // layer 0: z = W0 x + b0, d_k z = W0[:, dcol_k], L z = 0
-#pragma unroll
-          for (int cc = 0; cc < MAXIO; ++cc)
-            if (cc < d_in) {
-              float r = reduce4(zb[0][0] * xr[cc], zb[0][1] * xr[cc], zb[0][2] * xr[cc], zb[0][3] * xr[cc], lane);
-#pragma unroll
-              for (int k = 0; k < ND; ++k) {
-                const float rk = reduce4(zb[1 + k][0], zb[1 + k][1], zb[1 + k][2], zb[1 + k][3], lane);
-                if (dcol[k] == cc) r += rk;
-              }
-              if (lane < B_NW) acc[ACC_W0 + cc * HP + jn + lane] += r;
-            }
-        }
       }
     }
     if (dw_pending) {                        // the last gradient product of this CTA
@@ -527,6 +547,7 @@ int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet
   a.lay32 = lay32;
   a.jet = jet;
   a.img = img; a.gacc = gacc; a.ckpt = ckpt;
+  a.dbg = g_tc_debug;
   const size_t per_tile = ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
   if (saved) {
     const size_t need = (size_t)((n + TILE - 1) / TILE) * per_tile;
