@@ -176,7 +176,7 @@ def run_native(args):
     fs = [source(x) for x in xs]
     flat = torch.zeros(n_theta + 1, dtype=torch.float32, device=dev)
     launches = {"n": 0}
-    # activation-jet checkpoints: the forward kernel saves them (8 KB / point), the reverse kernel reads them
+    # activation-jet checkpoints: the forward kernel saves them (4 KB / point), the reverse kernel reads them
     saved_bytes = eng.saved_bytes(spec, N)
     saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev) if saved_bytes else None
 
@@ -296,14 +296,20 @@ def run_native(args):
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01c_tcbwd_raw.csv (4.313 GB for
+                         # 2^20 points: the 4 KB/point of saved activation jets + points + adjoints), scaled to this N
+                         "traffic": 4.313e9 * N / 2 ** 20, "traffic_unit": "bytes/launch",
+                         "peak_source": peak_src,
                          "algorithmic_flop_per_point": 2 * F_FWD, "ms_per_launch": ms_bwd,
                          "forward_kernel_ms": ms_fwd,
                          "tf32_issue_factor": 3,
                          "note": "FLOP = algorithmic GEMM FLOP of SURVEY 8(d) (reverse = 2 x forward); the kernel "
-                                 "issues 3 tf32 products per algorithmic product (fp32-accurate split) and tf32 runs at "
-                                 "half the bf16 rate (1.10 PFLOP/s measured with scripts/umma_probe2.cu), so frac = 1 "
-                                 "would need 6x the bf16 peak; the tensor-pipe share is in profiles/"},
+                                 "issues 3 tf32 products per algorithmic product (4 for dW; fp32-accurate split) and tf32 "
+                                 "runs at half the bf16 rate (1.10 PFLOP/s measured with scripts/umma_probe2.cu), so the "
+                                 "ceiling of frac is ~0.13.  ncu (profiles/r01c): tensor pipe active 20 %, shared-memory "
+                                 "LSU wavefronts 41 % of peak plus the UMMA operand reads of the gradient product "
+                                 "(~240 KB/tile-layer): the kernel is bound by shared-memory bandwidth (operand "
+                                 "transposition for dW + stream exchange), HBM 1.6 TB/s of 6.5"},
             "clocks": clk,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -76,6 +76,9 @@ def debug_bwd(N=1 << 18):
         for l in (3, 2, 1, 0):
             row = t[off + l * 16: off + l * 16 + 8]
             print(f"warp{w} l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
+    for l in (3, 2, 1):
+        row = t[512 + l * 4: 512 + l * 4 + 3]
+        print(f"mma l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(["a_w_ready", "issued", "d_done"], row) if v > 0))
 
 
 def debug_timestamps(N=1 << 18):

@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       mbar_wait(&bar_w, ph_w);
       ph_w ^= 1;
       fence_after();
+      const bool mdbg = a.dbg && blockIdx.x == 0 && g >= 2 * nphase && g < 3 * nphase && lane == 0;
+      if (mdbg) a.dbg[512 + l * 4 + 0] = clock64();
       if (elect_one()) {
         const uint32_t wh = ring, wl = wh + 16384u;
         const uint32_t tD = tmem + T_D, tAh = tmem + T_AH, tAl = tmem + T_AL;
@@ -177,10 +179,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         mma_commit(&bar_f);                  // ... the gradient product only gates the reuse of its operands
       }
       __syncwarp();
+      if (mdbg) a.dbg[512 + l * 4 + 1] = clock64();
       // the weight image is free once this phase's TMEM-operand products are done: fetch the next image
       // behind the activation warps' work
       mbar_wait(&bar_d, ph_d);
       ph_d ^= 1;
+      if (mdbg) a.dbg[512 + l * 4 + 2] = clock64();
       if (g + 1 < total_phases) {
         if (elect_one()) bulk_load(sm + so.wring, phase_src(g + 1), 32768u, &bar_w);
         __syncwarp();
@@ -281,10 +285,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     };
     // in: adjoint product of the previous step, rows of this warp's stream -> exchange buffer -> all streams of
     // this thread's neurons
+    long long* dbgp = nullptr;
+#define TPX_STAMP(e) do { if (dbgp) dbgp[e] = clock64(); } while (0)
     auto fetch_adjoint = [&](float (&ga)[S][B_NW]) {
+      TPX_STAMP(0);
       mbar_wait(&bar_d, ph_d);
       ph_d ^= 1;
       fence_after();
+      TPX_STAMP(1);
       if (owner) {
         float w[B_CH];
         tmem_ld16(tD + jc, w);
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
           *reinterpret_cast<float4*>(ex_own + 4 * v) = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
       }
       named_bar_sync(barid, 128);
+      TPX_STAMP(2);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         const float4 v4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * BXP);
@@ -304,10 +313,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     auto emit = [&](const float (&zb)[S][B_NW], const float (&cprev)[S][B_NW]) {
       float ap[S][B_NW];
       jets(cprev, ap);
+      TPX_STAMP(3);
       if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
         mbar_wait(&bar_f, ph_f);
         ph_f ^= 1;
       }
+      TPX_STAMP(4);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
 #pragma unroll
@@ -322,7 +333,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         *reinterpret_cast<float4*>(ex_cmp + s * TILE * BXP) = make_float4(zb[s][0], zb[s][1], zb[s][2], zb[s][3]);
       }
       dw_pending = true;
+      TPX_STAMP(5);
       named_bar_sync(barid, 128);
+      TPX_STAMP(6);
       if (owner) {
         float hi[B_CH], lo[B_CH];
 #pragma unroll
@@ -344,6 +357,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
+      TPX_STAMP(7);
+      if (dbgp) dbgp -= 16;
     };
     auto add_bias = [&](int l, const float (&zb)[S][B_NW]) {
       const float r = reduce4(zb[0][0], zb[0][1], zb[0][2], zb[0][3], lane);
@@ -353,6 +368,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gp = tile * TILE + lane;
       const bool valid = gp < a.n;
+      dbgp = (a.dbg && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x && lane == 0 && (warp == 0 || warp == 7))
+                 ? a.dbg + (warp == 0 ? 0 : 256) + (L - 1) * 16 : nullptr;
       const float* ck_tile = a.ckpt + (size_t)tile * ((size_t)L * 4 * HP * TILE);
       float ck[S][B_NW], ckn[S][B_NW];       // checkpoints of the current layer and of the one below (prefetched)
       load_ck(ck_tile, L - 1, ck);

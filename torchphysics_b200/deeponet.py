@@ -258,13 +258,13 @@ class DeepONetEvaluation:
         key = ("d", id(self.tev.du), k)
         if key not in self._cache:
             self._cache[key] = self._contract(self.tev.du[:, :, k])
-        return self._cache[key][..., list(out_cols)]
+        return jets.JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
 
     def second(self, out_cols):
         key = ("lap", id(self.tev.lap))
         if key not in self._cache:
             self._cache[key] = self._contract(self.tev.lap)
-        return self._cache[key][..., list(out_cols)]
+        return jets.JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
 
     def plain(self):
         if self._plain is None:

@@ -107,12 +107,24 @@ class JetEvaluation:
     def value(self):
         return self.u.reshape(*self.batch_shape, self.engine.d_out)
 
+    @staticmethod
+    def _columns(t, cols, axis):
+        """t[..., cols] along ``axis`` without advanced indexing when the columns are a contiguous range
+        (a view whose backward is a cheap slice instead of an index_put)."""
+        cols = list(cols)
+        if cols == list(range(t.shape[axis])):
+            return t
+        if cols == list(range(cols[0], cols[0] + len(cols))):
+            return t.narrow(axis, cols[0], len(cols))
+        return t.index_select(axis, torch.as_tensor(cols, device=t.device))
+
     def first(self, out_cols, in_col):
         k = self.spec.dcols.index(in_col)
-        return self.du[:, out_cols, k].reshape(*self.batch_shape, len(out_cols))
+        d = self.du.select(2, k)
+        return self._columns(d, out_cols, 1).reshape(*self.batch_shape, len(out_cols))
 
     def second(self, out_cols):
-        return self.lap[:, out_cols].reshape(*self.batch_shape, len(out_cols))
+        return self._columns(self.lap, out_cols, 1).reshape(*self.batch_shape, len(out_cols))
 
     def plain(self):
         """the same output through torch ops with a graph to the coordinate leaves."""

@@ -39,6 +39,11 @@ def _native(model_out, variables, need_lap):
     return ev, out_cols, per_var
 
 
+def _sum_last(t):
+    """sum over the output columns, keeping the axis (a single column is returned as is)."""
+    return t if t.shape[-1] == 1 else t.sum(dim=-1, keepdim=True)
+
+
 def _d(scalar, var):
     return torch.autograd.grad(scalar, var, create_graph=True)[0]
 
@@ -47,8 +52,8 @@ def grad(model_out, *derivative_variable):
     hit = _native(model_out, derivative_variable, False)
     if hit is not None:
         ev, oc, per_var = hit
-        pieces = [ev.first(oc, c).sum(dim=-1, keepdim=True) for cols in per_var for c in cols]
-        return torch.cat(pieces, dim=-1)
+        pieces = [_sum_last(ev.first(oc, c)) for cols in per_var for c in cols]
+        return pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=-1)
     u = plain_of(model_out)
     return torch.column_stack([_d(u.sum(), v) for v in derivative_variable])
 
@@ -57,7 +62,7 @@ def laplacian(model_out, *derivative_variable, grad=None):
     hit = _native(model_out, derivative_variable, True)
     if hit is not None:
         ev, oc, _ = hit
-        return ev.second(oc).sum(dim=-1, keepdim=True)
+        return _sum_last(ev.second(oc))
     u = plain_of(model_out)
     out = torch.zeros((*u.shape[:-1], 1), device=u.device)
     for v in derivative_variable:
