@@ -208,6 +208,35 @@ def deeponet(n_fn, n_pts, p, name, trunk_hidden=(32, 32), branch_hidden=(24, 24)
          p=np.array(p), trunk_hidden=np.array(trunk_hidden), branch_hidden=np.array(branch_hidden))
 
 
+# ---------------------------------------------------------------------------- normalised input
+def heat_normalized(hidden, n, name):
+    """heat residual with tp.models.Sequential(NormalizationLayer(domain), FCN): the trainable affine
+    input map of reference models/model.py:57-92 in front of the network."""
+    torch.manual_seed(12)
+    X, T, U = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
+    dom = tp.domains.Parallelogram(X, [0, 0], [2, 0], [0, 3]) * tp.domains.Interval(T, 0, 5)
+    model = tp.models.Sequential(tp.models.NormalizationLayer(dom), tp.models.FCN(X * T, U, hidden=hidden))
+    torch.manual_seed(13)
+    pts = tp.samplers.RandomUniformSampler(dom, n_points=n).make_static()
+    P = pts.sample_points()
+    xt = torch.cat([P.coordinates["x"], P.coordinates["t"]], dim=1).clone()
+    captured = {}
+
+    def residual(u, x, t):
+        captured["ut"] = tp.utils.grad(u, t)
+        captured["gx"] = tp.utils.grad(u, x)
+        captured["lap"] = tp.utils.laplacian(u, x)
+        captured["u"] = u
+        return captured["ut"] - 0.1 * captured["lap"]
+
+    cond = tp.conditions.PINNCondition(model, pts, residual)
+    model.zero_grad()
+    loss = cond(device="cpu")
+    loss.backward()
+    save(name, xt=xt, params=params_of(model), u=captured["u"], ut=captured["ut"], gx=captured["gx"],
+         lap=captured["lap"], loss=loss, dtheta=grads_of(model), hidden=np.array(hidden))
+
+
 # ---------------------------------------------------------------------------- domains
 def domains():
     X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
@@ -255,6 +284,7 @@ if __name__ == "__main__":
     heat((48, 48, 48), 193, "heat_3x48")
     navier_stokes((32, 32, 32), 130, "ns_3x32")
     deep_ritz((40, 40, 40, 40), 150, "ritz_4x40")
+    heat_normalized((48, 48, 48), 161, "heat_norm_3x48")
     deeponet(6, 40, 16, "deeponet_2x32")
     deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50)
     domains()

@@ -155,3 +155,47 @@ def test_generic_operator_semantics_on_plain_tensors():
     assert torch.allclose(tp.utils.div(v, a).reshape(-1), 2 * a[:, 0] + a[:, 0])
     j = tp.utils.jac(v, a)
     assert j.shape == (2, 2, 2) and torch.allclose(j[:, 1, 0], a[:, 1])
+
+
+def test_sequential_normalization_layer_is_folded_into_the_native_network():
+    """tp.models.Sequential(NormalizationLayer, FCN) against the real reference's outputs,
+    including the gradient of the trainable normalisation parameters."""
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import jets
+    G = load("heat_norm_3x48")
+    X, T, U = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
+    dom = tp.domains.Parallelogram(X, [0, 0], [2, 0], [0, 3]) * tp.domains.Interval(T, 0, 5)
+    norm = tp.models.NormalizationLayer(dom)
+    fcn = tp.models.FCN(X * T, U, hidden=(48,) * 3)
+    model = tp.models.Sequential(norm, fcn).cuda()
+    with torch.no_grad():
+        for q, w in zip(model.parameters(), G["params"]):
+            assert tuple(q.shape) == tuple(w.shape)
+            q.copy_(torch.as_tensor(w))
+    # the layer's own initialisation equals the reference's (bounding box -> (-1, 1)^d)
+    fresh = tp.models.NormalizationLayer(dom)
+    assert relerr(fresh.normalize.weight.detach().numpy(), G["params"][0]) < 1e-6
+    assert relerr(fresh.normalize.bias.detach().numpy(), G["params"][1]) < 1e-6
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["xt"]), X * T))
+    captured = {}
+
+    def residual(u, x, t):
+        captured.update(u=u, ut=tp.utils.grad(u, t), gx=tp.utils.grad(u, x), lap=tp.utils.laplacian(u, x))
+        return captured["ut"] - 0.1 * captured["lap"]
+
+    cond = tp.conditions.PINNCondition(model, sampler, residual)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", jets.TpxFallbackWarning)       # the native path must answer everything
+        for it in range(2):
+            model.zero_grad(set_to_none=True)
+            loss = cond(device="cuda")
+            loss.backward()
+    for name in ("u", "ut", "gx", "lap"):
+        assert relerr(captured[name].detach().cpu().numpy(), G[name]) < TOL, name
+    assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
+    for q, w in zip(model.parameters(), G["dtheta"]):
+        if w is None:
+            assert q.grad is None or float(q.grad.abs().max()) == 0.0
+        else:
+            assert relerr(q.grad.cpu().numpy(), w) < TOL

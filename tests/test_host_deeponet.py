@@ -17,7 +17,7 @@ class _TorchJetEngine:
     def __init__(self, lins):
         self.lins, self.d_out = lins, lins[-1].out_features
 
-    def jet(self, x, spec):
+    def jet(self, x, spec, params=None):
         n, nd = x.shape[0], spec.nd
         h = x
         d = [torch.zeros_like(x) for _ in range(nd)]

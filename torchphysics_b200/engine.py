@@ -114,10 +114,10 @@ class FcnEngine:
         if self._packed is None or key != self._packed_key or self._packed.device != params[0].device:
             dev = params[0].device
             buf = torch.empty(self.packed_floats, dtype=torch.float32, device=dev)
-            srcs = [p.detach() for p in params]
+            srcs = [p.detach().contiguous() for p in params]
             for s in srcs:
-                if s.dtype != torch.float32 or not s.is_contiguous():
-                    raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "parameters must be contiguous float32")
+                if s.dtype != torch.float32:
+                    raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "parameters must be float32")
             arr = _void_p_array(srcs)
             _lib.check(_lib.lib().tpx_fcn_pack(ctypes.byref(self.desc), arr, _lib.ptr(buf), _lib.stream_ptr()))
             self._packed, self._packed_key = buf, key
@@ -187,15 +187,17 @@ class FcnEngine:
         return grads
 
     # ---- autograd entry point --------------------------------------------------------
-    def jet(self, x, spec):
-        """(u, du, lap) as differentiable functions of the network parameters."""
+    def jet(self, x, spec, params=None):
+        """(u, du, lap) as differentiable functions of the network parameters.  ``params`` replaces the
+        modules' own tensors, e.g. a first layer with a NormalizationLayer folded in (``models.Sequential``)."""
         if not x.is_cuda:
             raise _lib.TpxError(_lib.TPX_E_ARG, "the native engine only runs on CUDA tensors")
         x = x.detach()
         if x.dtype != torch.float32:
             x = x.float()
         x = x.contiguous()
-        params = self.params()
+        if params is None:
+            params = self.params()
         return _FcnJetFn.apply(self, x, spec, *params)
 
 

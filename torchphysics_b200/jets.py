@@ -60,7 +60,7 @@ def warn_fallback(reason):
 class JetEvaluation:
     """One evaluation of a natively supported network on a batch of tracked points."""
 
-    def __init__(self, engine, x2d, batch_shape, leaf_cols, hints, hint_key, autograd_fn, spec):
+    def __init__(self, engine, x2d, batch_shape, leaf_cols, hints, hint_key, autograd_fn, spec, params=None):
         self.engine = engine
         self.x = x2d                        # (N, d_in) detached, contiguous
         self.batch_shape = tuple(batch_shape)
@@ -69,7 +69,8 @@ class JetEvaluation:
         self.autograd_fn = autograd_fn      # () -> plain autograd output (generic path)
         self._plain = None
         self.spec = spec
-        self.u, self.du, self.lap = engine.jet(x2d, spec)
+        self.params = params                # None: the engine's own module parameters
+        self.u, self.du, self.lap = engine.jet(x2d, spec, params)
 
     def columns_of(self, var):
         hit = self.leaf_cols.get(id(var))
@@ -97,7 +98,7 @@ class JetEvaluation:
         if len(cols) > 3:
             return False
         new = JetSpec(cols, lap_w)
-        u, du, lap = self.engine.jet(self.x, new)
+        u, du, lap = self.engine.jet(self.x, new, self.params)
         self.spec, self.du, self.lap = new, du, lap      # value stream: keep the first u
         self._u2 = u
         self.hints[self.hint_key] = new

@@ -128,24 +128,29 @@ class _NativeFcnMixin:
             object.__setattr__(self, "_engine", eng)
         return eng
 
-    def _evaluate(self, points):
-        """points: Points in model input order -> tensor (..., d_out) (JetTensor if native)."""
+    def _evaluate(self, points, input_space=None, first_layer=None, generic=None):
+        """points: Points in model input order -> tensor (..., d_out) (JetTensor if native).
+        ``first_layer`` = (W0, b0) tensors replacing the first Linear's (an affine input map folded in),
+        ``input_space`` the space whose columns ``points`` carries in that case."""
         x = points.as_tensor
         if not x.is_cuda:
             raise _lib.TpxError(_lib.TPX_E_ARG, "FCN evaluation runs on the sm_100a kernels only: the points "
                                 "must live on a CUDA device (there is no CPU path)")
         eng = self._native_engine()
+        seq = self.sequential
+        if generic is None:
+            generic = lambda: seq(x)  # noqa: E731
         if eng is False:
             if strict_native():
                 raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, self._engine_reason)
             jets.warn_fallback(self._engine_reason)
-            return self.sequential(x)
+            return generic()
         batch_shape = x.shape[:-1]
         x2d = x.detach().reshape(-1, x.shape[-1])
         leaves = getattr(points, "_coord_leaves", None)
         leaf_cols = {}
         if leaves is not None:
-            sl = self.input_space.column_slices()
+            sl = (self.input_space if input_space is None else input_space).column_slices()
             for name, leaf in leaves.items():
                 if name in sl:
                     leaf_cols[id(leaf)] = (leaf, list(range(sl[name].start, sl[name].stop)))
@@ -154,8 +159,10 @@ class _NativeFcnMixin:
         spec = hints.get(key) if leaves is not None else None
         if spec is None:
             spec = JetSpec()
-        seq = self.sequential
-        ev = jets.JetEvaluation(eng, x2d, batch_shape, leaf_cols, hints, key, lambda: seq(x), spec)
+        params = None
+        if first_layer is not None:
+            params = list(first_layer) + eng.params()[2:]
+        ev = jets.JetEvaluation(eng, x2d, batch_shape, leaf_cols, hints, key, generic, spec, params)
         return jets.JetTensor.wrap(ev.value(), ev, range(eng.d_out))
 
 
@@ -217,12 +224,42 @@ class Parallel(Model):
 
 
 class Sequential(Model):
+    """Chain of models (reference ``model.py:149-183``).  ``Sequential(NormalizationLayer, FCN)`` -- the
+    composition of the reference's examples -- is evaluated as ONE native network: the trainable affine
+    map is folded into the first layer (W0 Wn, W0 bn + b0 as differentiable torch expressions, so its
+    gradient still reaches ``normalize.weight`` / ``.bias``) and the jets are taken with respect to the
+    un-normalised coordinates."""
+
     def __init__(self, *models):
         super().__init__(models[0].input_space, models[-1].output_space)
         self.models = nn.ModuleList(models)
 
+    def _fused(self, points):
+        if len(self.models) != 2:
+            return None
+        norm, fcn = self.models
+        if not (isinstance(norm, NormalizationLayer) and isinstance(fcn, FCN)):
+            return None
+        if fcn.input_space.keys() != norm.output_space.keys() or not points.as_tensor.is_cuda:
+            return None
+        if fcn._native_engine() is False:
+            return None
+        # columns of the normalised point in the order the network wants them
+        src = norm.output_space.column_slices()
+        cols = [c for name in fcn.input_space for c in range(src[name].start, src[name].stop)]
+        lin0 = fcn.sequential[0]
+        Wn, bn = norm.normalize.weight[cols, :], norm.normalize.bias[cols]
+        first = (lin0.weight @ Wn, lin0.bias + lin0.weight @ bn)
+        x = points.as_tensor
+        out = fcn._evaluate(points, input_space=norm.input_space, first_layer=first,
+                            generic=lambda: fcn.sequential(norm.normalize(x)[..., cols]))
+        return Points(out, fcn.output_space)
+
     def forward(self, points):
         points = self._fix_points_order(points)
+        fused = self._fused(points)
+        if fused is not None:
+            return fused
         for m in self.models:
             points = m(points)
         return points
