@@ -127,6 +127,11 @@ int tpx_fcn_unpack_grads(const tpx_fcn_desc* net, const double* grad_acc, void* 
 #define TPX_SHAPE_INTERVAL 1      /* p = {lower, upper}                  domain1D/interval.py       */
 #define TPX_SHAPE_PARALLELOGRAM 2 /* p = {ox, oy, c1x, c1y, c2x, c2y}    domain2D/parallelogram.py  */
 #define TPX_SHAPE_CIRCLE 3        /* p = {cx, cy, r}                     domain2D/circle.py         */
+/* boundaries of the three primitives (membership = the reference's torch.isclose tests) */
+#define TPX_SHAPE_INTERVAL_BOUNDARY 4      /* p = {lower, upper}          interval.py:96-149        */
+#define TPX_SHAPE_INTERVAL_POINT 5         /* p = {side, normal}          interval.py:152-191       */
+#define TPX_SHAPE_PARALLELOGRAM_BOUNDARY 6 /* p as the parallelogram      parallelogram.py:159-291  */
+#define TPX_SHAPE_CIRCLE_BOUNDARY 7        /* p as the circle             circle.py:111-175         */
 #define TPX_MAX_SHAPES 8
 #define TPX_MAX_OPS 24
 #define TPX_OP_SHAPE 0 /* push membership of shapes[arg]; op word = opcode | arg << 8 */
@@ -178,6 +183,13 @@ int tpx_sample_uniform_reject(const tpx_shape* generator, const tpx_region* acce
  * arrangement (circle.py:70-99). */
 int tpx_sample_grid(const tpx_shape* shape, int64_t n, int32_t n1, int32_t n2, float* out, int32_t row_stride,
                     void* stream);
+
+/* Outward unit normals of a boundary shape at n points lying on it (rows of row_stride floats, the
+ * shape's columns); normals = n x dim floats.  Replaces BoundaryDomain.normal of interval.py:139-144,
+ * 181-186, parallelogram.py:248-286, circle.py:162-170 with the same float32 operation order (a
+ * parallelogram point that fails the reference's isclose tests gets the reference's NaN). */
+int tpx_boundary_normal(const tpx_shape* shape, const float* points, int64_t n, int32_t row_stride,
+                        float* normals, void* stream);
 
 /* Latin hypercube (samplers/random_samplers.py:203-221): keys = iid 63-bit sort keys (their
  * argsort is the random permutation of one axis); tpx_sample_lhs writes column c of row i

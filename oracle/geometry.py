@@ -144,3 +144,117 @@ def grid(dom, n):
         P = np.stack([rad * np.cos(phi, dtype=f32), rad * np.sin(phi, dtype=f32)], axis=1)
         return r * P + c
     raise ValueError(kind)
+
+
+# --------------------------------------------------------------------------------------
+# boundaries of the three primitives: ("boundary", dom), ("left", interval),
+# ("right", interval).  interval.py:96-191, parallelogram.py:159-291, circle.py:111-175
+# --------------------------------------------------------------------------------------
+def isclose(a, b):
+    """torch.isclose(a, b) with the default rtol=1e-5, atol=1e-8, float32."""
+    a, b = np.asarray(a, f32), np.asarray(b, f32)
+    return np.abs(a - b) <= (f32(1e-8) + f32(1e-5) * np.abs(b))
+
+
+def _bary(dom, pts):
+    o = np.asarray(dom[1], f32)
+    d1 = np.asarray(dom[2], f32) - o
+    d2 = np.asarray(dom[3], f32) - o
+    p = np.asarray(pts, f32) - o
+    det = d1[0] * d2[1] - d1[1] * d2[0]
+    bx = (d2[1] * p[:, 0] - d2[0] * p[:, 1]) / det
+    by = (d1[0] * p[:, 1] - d1[1] * p[:, 0]) / det
+    return o, d1, d2, bx, by
+
+
+def boundary_contains(bnd, pts):
+    pts = np.asarray(pts, f32)
+    kind, dom = bnd[0], bnd[1]
+    if kind in ("left", "right"):
+        return isclose(pts[:, 0], f32(dom[1] if kind == "left" else dom[2]))          # interval.py:161-165
+    if dom[0] == "interval":
+        return isclose(pts[:, 0], f32(dom[1])) | isclose(pts[:, 0], f32(dom[2]))      # interval.py:103-113
+    if dom[0] == "parallelogram":                                                      # parallelogram.py:166-181
+        _, _, _, bx, by = _bary(dom, pts)
+
+        def edge(c1, c2):
+            return (isclose(c1, f32(0)) | isclose(c1, f32(1))) & (c2 >= 0) & (c2 <= 1)
+        return edge(bx, by) | edge(by, bx)
+    if dom[0] == "circle":                                                             # circle.py:118-124
+        q = pts - np.asarray(dom[1], f32)
+        nrm = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1], dtype=f32)
+        return isclose(nrm, f32(dom[2]))
+    raise ValueError(bnd)
+
+
+def boundary_volume(bnd):
+    kind, dom = bnd[0], bnd[1]
+    if kind in ("left", "right"):
+        return f32(1)
+    if dom[0] == "interval":
+        return f32(2)
+    if dom[0] == "parallelogram":
+        o = np.asarray(dom[1], f32)
+        d1, d2 = np.asarray(dom[2], f32) - o, np.asarray(dom[3], f32) - o
+        return f32(2) * (np.sqrt(d1 @ d1, dtype=f32) + np.sqrt(d2 @ d2, dtype=f32))
+    if dom[0] == "circle":
+        return f32(2 * np.pi) * f32(dom[2])
+    raise ValueError(bnd)
+
+
+def _walk(dom, loc):
+    """parallelogram.py:220-246: walk the four sides, ``loc`` = arc length from the origin."""
+    o = np.asarray(dom[1], f32)
+    d1, d2 = np.asarray(dom[2], f32) - o, np.asarray(dom[3], f32) - o
+    s1, s2 = np.sqrt(d1 @ d1, dtype=f32), np.sqrt(d2 @ d2, dtype=f32)
+    loc = np.asarray(loc, f32).copy()
+    pts = np.zeros((len(loc), 2), f32)
+    for d, s in ((d1, s1), (d2, s2), (-d1, s1), (-d2, s2)):
+        scale = np.clip(loc / s, f32(0), f32(1))
+        pts += scale[:, None] * d
+        loc -= s
+    return pts + o
+
+
+def boundary_grid(bnd, n):
+    kind, dom = bnd[0], bnd[1]
+    if kind in ("left", "right"):
+        return np.full((n, 1), f32(dom[1] if kind == "left" else dom[2]), f32)
+    if dom[0] == "interval":                     # interval.py:128-137: upper, lower, upper, ...
+        return np.where(np.arange(n) % 2 == 1, f32(dom[1]), f32(dom[2])).astype(f32).reshape(-1, 1)
+    t = np.linspace(0, 1, n + 1, dtype=f32)[:-1]
+    if dom[0] == "parallelogram":
+        return _walk(dom, t * boundary_volume(bnd))
+    if dom[0] == "circle":                       # circle.py:143-160
+        phi = np.linspace(0, 2 * np.pi, n + 1, dtype=f32)[:-1]
+        c, r = np.asarray(dom[1], f32), f32(dom[2])
+        return np.stack([r * np.cos(phi, dtype=f32), r * np.sin(phi, dtype=f32)], axis=1) + c
+    raise ValueError(bnd)
+
+
+def boundary_normal(bnd, pts):
+    pts = np.asarray(pts, f32)
+    kind, dom = bnd[0], bnd[1]
+    if kind == "left":
+        return np.full((len(pts), 1), f32(-1))
+    if kind == "right":
+        return np.full((len(pts), 1), f32(1))
+    if dom[0] == "interval":                     # interval.py:139-144
+        return np.where(isclose(pts[:, 0], f32(dom[1])), f32(-1), f32(1)).reshape(-1, 1)
+    if dom[0] == "circle":                       # circle.py:162-170
+        return (pts - np.asarray(dom[1], f32)) / f32(dom[2])
+    if dom[0] == "parallelogram":                # parallelogram.py:248-286
+        _, d1, d2, bx, by = _bary(dom, pts)
+
+        def unit_normal(d):
+            v = np.array([-d[1], d[0]], f32)
+            return v / np.sqrt(v @ v, dtype=f32)
+        n1, n2 = unit_normal(d1), -unit_normal(d2)
+        out = np.zeros((len(pts), 2), f32)
+        for i in (0.0, 1.0):
+            sgn = f32(2 * i - 1)
+            out += n1 * np.where(isclose(by, f32(i)), sgn, f32(0))[:, None]
+            out += n2 * np.where(isclose(bx, f32(i)), sgn, f32(0))[:, None]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return out / np.sqrt(out[:, 0] * out[:, 0] + out[:, 1] * out[:, 1], dtype=f32)[:, None]
+    raise ValueError(bnd)

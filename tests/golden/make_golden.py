@@ -237,6 +237,49 @@ def heat_normalized(hidden, n, name):
          lap=captured["lap"], loss=loss, dtheta=grads_of(model), hidden=np.array(hidden))
 
 
+# ---------------------------------------------------------------------------- boundaries
+def boundaries():
+    """boundary domains of Interval / Parallelogram / Circle: membership, normals, grids, volumes
+    (reference interval.py:96-191, parallelogram.py:159-291, circle.py:111-175)."""
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    ival = tp.domains.Interval(T, -0.3, 0.8)
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    for nm, d in [("para", para), ("circ", circ), ("ival", ival)]:
+        b = d.boundary
+        for n in (1, 7, 50):
+            out[f"grid_{nm}_{n}"] = b.sample_grid(n).as_tensor
+        on = b.sample_grid(200).as_tensor
+        # candidates: exact boundary points, slightly perturbed ones (inside/outside isclose), far points
+        eps = torch.rand(on.shape, generator=g) * 4e-5 - 2e-5
+        far = torch.rand(on.shape, generator=g) * 3.0 - 1.5
+        cand = torch.cat([on, on + eps, on * (1 + 1e-6), far], dim=0)
+        out["cand_" + nm] = cand
+        out["in_" + nm] = b._contains(tp.spaces.Points(cand.clone(), d.space)).reshape(-1)
+        out["normal_" + nm] = b.normal(tp.spaces.Points(on.clone(), d.space))
+        out["on_" + nm] = on
+        out["vol_" + nm] = b.volume().reshape(-1)
+        torch.manual_seed(22)
+        r = b.sample_random_uniform(n=300)
+        out["n_random_" + nm] = np.array(len(r))
+        out["allin_random_" + nm] = np.array(bool(b._contains(r).all()))
+    for nm, b in [("left", ival.boundary_left), ("right", ival.boundary_right)]:
+        cand = out["cand_ival"]
+        out["in_" + nm] = b._contains(tp.spaces.Points(cand.clone(), T)).reshape(-1)
+        out["grid_" + nm] = b.sample_grid(5).as_tensor
+        out["normal_" + nm] = b.normal(tp.spaces.Points(b.sample_grid(5).as_tensor, T))
+        out["vol_" + nm] = b.volume().reshape(-1)
+    # a boundary condition as the examples write it: u = 0 on the boundary of the square x time
+    prod = para.boundary * ival
+    cand3 = torch.cat([out["cand_para"][:600], torch.rand(600, 1, generator=g) * 1.5 - 0.5], dim=1)
+    out["cand3"] = cand3
+    out["in_prod"] = prod._contains(tp.spaces.Points(cand3.clone(), X * T)).reshape(-1)
+    out["vol_prod"] = prod.volume().reshape(-1)
+    save("boundaries", **out)
+
+
 # ---------------------------------------------------------------------------- domains
 def domains():
     X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
@@ -288,3 +331,4 @@ if __name__ == "__main__":
     deeponet(6, 40, 16, "deeponet_2x32")
     deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50)
     domains()
+    boundaries()

@@ -5,8 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import geometry
-from tests.golden_io import load
+from oracle import geometry, ref_autograd
+from tests.golden_io import load, relerr
 from tests.test_oracle_golden import DOMS
 
 pytestmark = pytest.mark.gpu
@@ -186,3 +186,90 @@ def test_empty_and_error_paths():
     far = tp.domains.Circle(X, [10, 10], 0.1)
     with pytest.raises(RuntimeError):
         (sq & far).sample_random_uniform(n=5, device="cuda")
+
+
+# ---------------------------------------------------------------------------- boundaries
+def _boundary_domains(tp):
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    ival = tp.domains.Interval(T, -0.3, 0.8)
+    return X, T, para, circ, ival
+
+
+def test_boundary_membership_normals_grids_match_reference():
+    import torchphysics_b200 as tp
+    from tests.test_oracle_golden import BNDS
+    G = load("boundaries")
+    X, T, para, circ, ival = _boundary_domains(tp)
+    for nm, d in (("para", para), ("circ", circ), ("ival", ival)):
+        b = d.boundary
+        assert b.dim == d.dim - 1 and b.space == d.space
+        cand = tp.spaces.Points(torch.from_numpy(G["cand_" + nm]).cuda(), d.space)
+        assert np.array_equal(b._contains(cand).reshape(-1).cpu().numpy(), G["in_" + nm]), nm      # bit exact
+        assert abs(float(b.volume()) - float(G["vol_" + nm])) < 1e-6 * float(G["vol_" + nm])
+        for n in (1, 7, 50):
+            got = b.sample_grid(n, device="cuda").as_tensor.cpu().numpy()
+            assert np.allclose(got, G[f"grid_{nm}_{n}"], rtol=1e-6, atol=1e-6), (nm, n)
+        nrm = b.normal(tp.spaces.Points(torch.from_numpy(G["on_" + nm]).cuda(), d.space)).cpu().numpy()
+        want = G["normal_" + nm]
+        assert np.array_equal(np.isnan(nrm), np.isnan(want)), nm
+        assert np.allclose(nrm, want, rtol=1e-6, atol=1e-7, equal_nan=True), nm
+        # random boundary points: right count, on the boundary (distance, not the reference's brittle isclose)
+        torch.manual_seed(5)
+        pts = b.sample_random_uniform(n=4000, device="cuda").as_tensor.cpu().numpy()
+        assert pts.shape == (4000, d.space.dim)
+        if nm == "circ":
+            r = np.linalg.norm(pts - np.array([0.1, -0.2], np.float32), axis=1)
+            assert np.abs(r - 0.9).max() < 1e-6
+            ang = np.arctan2(pts[:, 1] + 0.2, pts[:, 0] - 0.1)
+            assert np.histogram(ang, bins=8, range=(-np.pi, np.pi))[0].min() > 380            # uniform in angle
+        elif nm == "ival":
+            assert set(np.unique(pts).tolist()) == {np.float32(-0.3).item(), np.float32(0.8).item()}
+            assert 1800 < (pts == np.float32(-0.3)).sum() < 2200
+        else:
+            _, _, _, bx, by = geometry._bary(BNDS["para"][1], pts)
+            on_edge = np.minimum(np.minimum(np.abs(bx), np.abs(bx - 1)), np.minimum(np.abs(by), np.abs(by - 1)))
+            assert on_edge.max() < 1e-6 and bx.min() > -1e-6 and bx.max() < 1 + 1e-6
+    for nm, b in (("left", ival.boundary_left), ("right", ival.boundary_right)):
+        cand = tp.spaces.Points(torch.from_numpy(G["cand_ival"]).cuda(), T)
+        assert np.array_equal(b._contains(cand).reshape(-1).cpu().numpy(), G["in_" + nm])
+        g = b.sample_grid(5, device="cuda")
+        assert np.allclose(g.as_tensor.cpu().numpy(), G["grid_" + nm])
+        assert np.allclose(b.normal(g).cpu().numpy(), G["normal_" + nm])
+        assert float(b.volume()) == 1.0
+    prod = para.boundary * ival
+    cand3 = tp.spaces.Points(torch.from_numpy(G["cand3"]).cuda(), X * T)
+    assert np.array_equal(prod._contains(cand3).reshape(-1).cpu().numpy(), G["in_prod"])
+    assert abs(float(prod.volume()) - float(G["vol_prod"])) < 1e-5
+    s = tp.samplers.RandomUniformSampler(prod, n_points=1000).sample_points(device="cuda")
+    assert s.as_tensor.shape == (1000, 3) and bool(ival._contains(s).all())
+
+
+def test_boundary_condition_trains_through_native_path():
+    """a Dirichlet + Neumann boundary condition as the reference's examples write it (poisson-equation.ipynb):
+    value and normal derivative of the native FCN on sampled boundary points, gradient to the parameters."""
+    import torchphysics_b200 as tp
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    model = tp.models.FCN(X, U, hidden=(32, 32)).cuda()
+    sampler = tp.samplers.RandomUniformSampler(sq.boundary, n_points=512).make_static()
+
+    def residual(u, x):
+        n = sq.boundary.normal(x)
+        return u - 1.0 + tp.utils.normal_derivative(u, n, x)
+
+    cond = tp.conditions.PINNCondition(model, sampler, residual)
+    loss = cond(device="cuda")
+    loss.backward()
+    x = sampler.sample_points(device="cuda").as_tensor.detach().cpu()
+    assert bool(((x == 0) | (x == 1)).any(dim=1).all())              # unit square: exact edges
+    seq = ref_autograd.fcn_from_params([p.detach().cpu().numpy() for p in model._native_engine().params()])
+    cols, xin = ref_autograd.track(x, [("x", 2)])
+    u = seq(xin)
+    nrm = torch.from_numpy(geometry.boundary_normal(("boundary", ("parallelogram", [0, 0], [1, 0], [0, 1])), x.numpy()))
+    want = ref_autograd.pinn_loss(u - 1.0 + ref_autograd.normal_derivative(u, nrm, cols["x"]))
+    assert abs(float(loss) - float(want)) < 1e-5 * abs(float(want))
+    gs = torch.autograd.grad(want, ref_autograd.linear_params(seq))
+    for p, w in zip(model._native_engine().params(), gs):
+        assert relerr(p.grad.cpu().numpy(), w.numpy()) < 1e-5

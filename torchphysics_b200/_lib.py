@@ -39,6 +39,7 @@ EXPORTS = (
     "tpx_sample_reject_workspace_bytes",
     "tpx_sample_uniform_reject",
     "tpx_sample_grid",
+    "tpx_boundary_normal",
     "tpx_sample_keys",
     "tpx_sample_lhs",
     "tpx_union_pick",
@@ -47,6 +48,10 @@ EXPORTS = (
 TPX_SHAPE_INTERVAL = 1
 TPX_SHAPE_PARALLELOGRAM = 2
 TPX_SHAPE_CIRCLE = 3
+TPX_SHAPE_INTERVAL_BOUNDARY = 4
+TPX_SHAPE_INTERVAL_POINT = 5
+TPX_SHAPE_PARALLELOGRAM_BOUNDARY = 6
+TPX_SHAPE_CIRCLE_BOUNDARY = 7
 TPX_MAX_SHAPES = 8
 TPX_MAX_OPS = 24
 TPX_OP_SHAPE, TPX_OP_AND, TPX_OP_OR, TPX_OP_NOT = 0, 1, 2, 3

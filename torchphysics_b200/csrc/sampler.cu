@@ -37,6 +37,50 @@ struct Philox {
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r & 0x00FFFFFFu) * 5.9604644775390625e-8f; }
 
 // ---------------------------------------------------------------- shapes
+// torch.isclose(a, b), rtol = 1e-5, atol = 1e-8, float32
+__device__ __forceinline__ bool isclose32(float a, float b) {
+  return fabsf(__fsub_rn(a, b)) <= __fadd_rn(1e-8f, __fmul_rn(1e-5f, fabsf(b)));
+}
+// barycentric coordinates of a point in a parallelogram (parallelogram.py:96-103, Cramer's rule)
+__device__ __forceinline__ void bary(const tpx_shape& s, const float* q, float& bx, float& by) {
+  const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
+  const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
+  const float px = __fsub_rn(q[0], s.p[0]), py = __fsub_rn(q[1], s.p[1]);
+  const float det = __fsub_rn(__fmul_rn(d1x, d2y), __fmul_rn(d1y, d2x));
+  bx = __fdiv_rn(__fsub_rn(__fmul_rn(d2y, px), __fmul_rn(d2x, py)), det);
+  by = __fdiv_rn(__fsub_rn(__fmul_rn(d1x, py), __fmul_rn(d1y, px)), det);
+}
+// point at arc length `loc` along the four sides of a parallelogram (parallelogram.py:220-246)
+__device__ __forceinline__ void para_walk(const tpx_shape& s, float loc, float* q) {
+  const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
+  const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
+  const float s1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
+  const float s2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+  float x = 0.0f, y = 0.0f;
+  const float dx[4] = {d1x, d2x, -d1x, -d2x}, dy[4] = {d1y, d2y, -d1y, -d2y}, len[4] = {s1, s2, s1, s2};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float sc = fminf(fmaxf(__fdiv_rn(loc, len[k]), 0.0f), 1.0f);
+    x = __fadd_rn(x, __fmul_rn(sc, dx[k]));
+    y = __fadd_rn(y, __fmul_rn(sc, dy[k]));
+    loc = __fsub_rn(loc, len[k]);
+  }
+  q[0] = __fadd_rn(x, s.p[0]);
+  q[1] = __fadd_rn(y, s.p[1]);
+}
+__device__ __forceinline__ float para_perimeter(const tpx_shape& s) {
+  const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
+  const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
+  const float s1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
+  const float s2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+  return __fmul_rn(2.0f, __fadd_rn(s1, s2));
+}
+// element j of torch.linspace(0, 1, steps) in float32
+__device__ __forceinline__ float lin01(int64_t j, int64_t steps) {
+  const float step = 1.0f / (float)(steps - 1);
+  return (j < steps / 2) ? (float)j * step : 1.0f - step * (float)(steps - 1 - j);
+}
+
 __device__ __forceinline__ bool shape_contains(const tpx_shape& s, const float* row) {
   const float* q = row + s.col;
   switch (s.kind) {
@@ -56,6 +100,21 @@ __device__ __forceinline__ bool shape_contains(const tpx_shape& s, const float* 
       const float dx = __fsub_rn(q[0], s.p[0]), dy = __fsub_rn(q[1], s.p[1]);
       const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
       return nrm <= s.p[2];
+    }
+    case TPX_SHAPE_INTERVAL_BOUNDARY:
+      return isclose32(q[0], s.p[0]) || isclose32(q[0], s.p[1]);
+    case TPX_SHAPE_INTERVAL_POINT:
+      return isclose32(q[0], s.p[0]);
+    case TPX_SHAPE_PARALLELOGRAM_BOUNDARY: {
+      float bx, by;
+      bary(s, q, bx, by);
+      const bool xe = (isclose32(bx, 0.0f) || isclose32(bx, 1.0f)) && by >= 0.0f && by <= 1.0f;
+      const bool ye = (isclose32(by, 0.0f) || isclose32(by, 1.0f)) && bx >= 0.0f && bx <= 1.0f;
+      return xe || ye;
+    }
+    case TPX_SHAPE_CIRCLE_BOUNDARY: {
+      const float dx = __fsub_rn(q[0], s.p[0]), dy = __fsub_rn(q[1], s.p[1]);
+      return isclose32(__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), s.p[2]);
     }
     default:
       return false;
@@ -77,7 +136,9 @@ __device__ __forceinline__ bool region_contains(const tpx_region& rg, const floa
   return (stack & 1u) != 0;
 }
 
-__device__ __forceinline__ int shape_dim(int kind) { return kind == TPX_SHAPE_INTERVAL ? 1 : 2; }
+__device__ __host__ __forceinline__ int shape_dim(int kind) {
+  return (kind == TPX_SHAPE_INTERVAL || kind == TPX_SHAPE_INTERVAL_BOUNDARY || kind == TPX_SHAPE_INTERVAL_POINT) ? 1 : 2;
+}
 
 // uniform sample of a shape from one Philox block (reference sample_random_uniform:
 // interval.py:45-55, parallelogram.py:105-117, circle.py:52-68)
@@ -103,6 +164,23 @@ __device__ __forceinline__ void shape_sample(const tpx_shape& s, uint4 r, float*
       q[1] = __fadd_rn(__fmul_rn(rr, sn), s.p[1]);
       break;
     }
+    case TPX_SHAPE_INTERVAL_BOUNDARY:       // interval.py:115-126
+      q[0] = u01(r.x) < 0.5f ? s.p[0] : s.p[1];
+      break;
+    case TPX_SHAPE_INTERVAL_POINT:          // interval.py:167-176
+      q[0] = s.p[0];
+      break;
+    case TPX_SHAPE_PARALLELOGRAM_BOUNDARY:  // parallelogram.py:183-200
+      para_walk(s, __fmul_rn(u01(r.x), para_perimeter(s)), q);
+      break;
+    case TPX_SHAPE_CIRCLE_BOUNDARY: {       // circle.py:126-141
+      const float phi = __fmul_rn(6.283185307179586f, u01(r.x));
+      float sn, cs;
+      sincosf(phi, &sn, &cs);
+      q[0] = __fadd_rn(__fmul_rn(s.p[2], cs), s.p[0]);
+      q[1] = __fadd_rn(__fmul_rn(s.p[2], sn), s.p[1]);
+      break;
+    }
     default: break;
   }
 }
@@ -121,7 +199,7 @@ __global__ void sample_kernel(tpx_shape s, uint64_t seed, uint64_t offset, int64
     shape_sample(s, ph(offset + (uint64_t)i, 0), q);
     float* row = out + i * stride + s.col;
     row[0] = q[0];
-    if (s.kind != TPX_SHAPE_INTERVAL) row[1] = q[1];
+    if (shape_dim(s.kind) > 1) row[1] = q[1];
   }
 }
 
@@ -268,6 +346,21 @@ __global__ void grid_kernel(tpx_shape s, int64_t n, int n1, int n2, float* __res
       const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
       row[0] = __fadd_rn(__fadd_rn(__fmul_rn(b0, d1x), __fmul_rn(b1, d2x)), s.p[0]);
       row[1] = __fadd_rn(__fadd_rn(__fmul_rn(b0, d1y), __fmul_rn(b1, d2y)), s.p[1]);
+    } else if (s.kind == TPX_SHAPE_INTERVAL_BOUNDARY) {
+      row[0] = (i & 1) ? s.p[0] : s.p[1];                    // interval.py:128-137: upper, lower, upper, ...
+    } else if (s.kind == TPX_SHAPE_INTERVAL_POINT) {
+      row[0] = s.p[0];
+    } else if (s.kind == TPX_SHAPE_PARALLELOGRAM_BOUNDARY) {
+      para_walk(s, __fmul_rn(lin01(i, n + 1), para_perimeter(s)), row);   // parallelogram.py:202-218
+    } else if (s.kind == TPX_SHAPE_CIRCLE_BOUNDARY) {
+      // torch.linspace(0, 2 pi, n + 1)[:-1] (circle.py:143-160)
+      const int64_t steps = n + 1;
+      const float end = 6.283185307179586f, step = end / (float)(steps - 1);
+      const float phi = (i < steps / 2) ? (float)i * step : end - step * (float)(steps - 1 - i);
+      float sn, cs;
+      sincosf(phi, &sn, &cs);
+      row[0] = __fadd_rn(__fmul_rn(s.p[2], cs), s.p[0]);
+      row[1] = __fadd_rn(__fmul_rn(s.p[2], sn), s.p[1]);
     } else {
       // sunflower seed arrangement, float64 angle reduced before the float32 sin/cos
       const double gr = (2.23606797749979 + 1.0) / 2.0;
@@ -319,10 +412,48 @@ __global__ void union_pick_kernel(tpx_region in_a, const float* __restrict__ a, 
   }
 }
 
+// outward unit normals (interval.py:139-144,181-186, parallelogram.py:248-286, circle.py:162-170)
+__global__ void normal_kernel(tpx_shape s, const float* __restrict__ pts, int64_t n, int stride, float* __restrict__ out) {
+  const int d = shape_dim(s.kind);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* q = pts + i * stride + s.col;
+    float* o = out + i * d;
+    if (s.kind == TPX_SHAPE_INTERVAL_BOUNDARY) {
+      o[0] = isclose32(q[0], s.p[0]) ? -1.0f : 1.0f;
+    } else if (s.kind == TPX_SHAPE_INTERVAL_POINT) {
+      o[0] = s.p[1];
+    } else if (s.kind == TPX_SHAPE_CIRCLE_BOUNDARY) {
+      o[0] = __fdiv_rn(__fsub_rn(q[0], s.p[0]), s.p[2]);
+      o[1] = __fdiv_rn(__fsub_rn(q[1], s.p[1]), s.p[2]);
+    } else {
+      float bx, by;
+      bary(s, q, bx, by);
+      const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
+      const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
+      // unit normals of the two directions: (-dy, dx) / |d|, the second one negated
+      const float l1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1y, d1y), __fmul_rn(d1x, d1x)));
+      const float l2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2y, d2y), __fmul_rn(d2x, d2x)));
+      const float n1x = __fdiv_rn(-d1y, l1), n1y = __fdiv_rn(d1x, l1);
+      const float n2x = -__fdiv_rn(-d2y, l2), n2y = -__fdiv_rn(d2x, l2);
+      float x = 0.0f, y = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float lvl = (float)k, sgn = 2.0f * lvl - 1.0f;
+        const float wy = isclose32(by, lvl) ? sgn : 0.0f, wx = isclose32(bx, lvl) ? sgn : 0.0f;
+        x = __fadd_rn(x, __fmul_rn(n1x, wy)); y = __fadd_rn(y, __fmul_rn(n1y, wy));
+        x = __fadd_rn(x, __fmul_rn(n2x, wx)); y = __fadd_rn(y, __fmul_rn(n2y, wx));
+      }
+      const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+      o[0] = __fdiv_rn(x, nrm);
+      o[1] = __fdiv_rn(y, nrm);
+    }
+  }
+}
+
 static int check_shape(const tpx_shape* s, int stride) {
   if (!s) return fail(TPX_E_ARG, "shape is NULL");
-  if (s->kind < TPX_SHAPE_INTERVAL || s->kind > TPX_SHAPE_CIRCLE) return fail(TPX_E_UNSUPPORTED, "shape kind %d", s->kind);
-  const int d = s->kind == TPX_SHAPE_INTERVAL ? 1 : 2;
+  if (s->kind < TPX_SHAPE_INTERVAL || s->kind > TPX_SHAPE_CIRCLE_BOUNDARY) return fail(TPX_E_UNSUPPORTED, "shape kind %d", s->kind);
+  const int d = shape_dim(s->kind);
   if (s->col < 0 || s->col + d > stride || s->col + d > 4) return fail(TPX_E_ARG, "shape columns %d..%d outside row of %d (max 4)", s->col, s->col + d, stride);
   return 0;
 }
@@ -428,6 +559,18 @@ int tpx_sample_grid(const tpx_shape* shape, int64_t n, int32_t n1, int32_t n2, f
   if (shape->kind == TPX_SHAPE_PARALLELOGRAM && ((int64_t)n1 * n2 != n || n1 < 1)) return fail(TPX_E_ARG, "grid %d x %d != %lld", n1, n2, (long long)n);
   grid_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*shape, n, n1, n2, out, row_stride);
   return cudaGetLastError() == cudaSuccess ? 0 : cuda_fail("grid_kernel");
+}
+
+int tpx_boundary_normal(const tpx_shape* shape, const float* points, int64_t n, int32_t row_stride,
+                        float* normals, void* stream) {
+  int rc = check_shape(shape, row_stride);
+  if (rc) return rc;
+  if (shape->kind < TPX_SHAPE_INTERVAL_BOUNDARY) return fail(TPX_E_ARG, "shape kind %d is not a boundary", shape->kind);
+  if (n < 0) return fail(TPX_E_ARG, "n < 0");
+  if (n == 0) return 0;
+  if (!points || !normals) return fail(TPX_E_ARG, "NULL pointer");
+  normal_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*shape, points, n, row_stride, normals);
+  return cudaGetLastError() == cudaSuccess ? 0 : cuda_fail("normal_kernel");
 }
 
 int tpx_sample_keys(uint64_t seed, uint64_t offset, int64_t n, int64_t* keys, void* stream) {

@@ -284,7 +284,7 @@ class _ShapeDomain(Domain):
         return 0, 0
 
     def _grid(self, n, dev, exact=True):
-        out = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
+        out = torch.empty((n, self.dim_cols()), dtype=torch.float32, device=dev)
         self._fill_grid(out, 0, n, exact)
         return out
 
@@ -386,6 +386,107 @@ class Circle(_ShapeDomain):
     def _box(self):
         c, r = self.center, _F32(self.radius)
         return [float(c[0] - r), float(c[0] + r), float(c[1] - r), float(c[1] + r)]
+
+
+# --------------------------------------------------------------------------------------
+# boundaries of the basic shapes
+# --------------------------------------------------------------------------------------
+class BoundaryDomain(_ShapeDomain):
+    """Boundary of a basic shape (reference ``domain.py:295-348``): a domain of one dimension
+    less in the same space, sampled / tested / given normals by the libtpx boundary shapes."""
+
+    def __init__(self, domain):
+        assert isinstance(domain, Domain)
+        super().__init__(space=domain.space, dim=domain.dim - 1)
+        self.domain = domain
+        self.necessary_variables = domain.necessary_variables
+
+    def __call__(self, **data):
+        return self
+
+    def _params(self):
+        return self.domain._params()
+
+    def _box(self):
+        return self.domain._box()
+
+    def normal(self, points, params=Points.empty(), device="cpu"):
+        """outward unit normals at ``points`` (which should lie on the boundary), shape (len(points), dim)."""
+        if not isinstance(points, Points):
+            points = Points(points, self.space)
+        rows = points[:, list(self.space.keys())].as_tensor if points.space != self.space else points.as_tensor
+        out_device = rows.device
+        dev = _compute_device(out_device)
+        rows = rows.detach().to(device=dev, dtype=torch.float32).contiguous()
+        n, stride = rows.shape
+        out = torch.empty((n, self.space.dim), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().tpx_boundary_normal(ctypes.byref(self._shape(0)), _lib.ptr(rows), ctypes.c_int64(n),
+                                                      ctypes.c_int32(stride), _lib.ptr(out), _lib.stream_ptr()))
+        return out.to(out_device)
+
+
+class IntervalBoundary(BoundaryDomain):
+    """both end points (reference ``interval.py:96-149``)."""
+    kind = _lib.TPX_SHAPE_INTERVAL_BOUNDARY
+
+    def __init__(self, domain):
+        assert isinstance(domain, Interval)
+        super().__init__(domain)
+
+    def _get_volume(self):
+        return _F32(2.0)
+
+
+class IntervalSingleBoundaryPoint(BoundaryDomain):
+    """one end point, e.g. for initial conditions (reference ``interval.py:152-191``)."""
+    kind = _lib.TPX_SHAPE_INTERVAL_POINT
+
+    def __init__(self, domain, side, normal_vec=-1):
+        assert isinstance(domain, Interval)
+        super().__init__(domain)
+        self.side = float(_const(side, "side")[0])
+        self.normal_vec = normal_vec
+
+    def _params(self):
+        return [self.side, float(self.normal_vec)]
+
+    def _get_volume(self):
+        return _F32(1.0)
+
+
+class ParallelogramBoundary(BoundaryDomain):
+    """the four sides (reference ``parallelogram.py:159-291``)."""
+    kind = _lib.TPX_SHAPE_PARALLELOGRAM_BOUNDARY
+
+    def __init__(self, domain):
+        assert isinstance(domain, Parallelogram)
+        super().__init__(domain)
+
+    def _get_volume(self):
+        d1, d2 = self.domain._dirs()
+        l1 = np.sqrt(d1[0] * d1[0] + d1[1] * d1[1], dtype=_F32)
+        l2 = np.sqrt(d2[0] * d2[0] + d2[1] * d2[1], dtype=_F32)
+        return _F32(2.0) * (l1 + l2)
+
+
+class CircleBoundary(BoundaryDomain):
+    """the circle line (reference ``circle.py:111-175``)."""
+    kind = _lib.TPX_SHAPE_CIRCLE_BOUNDARY
+
+    def __init__(self, domain):
+        assert isinstance(domain, Circle)
+        super().__init__(domain)
+
+    def _get_volume(self):
+        return _F32(2 * np.pi) * _F32(self.domain.radius)
+
+
+Interval.boundary = property(lambda self: IntervalBoundary(self))
+Interval.boundary_left = property(lambda self: IntervalSingleBoundaryPoint(self, side=self.lower_bound))
+Interval.boundary_right = property(lambda self: IntervalSingleBoundaryPoint(self, side=self.upper_bound, normal_vec=1))
+Parallelogram.boundary = property(lambda self: ParallelogramBoundary(self))
+Circle.boundary = property(lambda self: CircleBoundary(self))
 
 
 # --------------------------------------------------------------------------------------
