@@ -64,3 +64,49 @@ def test_deeponet_uncopied_trunk_input():
     lap_ref = torch.autograd.grad(g.sum(), coords["t"])[0]
     assert relerr(out.detach().cpu().numpy(), gen.detach().cpu().numpy()) < TOL
     assert relerr(lap.detach().cpu().numpy(), lap_ref.cpu().numpy()) < TOL
+
+
+def test_deeponet_full_size_equals_generic_autograd_definition():
+    """config 4 at BASELINE.json's size (256 functions x 16,384 trunk points, p = 64, trunk 4x64): the native
+    path (trunk jets once per point + one GEMM per stream) against the reference's definition evaluated with
+    torch autograd on the SAME modules on the GPU (the trunk on all F x N copies, two create_graph sweeps)."""
+    import math
+    import torchphysics_b200 as tp
+    torch.manual_seed(0)
+    F, N, p = 256, 16384, 64
+    T, U, Fs, K = tp.spaces.R1("t"), tp.spaces.R1("u"), tp.spaces.R1("f"), tp.spaces.R1("k")
+    fspace = tp.spaces.FunctionSpace(T, Fs)
+    ival = tp.domains.Interval(T, 0, 1)
+    grid = tp.samplers.GridSampler(ival, n_points=50).sample_points(device="cuda")
+    trunk = tp.models.FCTrunkNet(T, hidden=(64,) * 4, default_trunk_input=grid)
+    branch = tp.models.FCBranchNet(fspace, hidden=(64,) * 4, grid=grid)
+    net = tp.models.DeepONet(trunk, branch, U, output_neurons=p).cuda()
+    fset = tp.domains.CustomFunctionSet(fspace, tp.samplers.RandomUniformSampler(tp.domains.Interval(K, -1, 1), n_points=F),
+                                        lambda k, t: k * torch.sin(math.pi * t))
+    fsampler = tp.samplers.FunctionSamplerRandomUniform(F, fset, function_creation_interval=1000)
+    tsampler = tp.samplers.RandomUniformSampler(ival, n_points=N).make_static()
+    cond = tp.conditions.PIDeepONetCondition(net, fsampler, tsampler, lambda u, t, f: tp.utils.laplacian(u, t) + f)
+    for _ in range(2):
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(1)                                  # same function indices in every call
+        loss = cond(device="cuda")
+        loss.backward()
+    got = [q.grad.clone() for q in net.parameters() if q.grad is not None]
+    # the reference's definition on the same modules
+    net.zero_grad(set_to_none=True)
+    t = tsampler.sample_points(device="cuda").as_tensor
+    tt = t.unsqueeze(0).repeat(F, 1, 1).requires_grad_(True)
+    pts = tp.spaces.Points(tt, T)
+    net.fix_branch_input(fset.get_function(fsampler.current_indices)(net.branch.grid), device="cuda")
+    u = net._generic(pts)
+    g = torch.autograd.grad(u.sum(), tt, create_graph=True)[0]
+    lap = torch.autograd.grad(g.sum(), tt, create_graph=True)[0]
+    k = fset.param_samples.as_tensor[fsampler.current_indices.cuda()]
+    f = k.unsqueeze(1) * torch.sin(math.pi * tt)
+    want = ((lap + f) ** 2).sum(dim=(1, 2)).mean()
+    want.backward()
+    assert abs(float(loss) - float(want)) < TOL * abs(float(want))
+    ref = [q.grad for q in net.parameters() if q.grad is not None]
+    assert len(ref) == len(got)
+    for a, w in zip(got, ref):
+        assert relerr(a.cpu().numpy(), w.cpu().numpy()) < 2e-5      # two fp32 evaluations, 4.2e6-term sums
