@@ -203,6 +203,26 @@ int tpx_sample_lhs(int32_t d, const float* box, const int64_t* perm, uint64_t se
 int tpx_union_pick(const tpx_region* in_a, const float* a, const float* b, int64_t n, int32_t d, int32_t row_stride,
                    float ratio, uint64_t seed, uint64_t offset, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Parameter update (reference: torch.optim.Adam configured by OptimizerSetting, solver.py:111-136, stepped by
+ * Lightning after Solver.training_step): one launch for all parameter tensors, same arithmetic as
+ * torch.optim.Adam (amsgrad = False).  Tensors are fp32, contiguous; a NULL grad skips the tensor (torch skips
+ * parameters whose .grad is None).  `step` is the 1-based step count of the bias correction.
+ * ------------------------------------------------------------------------------------ */
+#define TPX_MAX_TENSORS 64
+typedef struct tpx_tensor_list {
+  int32_t n;
+  int32_t reserved;
+  void* param[TPX_MAX_TENSORS];
+  const void* grad[TPX_MAX_TENSORS];
+  void* exp_avg[TPX_MAX_TENSORS];
+  void* exp_avg_sq[TPX_MAX_TENSORS];
+  int64_t numel[TPX_MAX_TENSORS];
+} tpx_tensor_list;
+
+int tpx_adam_step(const tpx_tensor_list* list, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

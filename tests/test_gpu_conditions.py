@@ -199,3 +199,41 @@ def test_sequential_normalization_layer_is_folded_into_the_native_network():
             assert q.grad is None or float(q.grad.abs().max()) == 0.0
         else:
             assert relerr(q.grad.cpu().numpy(), w) < TOL
+
+
+def test_native_adam_equals_torch_adam():
+    """the one-launch multi-tensor Adam against torch.optim.Adam, including a parameter without
+    gradient (left untouched) and weight decay."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(0)
+    shapes = [(64, 2), (64,), (64, 64), (64,), (1, 64), (1,), (3, 5, 7)]
+    for wd in (0.0, 0.01):
+        a = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+        b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+        oa = tp.optim.Adam(a, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+        ob = torch.optim.Adam(b, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+        for it in range(25):
+            for i, (p, q) in enumerate(zip(a, b)):
+                if i == 5 and it < 10:                       # no gradient for this parameter in the first steps
+                    p.grad, q.grad = None, None
+                    continue
+                g = torch.randn_like(p) * (1.0 + it)
+                p.grad, q.grad = g.clone(), g.clone()
+            oa.step()
+            ob.step()
+        for p, q in zip(a, b):
+            assert relerr(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 2e-6
+        assert int(oa.state[a[5]]["step"]) == 15 and int(oa.state[a[0]]["step"]) == 25
+        sa, sb = oa.state[a[2]], ob.state[b[2]]
+        assert relerr(sa["exp_avg"].cpu().numpy(), sb["exp_avg"].cpu().numpy()) < 2e-6
+        assert relerr(sa["exp_avg_sq"].cpu().numpy(), sb["exp_avg_sq"].cpu().numpy()) < 2e-6
+    # the Trainer picks it for OptimizerSetting(torch.optim.Adam, ...)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(16, 16))
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    cond = tp.conditions.PINNCondition(model, tp.samplers.RandomUniformSampler(sq, n_points=256),
+                                       lambda u, x: tp.utils.laplacian(u, x) + 1.0)
+    solver = tp.solver.Solver([cond], optimizer_setting=tp.OptimizerSetting(torch.optim.Adam, lr=1e-3))
+    trainer = tp.solver.Trainer(max_steps=3)
+    trainer.fit(solver)
+    assert isinstance(trainer.optimizer, tp.optim.Adam)

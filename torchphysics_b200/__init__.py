@@ -6,7 +6,7 @@
 """
 __version__ = "0.1.0"
 
-from . import spaces, userfn, functionsets, domains, samplers, models, operators, utils, conditions, solver, parallel  # noqa: F401
+from . import spaces, userfn, functionsets, domains, samplers, models, operators, utils, conditions, optim, solver, parallel  # noqa: F401
 from . import deeponet as _deeponet
 
 # the reference's tp.models namespace also holds the DeepONet classes (models/__init__.py)

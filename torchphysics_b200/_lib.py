@@ -43,6 +43,7 @@ EXPORTS = (
     "tpx_sample_keys",
     "tpx_sample_lhs",
     "tpx_union_pick",
+    "tpx_adam_step",
 )
 
 TPX_SHAPE_INTERVAL = 1
@@ -52,6 +53,7 @@ TPX_SHAPE_INTERVAL_BOUNDARY = 4
 TPX_SHAPE_INTERVAL_POINT = 5
 TPX_SHAPE_PARALLELOGRAM_BOUNDARY = 6
 TPX_SHAPE_CIRCLE_BOUNDARY = 7
+TPX_MAX_TENSORS = 64
 TPX_MAX_SHAPES = 8
 TPX_MAX_OPS = 24
 TPX_OP_SHAPE, TPX_OP_AND, TPX_OP_OR, TPX_OP_NOT = 0, 1, 2, 3
@@ -96,6 +98,18 @@ class Region(ctypes.Structure):
         ("n_ops", ctypes.c_int32),
         ("shapes", Shape * TPX_MAX_SHAPES),
         ("ops", ctypes.c_int32 * TPX_MAX_OPS),
+    ]
+
+
+class TensorList(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("param", ctypes.c_void_p * TPX_MAX_TENSORS),
+        ("grad", ctypes.c_void_p * TPX_MAX_TENSORS),
+        ("exp_avg", ctypes.c_void_p * TPX_MAX_TENSORS),
+        ("exp_avg_sq", ctypes.c_void_p * TPX_MAX_TENSORS),
+        ("numel", ctypes.c_int64 * TPX_MAX_TENSORS),
     ]
 
 

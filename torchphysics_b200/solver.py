@@ -6,7 +6,7 @@ of dL/dtheta per step (``parallel.FlatGradAllReduce``)."""
 import torch
 import torch.nn as nn
 
-from . import domains, parallel
+from . import domains, optim, parallel
 
 
 class OptimizerSetting:
@@ -59,7 +59,14 @@ class Solver(nn.Module):
 
     def configure_optimizers(self):
         setting = self.optimizer_setting
-        optimizer = setting.optimizer_class(self.parameters(), lr=setting.lr, **setting.optimizer_args)
+        cls = setting.optimizer_class
+        if (cls is torch.optim.Adam and self.device.type == "cuda" and optim.Adam.covers(setting.optimizer_args)
+                and all(p.is_cuda for p in self.parameters())):
+            # same update, one launch per step instead of 4-5 per parameter tensor
+            args = {k: v for k, v in setting.optimizer_args.items() if k in ("betas", "eps", "weight_decay")}
+            optimizer = optim.Adam(self.parameters(), lr=setting.lr, **args)
+        else:
+            optimizer = cls(self.parameters(), lr=setting.lr, **setting.optimizer_args)
         if setting.scheduler_class is None:
             return optimizer
         scheduler = setting.scheduler_class(optimizer, **setting.scheduler_args)
@@ -95,6 +102,7 @@ class Trainer:
             schedulers = configured[1]
         else:
             optimizer = configured
+        self.optimizer = optimizer
         solver.on_train_start()
         params = [p for p in solver.parameters() if p.requires_grad]
         reducer = parallel.FlatGradAllReduce(params, n_scalars=1)
