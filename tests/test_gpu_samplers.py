@@ -273,3 +273,36 @@ def test_boundary_condition_trains_through_native_path():
     gs = torch.autograd.grad(want, ref_autograd.linear_params(seq))
     for p, w in zip(model._native_engine().params(), gs):
         assert relerr(p.grad.cpu().numpy(), w.numpy()) < 1e-5
+
+
+def test_adaptive_rejection_samplers_through_a_condition():
+    """points with a high per-point loss survive, the rest are redrawn uniformly; the condition
+    hands the unreduced loss of the previous iteration to the sampler (reference condition.py:280-302)."""
+    import torchphysics_b200 as tp
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    torch.manual_seed(0)
+    s = tp.samplers.AdaptiveThresholdRejectionSampler(sq, resample_ratio=0.25, n_points=4000)
+    assert s.is_adaptive
+    first = s.sample_points(device="cuda").as_tensor.clone()
+    loss = first[:, 0].clone()                                   # loss grows with x1
+    second = s.sample_points(unreduced_loss=loss, device="cuda").as_tensor
+    thr = loss.min() + (loss.max() - loss.min()) * 0.25
+    keep = loss >= thr
+    assert torch.equal(second[keep], first[keep]) and not torch.equal(second[~keep], first[~keep])
+    assert bool(sq._contains(tp.spaces.Points(second, X)).all())
+    r = tp.samplers.AdaptiveRandomRejectionSampler(sq, n_points=20000)
+    first = r.sample_points(device="cuda").as_tensor.clone()
+    loss = first[:, 0].clone()
+    second = r.sample_points(unreduced_loss=loss, device="cuda").as_tensor
+    kept = (second == first).all(dim=1)
+    hi, lo = kept[loss > 0.8].float().mean(), kept[loss < 0.2].float().mean()
+    assert hi > 0.8 and lo < 0.2                                  # P(keep) = (loss - min) / (max - min)
+    model = tp.models.FCN(X, U, hidden=(16, 16)).cuda()
+    cond = tp.conditions.PINNCondition(model, tp.samplers.AdaptiveThresholdRejectionSampler(sq, 0.5, n_points=512),
+                                       lambda u, x: tp.utils.laplacian(u, x) + 1.0)
+    a = cond(device="cuda")
+    assert cond.last_unreduced_loss is not None and cond.last_unreduced_loss.shape == (512,)
+    b = cond(device="cuda")
+    b.backward()
+    assert torch.isfinite(a) and torch.isfinite(b)

@@ -332,5 +332,57 @@ class LHSSampler(PointSampler):
         return Points(out.to(device), self.domain.space)
 
 
+class AdaptiveSampler(PointSampler):
+    """Sampler that needs the per-point loss of the previous iteration (reference ``sampler_base.py:396-440``)."""
+
+    @property
+    def is_adaptive(self):
+        return True
+
+    def sample_points(self, unreduced_loss=None, params=Points.empty(), device="cpu"):
+        raise NotImplementedError
+
+
+class _RejectionAdaptive(AdaptiveSampler):
+    def __init__(self, domain, n_points=None, density=None, filter_fn=None):
+        super().__init__(n_points=n_points, density=density, filter_fn=filter_fn)
+        self.domain = domain
+        self.random_sampler = RandomUniformSampler(domain, n_points=n_points, density=density, filter_fn=filter_fn)
+        self.last_points = None
+
+    def _level(self, unreduced_loss):
+        raise NotImplementedError
+
+    def sample_points(self, unreduced_loss=None, params=Points.empty(), device="cpu"):
+        new_points = self.random_sampler.sample_points(params, device=device)
+        if self.last_points is None or unreduced_loss is None:
+            self.last_points = new_points
+        else:
+            loss = unreduced_loss.detach()
+            max_l, min_l = torch.max(loss), torch.min(loss)
+            replace = loss < min_l + (max_l - min_l) * self._level(loss)
+            self.last_points._t[replace, :] = new_points._t[replace, :]
+        return self.last_points
+
+
+class AdaptiveThresholdRejectionSampler(_RejectionAdaptive):
+    """keeps points whose loss is above min + ratio (max - min), resamples the rest uniformly
+    (reference ``random_samplers.py:241-292``)."""
+
+    def __init__(self, domain, resample_ratio, n_points=None, density=None, filter_fn=None):
+        super().__init__(domain, n_points=n_points, density=density, filter_fn=filter_fn)
+        self.resample_ratio = resample_ratio
+
+    def _level(self, loss):
+        return self.resample_ratio
+
+
+class AdaptiveRandomRejectionSampler(_RejectionAdaptive):
+    """keeps a point with probability (loss - min) / (max - min) (reference ``random_samplers.py:295-345``)."""
+
+    def _level(self, loss):
+        return torch.rand_like(loss)
+
+
 # function sets / function samplers live in the same namespaces as in the reference
 from .functionsets import FunctionSampler, FunctionSamplerRandomUniform, FunctionSamplerOrdered, FunctionSamplerCoupled  # noqa: E402,F401
