@@ -306,3 +306,15 @@ def test_adaptive_rejection_samplers_through_a_condition():
     b = cond(device="cuda")
     b.backward()
     assert torch.isfinite(a) and torch.isfinite(b)
+
+
+def test_host_stream_sampler_delivers_batches_in_order():
+    import torchphysics_b200 as tp
+    X = tp.spaces.R2("x")
+    batches = [torch.rand(1000, 2) + k for k in range(3)]
+    s = tp.samplers.HostStreamSampler(batches, X)
+    for i in range(7):
+        pts = s.sample_points(device="cuda")
+        assert pts.space == X and torch.equal(pts.as_tensor.cpu(), batches[i % 3])
+    with pytest.raises(ValueError):
+        s.sample_points(device="cpu")

@@ -35,6 +35,9 @@ class FlatGradAllReduce:
         rank, size = world()
         if not self.params:
             return list(scalars)
+        if size == 1:                       # nothing to exchange: gradients stay where backward left them
+            return [s.detach().reshape(()).clone() if isinstance(s, torch.Tensor) else torch.tensor(float(s))
+                    for s in scalars]
         device = self.params[0].device
         buf = self._buffer(device)
         buf.zero_()

@@ -332,6 +332,53 @@ class LHSSampler(PointSampler):
         return Points(out.to(device), self.domain.space)
 
 
+class HostStreamSampler(PointSampler):
+    """Collocation batches that live in pinned HOST memory, streamed to the device one batch ahead.
+
+    ``batches`` is a sequence of (n, dim) float32 tensors (pinned here if they are not); ``sample_points``
+    returns batch i on the device and starts the host->device copy of batch i+1 on a side stream, so the
+    copy overlaps the kernels of step i (two device buffers; the caller's per-step read of the loss is what
+    orders a buffer's reuse after the step that consumed it).  The reference has no counterpart: its samplers
+    create points on ``device`` directly (``sampler_base.py:130``); this is the drop-in for points produced
+    on the host."""
+
+    def __init__(self, batches, space):
+        batches = [b if b.is_pinned() else b.contiguous().pin_memory() for b in batches]
+        assert len(batches) > 0 and all(b.shape == batches[0].shape and b.dtype == torch.float32 for b in batches)
+        super().__init__(n_points=batches[0].shape[0])
+        self.batches, self.space = batches, space
+        self._i = 0
+        self._dev = None
+
+    def __len__(self):
+        return self.n_points
+
+    def _start_copy(self, slot, index):
+        with torch.cuda.stream(self._stream):
+            self._bufs[slot].copy_(self.batches[index % len(self.batches)], non_blocking=True)
+            self._ready[slot].record(self._stream)
+
+    def sample_points(self, params=Points.empty(), device="cpu"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("HostStreamSampler delivers to a CUDA device")
+        if self._dev != dev:
+            self._dev = dev
+            with torch.cuda.device(dev):
+                self._stream = torch.cuda.Stream()
+                self._bufs = [torch.empty(self.batches[0].shape, dtype=torch.float32, device=dev) for _ in range(2)]
+                self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+                self._start_copy(self._i % 2, self._i)
+        slot = self._i % 2
+        torch.cuda.current_stream(dev).wait_event(self._ready[slot])
+        # the other buffer was last read by step i-1, which the current stream has already finished enqueuing:
+        # the copy stream waits for it before overwriting
+        self._stream.wait_stream(torch.cuda.current_stream(dev))
+        self._start_copy(1 - slot, self._i + 1)
+        self._i += 1
+        return Points(self._bufs[slot], self.space)
+
+
 class AdaptiveSampler(PointSampler):
     """Sampler that needs the per-point loss of the previous iteration (reference ``sampler_base.py:396-440``)."""
 
