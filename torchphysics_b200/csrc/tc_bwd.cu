@@ -46,6 +46,16 @@ constexpr uint32_t B_TMEM_COLS = 512;
 constexpr uint32_t T_D = 0, T_AH = 64, T_AL = 128, T_DW = 192;   // TMEM columns
 constexpr int MAXL = 6;                  // hidden layers supported (dW accumulators: 64 columns each, L - 1 <= 5)
 constexpr int MAXIO = 4;                 // d_in, d_out supported
+// dW accumulators: the hidden matrices processed first get N = 128 accumulators ([a_hi | a_lo] as ONE B operand, so the
+// stacked Zt operand is read once per K step: 16 MMAs of 64 cycles instead of 2 x 16 of 48) as far as the 320 TMEM
+// columns behind D | A_hi | A_lo allow; the rest keep N = 64 and two chains.
+__host__ __device__ inline int dw_wide_count(int L) { const int n = L - 1, spare = (320 - 64 * n) / 64; return spare < 0 ? 0 : (spare < n ? spare : n); }
+__host__ __device__ inline bool dw_is_wide(int L, int l) { return (L - 1 - l) < dw_wide_count(L); }            // l = L-1 first
+__host__ __device__ inline uint32_t dw_col(int L, int l) {                                                      // columns from T_DW
+  uint32_t c = 0;
+  for (int m = L - 1; m > l; --m) c += dw_is_wide(L, m) ? 128u : 64u;
+  return c;
+}
 constexpr int BXP = 20;                  // padded neuron extent of one (stream, point) row of the exchange buffer
 constexpr int BX_GROUP = 4 * TILE * BXP;
 
@@ -58,7 +68,7 @@ __host__ __device__ inline BwdSmem bwd_smem(const TcLayout& lay) {
   BwdSmem s;
   s.wring = 0;                            // (hi, lo) x 4096: one product image, refetched per phase
   s.zt = 8192;                            // 128 rows x 128 K
-  s.at = s.zt + 16384;                    // hi: 64 rows x 128 K, lo: 64 rows x 128 K
+  s.at = s.zt + 16384;                    // 128 rows (a_hi 0-63, a_lo 64-127) x 128 K
   s.ex = s.at + 16384;
   s.acc = s.ex + B_GROUPS * BX_GROUP;
   s.small = s.acc + ACC_TOTAL;
@@ -167,15 +177,23 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         for (int ks = 0; ks < 8; ++ks)
           mma_tf32_ts(tD, tAl + ks * 8, desc_k_sw128(wh + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, 1);
         mma_commit(&bar_d);                  // the adjoint product is all the next activation step needs ...
-        const uint32_t tW = tmem + T_DW + (uint32_t)(l - 1) * 64;
+        const uint32_t tW = tmem + T_DW + dw_col(L, l);
+        if (dw_is_wide(L, l)) {
+          constexpr uint32_t idesc_w = idesc_tf32(128, 2 * HP);
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 8192 + (ks & 3) * 32),
-                      idesc, (ks > 0 || !first_tile) ? 1u : 0u);
+          for (int ks = 0; ks < 16; ++ks)
+            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 16384 + (ks & 3) * 32),
+                        idesc_w, (ks > 0 || !first_tile) ? 1u : 0u);
+        } else {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32),
-                      desc_k_sw128(at + 32768u + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, 1);
+          for (int ks = 0; ks < 16; ++ks)
+            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 16384 + (ks & 3) * 32),
+                        idesc, (ks > 0 || !first_tile) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)
+            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32),
+                        desc_k_sw128(at + 8192u + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, 1);
+        }
         mma_commit(&bar_f);                  // ... the gradient product only gates the reuse of its operands
       }
       __syncwarp();
@@ -327,8 +345,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
           Zt[s * 4096 + i * 32 + xo[i]] = zh;
           Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
           const float ah = tf32_hi(ap[s][i]);
-          At[s * 2048 + i * 32 + xo[i]] = ah;
-          At[8192 + s * 2048 + i * 32 + xo[i]] = ap[s][i] - ah;
+          At[s * 4096 + i * 32 + xo[i]] = ah;
+          At[s * 4096 + (64 + i) * 32 + xo[i]] = ap[s][i] - ah;
         }
         *reinterpret_cast<float4*>(ex_cmp + s * TILE * BXP) = make_float4(zb[s][0], zb[s][1], zb[s][2], zb[s][3]);
       }
@@ -485,13 +503,20 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       for (int o = 0; o < MAXIO; ++o)
         if (o < d_out) atomicAdd(a.gacc + lay32.bl() + o, (double)acc[ACC_BL + o]);
     }
-    // hidden matrices: rows j (hi, quadrants 0-1) and 64 + j (lo, quadrants 2-3) both add into dW[j][i]
+    // hidden matrices: rows j (hi, quadrants 0-1) and 64 + j (lo, quadrants 2-3) both add into dW[j][i]; a wide
+    // accumulator also holds the a_lo products in columns 64 + i
     if (my_tiles > 0) {
       const int j = (quad & 1) * 32 + lane;
       for (int l = 1; l < L; ++l) {
-        const uint32_t tW = tmem + T_DW + (uint32_t)(l - 1) * 64 + lane_base;
+        const uint32_t tW = tmem + T_DW + dw_col(L, l) + lane_base;
         float w[B_CH];
         tmem_ld16(tW + jc, w);
+        if (dw_is_wide(L, l)) {
+          float w2[B_CH];
+          tmem_ld16(tW + HP + jc, w2);
+#pragma unroll
+          for (int i = 0; i < B_CH; ++i) w[i] += w2[i];
+        }
 #pragma unroll
         for (int i = 0; i < B_CH; ++i) {
           const int col = jc + i;
