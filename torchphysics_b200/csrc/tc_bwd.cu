@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 #pragma unroll
       for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int i = 0; i < B_NW; ++i) c[s][i] = __ldg(base + (s * HP + i) * TILE);
+        for (int i = 0; i < B_NW; ++i) c[s][i] = __ldcs(base + (s * HP + i) * TILE);
     };
 
     // adjoints of the pre-activation streams of a layer from the adjoints of its activation streams (thread-local)

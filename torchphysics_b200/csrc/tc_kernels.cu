@@ -299,19 +299,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           const float t = tanh_fast(z[0][i]);
           const float s1 = fmaf(-t, t, 1.0f);
           z[0][i] = t;
-          if (ckl) ckl[(0 * HP + i) * TILE] = t;
+          if (ckl) __stcs(ckl + (0 * HP + i) * TILE, t);
           float qq = 0.0f;
 #pragma unroll
           for (int k = 0; k < ND; ++k) {
             const float dz = z[1 + k][i];
             if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
             z[1 + k][i] = s1 * dz;
-            if (ckl) ckl[((1 + k) * HP + i) * TILE] = dz;
+            if (ckl) __stcs(ckl + ((1 + k) * HP + i) * TILE, dz);
           }
           if (LAP) {
             const float lz = z[S - 1][i];
             z[S - 1][i] = fmaf(-2.0f * t * s1, qq, s1 * lz);
-            if (ckl) ckl[((S - 1) * HP + i) * TILE] = lz;
+            if (ckl) __stcs(ckl + ((S - 1) * HP + i) * TILE, lz);
           }
         }
         if (!last) {
