@@ -7,9 +7,10 @@
 // tf32 products  A_hi W_hi + A_hi W_lo + A_lo W_hi  (hi = round-to-nearest tf32, lo = exact rest).
 //   * A_hi / A_lo live in TMEM (written by the activation warps with tcgen05.st), W_hi / W_lo in
 //     shared memory (128-byte swizzle, K-major), D in TMEM: the MMA runs at its 32-cycle floor.
-//   * warp q of a tile slot owns TMEM quadrant q = stream q.  The activation jets couple the
-//     streams of a point (d_k h = s'(z) d_k z, L h = s''(z) sum c_k (d_k z)^2 + s'(z) L z), so the
-//     value warp publishes tanh(z) and the derivative warps publish d_k z through shared memory.
+//   * warp q of a tile slot owns TMEM quadrant q = the rows of stream q.  The activation jets couple the
+//     streams of a point (d_k h = s'(z) d_k z, L h = s''(z) sum c_k (d_k z)^2 + s'(z) L z), so each layer step
+//     moves D through a transposing exchange buffer in shared memory: rows of a stream in, all streams of a
+//     point out (see the comment above FwdSmem); tanh and the jets are then thread-local on every warp.
 //   * two tile slots per CTA ping-pong: while the tensor core works on one tile's layer, the
 //     activation warps of the other tile run.  One persistent CTA per SM; all weights resident.
 #include <cstdio>
