@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_a, bar_d, bar_f, bar_w;
+  __shared__ uint64_t bar_a, bar_z, bar_d, bar_f, bar_w;
   __shared__ uint32_t tmem_slot;
   float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const TcLayout lay = a.lay;
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   if (warp == B_EPI_WARPS) tmem_alloc(&tmem_slot, B_TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_a, B_EPI_WARPS);
+    mbar_init(&bar_z, B_EPI_WARPS);
     mbar_init(&bar_d, 1);
     mbar_init(&bar_f, 1);
     mbar_init(&bar_w, 1);
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     const uint32_t ring = smem_u32(sm + so.wring), zt = smem_u32(sm + so.zt), at = smem_u32(sm + so.at);
     constexpr uint32_t idesc = idesc_tf32(128, HP);
     const int64_t total_phases = my_tiles * nphase;
-    uint32_t ph_a = 0, ph_w = 0, ph_d = 0;
+    uint32_t ph_a = 0, ph_z = 0, ph_w = 0, ph_d = 0;
     auto phase_src = [&](int64_t g) -> const float* {
       const int l = (L - 1) - (int)(g % nphase);
       return a.img + lay.mat(l, 2);
@@ -177,6 +178,22 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         for (int ks = 0; ks < 8; ++ks)
           mma_tf32_ts(tD, tAl + ks * 8, desc_k_sw128(wh + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, 1);
         mma_commit(&bar_d);                  // the adjoint product is all the next activation step needs ...
+      }
+      __syncwarp();
+      // the weight image is free once the adjoint product is done: fetch the next image behind the activation warps' work
+      mbar_wait(&bar_d, ph_d);
+      ph_d ^= 1;
+      if (mdbg) a.dbg[512 + l * 4 + 1] = clock64();
+      if (g + 1 < total_phases) {
+        if (elect_one()) bulk_load(sm + so.wring, phase_src(g + 1), 32768u, &bar_w);
+        __syncwarp();
+      }
+      // ... and it only needs the TMEM A operand: the activation warps write the transposed operands of the gradient
+      // product (the longest phase of a step) while it runs, and signal them separately
+      mbar_wait(&bar_z, ph_z);
+      ph_z ^= 1;
+      fence_after();
+      if (elect_one()) {
         const uint32_t tW = tmem + T_DW + dw_col(L, l);
         if (dw_is_wide(L, l)) {
           constexpr uint32_t idesc_w = idesc_tf32(128, 2 * HP);
@@ -194,19 +211,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
             mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32),
                         desc_k_sw128(at + 8192u + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, 1);
         }
-        mma_commit(&bar_f);                  // ... the gradient product only gates the reuse of its operands
+        mma_commit(&bar_f);                  // the gradient product only gates the reuse of its operands
       }
       __syncwarp();
-      if (mdbg) a.dbg[512 + l * 4 + 1] = clock64();
-      // the weight image is free once this phase's TMEM-operand products are done: fetch the next image
-      // behind the activation warps' work
-      mbar_wait(&bar_d, ph_d);
-      ph_d ^= 1;
       if (mdbg) a.dbg[512 + l * 4 + 2] = clock64();
-      if (g + 1 < total_phases) {
-        if (elect_one()) bulk_load(sm + so.wring, phase_src(g + 1), 32768u, &bar_w);
-        __syncwarp();
-      }
     }
   } else {
     // =========================== activation warps ===========================
@@ -329,31 +337,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     // hand Zbar of layer l >= 1 to the two products: transposed operands of the gradient product (with the
     // activation jets of layer l - 1), TMEM A operand of the adjoint product
     auto emit = [&](const float (&zb)[S][B_NW], const float (&cprev)[S][B_NW]) {
-      float ap[S][B_NW];
-      jets(cprev, ap);
-      TPX_STAMP(3);
-      if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
-        mbar_wait(&bar_f, ph_f);
-        ph_f ^= 1;
-      }
-      TPX_STAMP(4);
+      // (1) Zbar -> exchange buffer -> TMEM A operand of the adjoint product, which starts as soon as all warps arrive
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-#pragma unroll
-        for (int i = 0; i < B_NW; ++i) {
-          const float zh = tf32_hi(zb[s][i]);
-          Zt[s * 4096 + i * 32 + xo[i]] = zh;
-          Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
-          const float ah = tf32_hi(ap[s][i]);
-          At[s * 4096 + i * 32 + xo[i]] = ah;
-          At[s * 4096 + (64 + i) * 32 + xo[i]] = ap[s][i] - ah;
-        }
+      for (int s = 0; s < S; ++s)
         *reinterpret_cast<float4*>(ex_cmp + s * TILE * BXP) = make_float4(zb[s][0], zb[s][1], zb[s][2], zb[s][3]);
-      }
-      dw_pending = true;
-      TPX_STAMP(5);
+      TPX_STAMP(3);
       named_bar_sync(barid, 128);
-      TPX_STAMP(6);
       if (owner) {
         float hi[B_CH], lo[B_CH];
 #pragma unroll
@@ -371,10 +360,34 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         tmem_st16(tAl + jc, lo);
         tmem_wait_st();
       }
-      fence_async_smem();
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a);
+      TPX_STAMP(4);
+      // (2) transposed operands of the gradient product, in the shadow of the adjoint product
+      float ap[S][B_NW];
+      jets(cprev, ap);
+      if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
+        mbar_wait(&bar_f, ph_f);
+        ph_f ^= 1;
+      }
+      TPX_STAMP(5);
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int i = 0; i < B_NW; ++i) {
+          const float zh = tf32_hi(zb[s][i]);
+          Zt[s * 4096 + i * 32 + xo[i]] = zh;
+          Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
+          const float ah = tf32_hi(ap[s][i]);
+          At[s * 4096 + i * 32 + xo[i]] = ah;
+          At[s * 4096 + (64 + i) * 32 + xo[i]] = ap[s][i] - ah;
+        }
+      dw_pending = true;
+      TPX_STAMP(6);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_z);
       TPX_STAMP(7);
       if (dbgp) dbgp -= 16;
     };
