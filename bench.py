@@ -299,7 +299,7 @@ def run_native(args):
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01d_tcbwd_raw.csv (4.313 GB for
+                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01e_tcbwd_raw.csv (4.313 GB for
                          # 2^20 points: the 4 KB/point of saved activation jets + points + adjoints), scaled to this N
                          "traffic": 4.313e9 * N / 2 ** 20, "traffic_unit": "bytes/launch",
                          "peak_source": peak_src,
@@ -309,9 +309,9 @@ def run_native(args):
                          "note": "FLOP = algorithmic GEMM FLOP of SURVEY 8(d) (reverse = 2 x forward); the kernel "
                                  "issues 3 tf32 products per algorithmic product (4 for dW; fp32-accurate split) and tf32 "
                                  "runs at half the bf16 rate (1.10 PFLOP/s measured with scripts/umma_probe2.cu), so the "
-                                 "ceiling of frac is ~0.13.  ncu (profiles/r01d): tensor pipe active 18 %, shared-memory "
-                                 "LSU wavefronts 44 % of peak plus the UMMA operand reads of the gradient product "
-                                 "(~180-240 KB/tile-layer): the kernel is bound by shared-memory bandwidth (operand "
+                                 "ceiling of frac is ~0.13.  ncu (profiles/r01e): tensor pipe active 25 %, shared-memory "
+                                 "LSU wavefronts 46 % of peak plus the UMMA operand reads of the gradient product "
+                                 "(~180-240 KB/tile-layer; 496 KB per tile-layer in total = 3970 port cycles vs 4980 measured): the kernel is bound by shared-memory bandwidth (operand "
                                  "transposition for dW + stream exchange), HBM 1.6 TB/s of 6.5"},
             "clocks": clk,
         }
