@@ -14,6 +14,15 @@ import numpy as np
 f32 = np.float32
 
 
+def _norm2(q):
+    """torch.linalg.norm(q, dim=1) of float32 rows of length 2 as torch's CPU kernel evaluates it:
+    sqrt(fma(y, y, x * x)) -- pinned on 1800 borderline candidates of tests/golden/cut_boundary.npz
+    (float64 holds the fused product-sum exactly before the single rounding to float32)."""
+    x2 = (q[:, 0] * q[:, 0]).astype(np.float64)
+    y = q[:, 1].astype(np.float64)
+    return np.sqrt((y * y + x2).astype(f32), dtype=f32)
+
+
 def dim(dom):
     kind = dom[0]
     if kind == "interval":
@@ -50,9 +59,7 @@ def contains(dom, pts):
     if kind == "circle":
         # domain2D/circle.py:34-40 -- ||p - c||_2 <= r
         c = np.asarray(dom[1], f32)
-        q = pts - c
-        nrm = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1], dtype=f32)
-        return nrm <= f32(dom[2])
+        return _norm2(pts - c) <= f32(dom[2])
     if kind == "cut":
         # domainoperations/cut.py:39-42
         return contains(dom[1], pts) & ~contains(dom[2], pts)
@@ -181,9 +188,7 @@ def boundary_contains(bnd, pts):
             return (isclose(c1, f32(0)) | isclose(c1, f32(1))) & (c2 >= 0) & (c2 <= 1)
         return edge(bx, by) | edge(by, bx)
     if dom[0] == "circle":                                                             # circle.py:118-124
-        q = pts - np.asarray(dom[1], f32)
-        nrm = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1], dtype=f32)
-        return isclose(nrm, f32(dom[2]))
+        return isclose(_norm2(pts - np.asarray(dom[1], f32)), f32(dom[2]))
     raise ValueError(bnd)
 
 
@@ -196,7 +201,7 @@ def boundary_volume(bnd):
     if dom[0] == "parallelogram":
         o = np.asarray(dom[1], f32)
         d1, d2 = np.asarray(dom[2], f32) - o, np.asarray(dom[3], f32) - o
-        return f32(2) * (np.sqrt(d1 @ d1, dtype=f32) + np.sqrt(d2 @ d2, dtype=f32))
+        return f32(2) * (_norm2(d1[None])[0] + _norm2(d2[None])[0])
     if dom[0] == "circle":
         return f32(2 * np.pi) * f32(dom[2])
     raise ValueError(bnd)
@@ -206,7 +211,7 @@ def _walk(dom, loc):
     """parallelogram.py:220-246: walk the four sides, ``loc`` = arc length from the origin."""
     o = np.asarray(dom[1], f32)
     d1, d2 = np.asarray(dom[2], f32) - o, np.asarray(dom[3], f32) - o
-    s1, s2 = np.sqrt(d1 @ d1, dtype=f32), np.sqrt(d2 @ d2, dtype=f32)
+    s1, s2 = _norm2(d1[None])[0], _norm2(d2[None])[0]
     loc = np.asarray(loc, f32).copy()
     pts = np.zeros((len(loc), 2), f32)
     for d, s in ((d1, s1), (d2, s2), (-d1, s1), (-d2, s2)):
@@ -248,7 +253,7 @@ def boundary_normal(bnd, pts):
 
         def unit_normal(d):
             v = np.array([-d[1], d[0]], f32)
-            return v / np.sqrt(v @ v, dtype=f32)
+            return v / _norm2(v[None])[0]
         n1, n2 = unit_normal(d1), -unit_normal(d2)
         out = np.zeros((len(pts), 2), f32)
         for i in (0.0, 1.0):
@@ -256,5 +261,38 @@ def boundary_normal(bnd, pts):
             out += n1 * np.where(isclose(by, f32(i)), sgn, f32(0))[:, None]
             out += n2 * np.where(isclose(bx, f32(i)), sgn, f32(0))[:, None]
         with np.errstate(invalid="ignore", divide="ignore"):
-            return out / np.sqrt(out[:, 0] * out[:, 0] + out[:, 1] * out[:, 1], dtype=f32)[:, None]
+            return out / _norm2(out)[:, None]
     raise ValueError(bnd)
+
+
+# boundary of a cut A - B of two primitives: ("cutb", A, B)   (domainoperations/cut.py:111-201)
+def cut_boundary_contains(A, B, pts):
+    on_a, on_b = boundary_contains(("boundary", A), pts), boundary_contains(("boundary", B), pts)
+    return (on_a & ~contains(B, pts)) | (on_b & contains(A, pts) & ~on_a)
+
+
+def cut_boundary_normal(A, B, pts):
+    """normal of A where the point lies on A's boundary, minus the normal of B elsewhere (cut.py:191-201)."""
+    on_a = boundary_contains(("boundary", A), pts)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        na, nb = boundary_normal(("boundary", A), pts), boundary_normal(("boundary", B), pts)
+    return np.where(on_a[:, None], na, -nb)
+
+
+def cut_boundary_volume(A, B):
+    return boundary_volume(("boundary", A)) + boundary_volume(("boundary", B))
+
+
+def cut_boundary_grid(A, B, n):
+    """deterministic part of sampler_helper.py:211-256 (None when the reference would top up with random points)."""
+    def on_main(g):
+        return g[cut_boundary_contains(A, B, g)]
+    ga, gb = boundary_grid(("boundary", A), n), boundary_grid(("boundary", B), n)
+    ka, kb = on_main(ga), on_main(gb)
+    if len(ka) + len(kb) == n:
+        return np.concatenate([ka, kb])
+    sa, sb = boundary_volume(("boundary", A)), boundary_volume(("boundary", B))
+    approx = sa * f32(len(ka)) / f32(n) + sb * f32(len(kb)) / f32(n)
+    na, nb = int(f32(n) * sa / approx) + 1, max(int(f32(n) * sb / approx), 1)
+    out = np.concatenate([on_main(boundary_grid(("boundary", A), na)), on_main(boundary_grid(("boundary", B), nb))])
+    return out[:n] if len(out) >= n else None

@@ -280,6 +280,41 @@ def boundaries():
     save("boundaries", **out)
 
 
+# ---------------------------------------------------------------------------- boundary of a cut
+def cut_boundary():
+    """boundary of Circle - Parallelogram (a domain with a hole, hole contained) and of a Parallelogram
+    cut by an overlapping Circle (reference domainoperations/cut.py:111-201, sampler_helper.py:129-266)."""
+    X = tp.spaces.R2("x")
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    sq = tp.domains.Parallelogram(X, [-0.25, -0.25], [0.25, -0.25], [-0.25, 0.25])
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    bite = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    for nm, dom in (("hole", circ - sq), ("bite", para - bite)):
+        b = dom.boundary
+        ga = dom.domain_a.boundary.sample_grid(150).as_tensor
+        gb = dom.domain_b.boundary.sample_grid(150).as_tensor
+        on = torch.cat([ga, gb], dim=0)
+        far = torch.rand(300, 2, generator=g) * 3.0 - 1.5
+        cand = torch.cat([on, on + (torch.rand(on.shape, generator=g) * 4e-5 - 2e-5), far], dim=0)
+        inside = b._contains(tp.spaces.Points(cand.clone(), X)).reshape(-1)
+        out["cand_" + nm], out["in_" + nm] = cand, inside
+        onb = cand[inside]
+        out["on_" + nm] = onb
+        out["normal_" + nm] = b.normal(tp.spaces.Points(onb.clone(), X))
+        out["vol_" + nm] = b.volume().reshape(-1)
+        for n in (40, 200):
+            torch.manual_seed(32)
+            gr = b.sample_grid(n)
+            out[f"ngrid_{nm}_{n}"] = np.array(len(gr))
+            out[f"grid_{nm}_{n}"] = gr.as_tensor
+        torch.manual_seed(33)
+        r = b.sample_random_uniform(n=500)
+        out["n_random_" + nm] = np.array(len(r))
+    save("cut_boundary", **out)
+
+
 # ---------------------------------------------------------------------------- domains
 def domains():
     X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
@@ -332,3 +367,4 @@ if __name__ == "__main__":
     deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50)
     domains()
     boundaries()
+    cut_boundary()

@@ -318,3 +318,55 @@ def test_host_stream_sampler_delivers_batches_in_order():
         assert pts.space == X and torch.equal(pts.as_tensor.cpu(), batches[i % 3])
     with pytest.raises(ValueError):
         s.sample_points(device="cpu")
+
+
+def test_cut_boundary_matches_reference():
+    """boundary of A - B (a hole, and an overlapping bite): membership bit for bit, normals, volume, grid and
+    random point counts, every produced point on the boundary (reference cut.py:111-201)."""
+    import torchphysics_b200 as tp
+    from tests.test_oracle_golden import CUTS
+    G = load("cut_boundary")
+    X = tp.spaces.R2("x")
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    sq = tp.domains.Parallelogram(X, [-0.25, -0.25], [0.25, -0.25], [-0.25, 0.25])
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    bite = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    import warnings
+    for nm, dom in (("hole", circ - sq), ("bite", para - bite)):
+        A, B = CUTS[nm]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            b = dom.boundary
+            cand = tp.spaces.Points(torch.from_numpy(G["cand_" + nm]).cuda(), X)
+            assert np.array_equal(b._contains(cand).reshape(-1).cpu().numpy(), G["in_" + nm]), nm
+            assert abs(float(b.volume()) - float(G["vol_" + nm][0])) < 1e-5
+            nrm = b.normal(tp.spaces.Points(torch.from_numpy(G["on_" + nm]).cuda(), X)).cpu().numpy()
+            assert np.allclose(nrm, G["normal_" + nm], rtol=1e-6, atol=1e-7), nm
+            for n in (40, 200):
+                g = b.sample_grid(n, device="cuda").as_tensor.cpu().numpy()
+                assert len(g) == int(G[f"ngrid_{nm}_{n}"]) == n
+                if nm == "hole":
+                    assert np.allclose(g, G[f"grid_{nm}_{n}"], rtol=1e-6, atol=1e-6)
+            torch.manual_seed(7)
+            pts = b.sample_random_uniform(n=3000, device="cuda")
+            assert len(pts) == 3000
+            p = pts.as_tensor.cpu().numpy()
+            assert geometry.cut_boundary_contains(A, B, p).mean() > 0.97       # (skewed edges: brittle isclose)
+            on_a = geometry.boundary_contains(("boundary", A), p)
+            share_a = float(geometry.boundary_volume(("boundary", A)) / geometry.cut_boundary_volume(A, B))
+            if nm == "hole":                                                    # both boundaries are complete
+                assert abs(on_a.mean() - share_a) < 0.04
+            d = b.sample_random_uniform(d=50.0, device="cuda")
+            assert 0 < len(d) <= int(np.ceil(50.0 * float(b.volume()))) + 2
+    # Neumann condition on the boundary of the domain with a hole: normals feed tp.utils.normal_derivative
+    U = tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(16, 16)).cuda()
+    dom = circ - sq
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bnd = dom.boundary
+        cond = tp.conditions.PINNCondition(model, tp.samplers.RandomUniformSampler(bnd, n_points=256),
+                                           lambda u, x: tp.utils.normal_derivative(u, bnd.normal(x), x))
+        loss = cond(device="cuda")
+        loss.backward()
+    assert torch.isfinite(loss)

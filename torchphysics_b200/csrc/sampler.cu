@@ -41,6 +41,9 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r & 0x00FFFFFF
 __device__ __forceinline__ bool isclose32(float a, float b) {
   return fabsf(__fsub_rn(a, b)) <= __fadd_rn(1e-8f, __fmul_rn(1e-5f, fabsf(b)));
 }
+// torch.linalg.norm of a float32 pair as torch's CPU kernel evaluates it: sqrt(fma(y, y, x * x)) (pinned on the
+// borderline candidates of tests/golden/cut_boundary.npz)
+__device__ __forceinline__ float norm2(float x, float y) { return __fsqrt_rn(__fmaf_rn(y, y, __fmul_rn(x, x))); }
 // barycentric coordinates of a point in a parallelogram (parallelogram.py:96-103, Cramer's rule)
 __device__ __forceinline__ void bary(const tpx_shape& s, const float* q, float& bx, float& by) {
   const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
@@ -54,8 +57,7 @@ __device__ __forceinline__ void bary(const tpx_shape& s, const float* q, float& 
 __device__ __forceinline__ void para_walk(const tpx_shape& s, float loc, float* q) {
   const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
   const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
-  const float s1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
-  const float s2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
+  const float s1 = norm2(d1x, d1y), s2 = norm2(d2x, d2y);
   float x = 0.0f, y = 0.0f;
   const float dx[4] = {d1x, d2x, -d1x, -d2x}, dy[4] = {d1y, d2y, -d1y, -d2y}, len[4] = {s1, s2, s1, s2};
 #pragma unroll
@@ -71,9 +73,7 @@ __device__ __forceinline__ void para_walk(const tpx_shape& s, float loc, float* 
 __device__ __forceinline__ float para_perimeter(const tpx_shape& s) {
   const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
   const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
-  const float s1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1x, d1x), __fmul_rn(d1y, d1y)));
-  const float s2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2x, d2x), __fmul_rn(d2y, d2y)));
-  return __fmul_rn(2.0f, __fadd_rn(s1, s2));
+  return __fmul_rn(2.0f, __fadd_rn(norm2(d1x, d1y), norm2(d2x, d2y)));
 }
 // element j of torch.linspace(0, 1, steps) in float32
 __device__ __forceinline__ float lin01(int64_t j, int64_t steps) {
@@ -98,8 +98,7 @@ __device__ __forceinline__ bool shape_contains(const tpx_shape& s, const float* 
     }
     case TPX_SHAPE_CIRCLE: {
       const float dx = __fsub_rn(q[0], s.p[0]), dy = __fsub_rn(q[1], s.p[1]);
-      const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-      return nrm <= s.p[2];
+      return norm2(dx, dy) <= s.p[2];
     }
     case TPX_SHAPE_INTERVAL_BOUNDARY:
       return isclose32(q[0], s.p[0]) || isclose32(q[0], s.p[1]);
@@ -114,7 +113,7 @@ __device__ __forceinline__ bool shape_contains(const tpx_shape& s, const float* 
     }
     case TPX_SHAPE_CIRCLE_BOUNDARY: {
       const float dx = __fsub_rn(q[0], s.p[0]), dy = __fsub_rn(q[1], s.p[1]);
-      return isclose32(__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))), s.p[2]);
+      return isclose32(norm2(dx, dy), s.p[2]);
     }
     default:
       return false;
@@ -431,8 +430,7 @@ __global__ void normal_kernel(tpx_shape s, const float* __restrict__ pts, int64_
       const float d1x = __fsub_rn(s.p[2], s.p[0]), d1y = __fsub_rn(s.p[3], s.p[1]);
       const float d2x = __fsub_rn(s.p[4], s.p[0]), d2y = __fsub_rn(s.p[5], s.p[1]);
       // unit normals of the two directions: (-dy, dx) / |d|, the second one negated
-      const float l1 = __fsqrt_rn(__fadd_rn(__fmul_rn(d1y, d1y), __fmul_rn(d1x, d1x)));
-      const float l2 = __fsqrt_rn(__fadd_rn(__fmul_rn(d2y, d2y), __fmul_rn(d2x, d2x)));
+      const float l1 = norm2(-d1y, d1x), l2 = norm2(-d2y, d2x);
       const float n1x = __fdiv_rn(-d1y, l1), n1y = __fdiv_rn(d1x, l1);
       const float n2x = -__fdiv_rn(-d2y, l2), n2y = -__fdiv_rn(d2x, l2);
       float x = 0.0f, y = 0.0f;
@@ -443,7 +441,7 @@ __global__ void normal_kernel(tpx_shape s, const float* __restrict__ pts, int64_
         x = __fadd_rn(x, __fmul_rn(n1x, wy)); y = __fadd_rn(y, __fmul_rn(n1y, wy));
         x = __fadd_rn(x, __fmul_rn(n2x, wx)); y = __fadd_rn(y, __fmul_rn(n2y, wx));
       }
-      const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+      const float nrm = norm2(x, y);
       o[0] = __fdiv_rn(x, nrm);
       o[1] = __fdiv_rn(y, nrm);
     }

@@ -594,6 +594,128 @@ class CutDomain(_BooleanDomain):
         return Points(self._select(t, keep).to(device), self.space)
 
 
+class CutBoundaryDomain(Domain):
+    """Boundary of ``A - B`` for two basic shapes (reference ``domainoperations/cut.py:111-201``): the part of
+    A's boundary outside B plus the part of B's boundary inside A.  Membership is one region program over the
+    boundary shapes; random points alternate between the two boundaries with rejection by that program
+    (``sampler_helper.py:129-200``), appended in candidate order by the stable-compaction kernels."""
+
+    def __init__(self, domain):
+        a, b = domain.domain_a, domain.domain_b
+        if not (isinstance(a, _ShapeDomain) and isinstance(b, _ShapeDomain)) or isinstance(a, BoundaryDomain) \
+                or isinstance(b, BoundaryDomain):
+            raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "boundary of a cut: both operands must be basic shapes")
+        super().__init__(space=domain.space, dim=domain.dim - 1)
+        self.domain = domain
+        self.necessary_variables = domain.necessary_variables
+
+    def __call__(self, **data):
+        return self
+
+    def _box(self):
+        return self.domain._box()
+
+    def dim_cols(self):
+        return self.space.dim
+
+    def _program(self, col):
+        a, b = self.domain.domain_a, self.domain.domain_b
+        S, AND, OR, NOT = _lib.TPX_OP_SHAPE, _lib.TPX_OP_AND, _lib.TPX_OP_OR, _lib.TPX_OP_NOT
+        shapes = [a.boundary._shape(col), b._shape(col), b.boundary._shape(col), a._shape(col)]
+        # (on dA and not in B) or (on dB and in A and not on dA)
+        ops = [S | (0 << 8), S | (1 << 8), NOT, AND, S | (2 << 8), S | (3 << 8), AND, S | (0 << 8), NOT, AND, OR]
+        return shapes, ops
+
+    def _get_volume(self):
+        if not self.domain.contained:
+            warnings.warn("Exact volume of this domain is not known, will use the estimate: volume = "
+                          "domain_a.volume + domain_b.volume. If you need the exact volume for sampling, use "
+                          "domain.set_volume().")
+        return _F32(self.domain.domain_a.boundary._volume_value()) + _F32(self.domain.domain_b.boundary._volume_value())
+
+    def _variable_count_with_density(self):
+        return True
+
+    def _fill_random(self, out, col, n):
+        if n == 0:
+            return
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+        vm = _F32(self._volume_value())
+        scaled = [int(_F32(n) * _F32(a._volume_value()) / vm) + 1, int(_F32(n) * _F32(b._volume_value()) / vm) + 1]
+        rg = _region_struct(*self._program(col))
+        lib = _lib.lib()
+        key, offset = _rng.next_key(), 0
+        counters = torch.zeros(4, dtype=torch.int64, device=out.device)
+        filled, use_b, rounds = 0, 0, 0
+        while filled < n:
+            m = scaled[use_b]
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.tpx_sample_reject_workspace_bytes(ctypes.c_int64(m), ctypes.byref(nbytes)))
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=out.device)
+            gen = (b if use_b else a)._shape(col)
+            _lib.check(lib.tpx_sample_uniform_reject(
+                ctypes.byref(gen), ctypes.byref(rg), ctypes.c_uint64(key), ctypes.c_uint64(offset), ctypes.c_int64(m),
+                ctypes.c_int64(n), _lib.ptr(out), ctypes.c_int32(out.shape[1]), _lib.ptr(counters), _lib.ptr(ws),
+                ctypes.c_size_t(ws.numel()), _lib.stream_ptr()))
+            offset += m
+            filled = int(counters[0])
+            use_b = 1 - use_b
+            rounds += 1
+            if rounds > 4000:
+                raise RuntimeError("Rejection sampling on the cut boundary does not find enough points.")
+
+    def _masked(self, pts, keep):
+        return pts[keep.reshape(-1)]
+
+    def _parts_with_d(self, sample, d, params, device):
+        """density mode (cut.py:146-163 / 176-189): both boundaries at density d, A's part outside B, B's part
+        strictly inside A; the count varies."""
+        dev = _compute_device(device)
+        a, b = self.domain.domain_a, self.domain.domain_b
+        pa = sample(a.boundary, d, dev).as_tensor
+        pa = self._masked(pa, ~b._contains_rows(pa, 0, dev))
+        pb = sample(b.boundary, d, dev).as_tensor
+        pb = self._masked(pb, a._contains_rows(pb, 0, dev) & ~a.boundary._contains_rows(pb, 0, dev))
+        return Points(torch.cat([pa, pb], dim=0).to(device), self.space)
+
+    def _sample_random_with_d(self, d, params, device):
+        return self._parts_with_d(lambda dom, dd, dev: dom.sample_random_uniform(d=dd, device=dev), d, params, device)
+
+    def _sample_grid_with_d(self, d, params, device):
+        return self._parts_with_d(lambda dom, dd, dev: dom.sample_grid(d=dd, device=dev), d, params, device)
+
+    def _grid(self, n, dev, exact=True):
+        """sampler_helper.py:211-256: grids on both boundaries, kept where they lie on the cut's boundary; one
+        rescaling by the estimated boundary length; random points if still short."""
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+
+        def on_main(dom, m):
+            g = dom._grid(m, dev)
+            return self._masked(g, self._contains_rows(g, 0, dev))
+        ka, kb = on_main(a, n), on_main(b, n)
+        if len(ka) + len(kb) == n:
+            return torch.cat([ka, kb], dim=0)
+        sa, sb = _F32(a._volume_value()), _F32(b._volume_value())
+        approx = sa * _F32(len(ka)) / _F32(n) + sb * _F32(len(kb)) / _F32(n)
+        na, nb = int(_F32(n) * sa / approx) + 1, max(int(_F32(n) * sb / approx), 1)
+        g = torch.cat([on_main(a, na), on_main(b, nb)], dim=0)
+        if len(g) >= n:
+            return g[:n]
+        extra = torch.empty((n - len(g), self.space.dim), dtype=torch.float32, device=dev)
+        self._fill_random(extra, 0, n - len(g))
+        return torch.cat([g, extra], dim=0)
+
+    def normal(self, points, params=Points.empty(), device="cpu"):
+        if not isinstance(points, Points):
+            points = Points(points, self.space)
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+        on_a = a._contains(points)
+        return torch.where(on_a, a.normal(points), -b.normal(points))
+
+
+CutDomain.boundary = property(lambda self: CutBoundaryDomain(self))
+
+
 class IntersectionDomain(_BooleanDomain):
     """domain_a and domain_b (reference ``domainoperations/intersection.py:14-109``)."""
 
