@@ -13,23 +13,15 @@ def world():
 
 
 class FlatGradAllReduce:
-    """Flattens the gradients of ``params`` (+ ``n_scalars`` trailing slots) into one fp32
-    buffer, all-reduces it once (NCCL over NVLink on GPUs, gloo on CPU) and scatters the
-    mean back into ``.grad``.  Parameters without a gradient (``.grad is None``, which the
-    reference also leaves unset for parameters the loss does not depend on) contribute
-    zeros and stay ``None`` unless some rank produced a gradient."""
+    """Flattens the gradients of ``params`` (+ ``n_scalars`` trailing slots) into one fp32 buffer, all-reduces
+    it once (NCCL over NVLink on GPUs, gloo on CPU) and writes the mean back into ``.grad`` -- one concatenation,
+    one collective, one multi-tensor copy, no host synchronisation.  A parameter without a gradient
+    (``.grad is None``, which the reference also leaves unset for parameters the loss does not depend on) is
+    left out: which parameters receive gradients is a property of the program, identical on every rank."""
 
     def __init__(self, params, n_scalars=0):
         self.params = [p for p in params]
-        self.sizes = [p.numel() for p in self.params]
         self.n_scalars = n_scalars
-        self.total = sum(self.sizes) + n_scalars + len(self.params)   # + has-grad flags
-        self.buf = None
-
-    def _buffer(self, device):
-        if self.buf is None or self.buf.device != device:
-            self.buf = torch.zeros(self.total, dtype=torch.float32, device=device)
-        return self.buf
 
     def __call__(self, scalars=()):
         rank, size = world()
@@ -38,33 +30,18 @@ class FlatGradAllReduce:
         if size == 1:                       # nothing to exchange: gradients stay where backward left them
             return [s.detach().reshape(()).clone() if isinstance(s, torch.Tensor) else torch.tensor(float(s))
                     for s in scalars]
+        grads = [p.grad for p in self.params if p.grad is not None]
         device = self.params[0].device
-        buf = self._buffer(device)
-        buf.zero_()
-        off = 0
-        nparam = len(self.params)
-        flags = buf[self.total - nparam:]
-        for i, (p, n) in enumerate(zip(self.params, self.sizes)):
-            if p.grad is not None:
-                buf[off:off + n].copy_(p.grad.reshape(-1))
-                flags[i] = 1.0
-            off += n
-        for k, s in enumerate(scalars):
-            buf[off + k] = s.detach().reshape(()) if isinstance(s, torch.Tensor) else float(s)
-        if size > 1:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-            buf[: self.total - nparam].mul_(1.0 / size)
-        off = 0
-        have = flags.tolist() if size > 1 else None
-        for i, (p, n) in enumerate(zip(self.params, self.sizes)):
-            if size > 1 and have[i] > 0:
-                g = buf[off:off + n].view_as(p)
-                if p.grad is None:
-                    p.grad = g.clone()
-                else:
-                    p.grad.copy_(g)
-            off += n
-        return [buf[off + k].clone() for k in range(len(scalars))]
+        tail = [s.detach().reshape(1).to(device=device, dtype=torch.float32) if isinstance(s, torch.Tensor)
+                else torch.full((1,), float(s), device=device) for s in scalars]
+        flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads] + tail)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.mul_(1.0 / size)
+        sizes = [g.numel() for g in grads]
+        chunks = flat.split(sizes + [1] * len(tail))
+        if grads:
+            torch._foreach_copy_(grads, [c.view_as(g) for c, g in zip(chunks[:len(grads)], grads)])
+        return [c.reshape(()).clone() for c in chunks[len(grads):]]
 
 
 def shard_count(n_total, rank=None, size=None):
