@@ -296,3 +296,25 @@ def cut_boundary_grid(A, B, n):
     na, nb = int(f32(n) * sa / approx) + 1, max(int(f32(n) * sb / approx), 1)
     out = np.concatenate([on_main(boundary_grid(("boundary", A), na)), on_main(boundary_grid(("boundary", B), nb))])
     return out[:n] if len(out) >= n else None
+
+
+# boundary of a union A + B of two primitives (domainoperations/union.py:153-266)
+def union_boundary_contains(A, B, pts):
+    pts = np.asarray(pts, f32)
+    in_a, in_b = contains(A, pts), contains(B, pts)
+    on_a, on_b = boundary_contains(("boundary", A), pts), boundary_contains(("boundary", B), pts)
+    on_both = on_a & on_b
+    ok = np.ones(len(pts), bool)
+    if on_both.any():                       # a shared boundary piece counts only where the normals agree (:170-189)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            na = boundary_normal(("boundary", A), pts[on_both])
+            nb = boundary_normal(("boundary", B), pts[on_both])
+        ok[on_both] = (na * nb).sum(axis=1, dtype=f32) >= f32(0.5)
+    return ((on_a & ~in_b) | (on_b & ~in_a) | on_both) & ok
+
+
+def union_boundary_normal(A, B, pts):
+    on_a = boundary_contains(("boundary", A), pts)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        na, nb = boundary_normal(("boundary", A), pts), boundary_normal(("boundary", B), pts)
+    return np.where(on_a[:, None], na, nb)

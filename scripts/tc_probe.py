@@ -1,4 +1,5 @@
-"""Development aid: times the tensor-core forward / reverse kernels for config 1 (FCN 4x64, S=4)."""
+"""Development aid: times the tensor-core forward / reverse kernels for config 1 (FCN 4x64, S=4);
+`python scripts/tc_probe.py N dbgb` prints the clock64 timeline of one tile of the reverse kernel."""
 import sys
 
 import torch
@@ -81,33 +82,5 @@ def debug_bwd(N=1 << 18):
         print(f"mma l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(["a_w_ready", "issued", "d_done"], row) if v > 0))
 
 
-def debug_timestamps(N=1 << 18):
-    import ctypes
-    from torchphysics_b200 import _lib
-    torch.manual_seed(0)
-    seq = ref_autograd.build_fcn(2, 1, (64,) * 4).cuda()
-    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
-    spec = JetSpec((0, 1), (1.0, 1.0))
-    x = torch.rand(N, 2, device="cuda")
-    packed = eng.packed(eng.params())
-    buf = torch.zeros(512, dtype=torch.int64, device="cuda")
-    lib = _lib.lib()
-    lib.tpx_debug_set_timestamps(ctypes.c_void_p(buf.data_ptr()))
-    eng.forward_raw(packed, x, spec)
-    torch.cuda.synchronize()
-    lib.tpx_debug_set_timestamps(ctypes.c_void_p(0))
-    t = buf.cpu().numpy()
-    t0 = t[t > 0].min()
-    names = ["enter", "d_ready", "phase1", "bar", "phase2", "arrived"]
-    for q in range(4):
-        for l in range(4):
-            row = t[(q * 8 + l) * 8:(q * 8 + l) * 8 + 6]
-            print(f"q{q} l{l}: " + "  ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
-    for l in range(1, 4):
-        print(f"mma l{l}: a_ready={int(t[256 + l * 4] - t0)} issued={int(t[256 + l * 4 + 1] - t0)}")
-
-
-if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbg":
-    debug_timestamps()
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbgb":
     debug_bwd()

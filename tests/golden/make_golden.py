@@ -315,6 +315,38 @@ def cut_boundary():
     save("cut_boundary", **out)
 
 
+# ---------------------------------------------------------------------------- boundary of a union
+def union_boundary():
+    """boundary of Parallelogram + Circle (overlapping) and of two touching squares (shared edge: the
+    normal test of reference domainoperations/union.py:161-192)."""
+    X = tp.spaces.R2("x")
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    circ = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    sq1 = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    sq2 = tp.domains.Parallelogram(X, [1, 0], [2, 0], [1, 1])
+    out = {}
+    g = torch.Generator().manual_seed(41)
+    for nm, dom in (("lens", para + circ), ("touch", sq1 + sq2)):
+        b = dom.boundary
+        ga = dom.domain_a.boundary.sample_grid(150).as_tensor
+        gb = dom.domain_b.boundary.sample_grid(150).as_tensor
+        on = torch.cat([ga, gb], dim=0)
+        far = torch.rand(300, 2, generator=g) * 3.0 - 0.75
+        cand = torch.cat([on, on + (torch.rand(on.shape, generator=g) * 4e-5 - 2e-5), far], dim=0)
+        inside = b._contains(tp.spaces.Points(cand.clone(), X)).reshape(-1)
+        out["cand_" + nm], out["in_" + nm] = cand, inside
+        onb = cand[inside]
+        out["on_" + nm] = onb
+        out["normal_" + nm] = b.normal(tp.spaces.Points(onb.clone(), X))
+        out["vol_" + nm] = b.volume().reshape(-1)
+        for n in (40, 200):
+            torch.manual_seed(42)
+            out[f"ngrid_{nm}_{n}"] = np.array(len(b.sample_grid(n)))
+        torch.manual_seed(43)
+        out["n_random_" + nm] = np.array(len(b.sample_random_uniform(n=500)))
+    save("union_boundary", **out)
+
+
 # ---------------------------------------------------------------------------- domains
 def domains():
     X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
@@ -368,3 +400,4 @@ if __name__ == "__main__":
     domains()
     boundaries()
     cut_boundary()
+    union_boundary()

@@ -370,3 +370,39 @@ def test_cut_boundary_matches_reference():
         loss = cond(device="cuda")
         loss.backward()
     assert torch.isfinite(loss)
+
+
+def test_union_boundary_matches_reference():
+    """boundary of A + B: overlapping shapes and two squares sharing an edge (normal-agreement test of reference
+    union.py:161-192): membership bit for bit, normals, volume, counts."""
+    import warnings
+    import torchphysics_b200 as tp
+    from tests.test_oracle_golden import UNIONS
+    G = load("union_boundary")
+    X = tp.spaces.R2("x")
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    circ = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    sq1 = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    sq2 = tp.domains.Parallelogram(X, [1, 0], [2, 0], [1, 1])
+    for nm, dom in (("lens", para + circ), ("touch", sq1 + sq2)):
+        A, B = UNIONS[nm]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            b = dom.boundary
+            cand = tp.spaces.Points(torch.from_numpy(G["cand_" + nm]).cuda(), X)
+            assert np.array_equal(b._contains(cand).reshape(-1).cpu().numpy(), G["in_" + nm]), nm
+            assert abs(float(b.volume()) - float(G["vol_" + nm][0])) < 1e-5
+            nrm = b.normal(tp.spaces.Points(torch.from_numpy(G["on_" + nm]).cuda(), X)).cpu().numpy()
+            assert np.allclose(nrm, G["normal_" + nm], rtol=1e-6, atol=1e-7), nm
+            for n in (40, 200):
+                assert len(b.sample_grid(n, device="cuda")) == int(G[f"ngrid_{nm}_{n}"]) == n
+            torch.manual_seed(9)
+            p = b.sample_random_uniform(n=2000, device="cuda").as_tensor.cpu().numpy()
+            assert len(p) == 2000
+            if nm == "touch":                    # axis-aligned: the isclose membership is exact
+                assert geometry.union_boundary_contains(A, B, p).all()
+                assert not np.any(np.isclose(p[:, 0], 1.0) & (p[:, 1] > 1e-6) & (p[:, 1] < 1 - 1e-6))   # no shared edge
+            else:
+                assert geometry.union_boundary_contains(A, B, p).mean() > 0.97
+            d = b.sample_grid(d=30.0, device="cuda")
+            assert 0 < len(d) <= int(np.ceil(30.0 * float(b.volume()))) + 2

@@ -716,6 +716,71 @@ class CutBoundaryDomain(Domain):
 CutDomain.boundary = property(lambda self: CutBoundaryDomain(self))
 
 
+class UnionBoundaryDomain(CutBoundaryDomain):
+    """Boundary of ``A + B`` for two basic shapes (reference ``domainoperations/union.py:153-266``): the part of
+    each boundary outside the other domain; a piece that lies on BOTH boundaries counts only where the outward
+    normals agree (inner product >= 0.5), which a region program cannot express -- membership composes the
+    shape / normal kernels on the device, random points alternate between the two boundaries with that mask."""
+
+    overlap_tol = 0.5
+
+    def _program(self, col):
+        raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "the boundary of a union is not a region program")
+
+    def _contains_rows(self, rows, col, out_device):
+        a, b = self.domain.domain_a, self.domain.domain_b
+        dev = _compute_device(rows.device)
+        rows = rows.to(device=dev, dtype=torch.float32).contiguous()
+        in_a, in_b = a._contains_rows(rows, col, dev), b._contains_rows(rows, col, dev)
+        on_a, on_b = a.boundary._contains_rows(rows, col, dev), b.boundary._contains_rows(rows, col, dev)
+        on_both = on_a & on_b
+        pts = rows[:, col:col + self.space.dim]
+        agree = (a.boundary.normal(pts) * b.boundary.normal(pts)).sum(dim=-1, keepdim=True) >= self.overlap_tol
+        ok = torch.where(on_both, agree, torch.ones_like(on_both))
+        return (((on_a & ~in_b) | (on_b & ~in_a) | on_both) & ok).to(out_device)
+
+    def _get_volume(self):
+        if not self.domain.disjoint:
+            warnings.warn("Exact volume of this domain is not known, will use the estimate: volume = "
+                          "domain_a.volume + domain_b.volume. If you need the exact volume for sampling, use "
+                          "domain.set_volume().")
+        return _F32(self.domain.domain_a.boundary._volume_value()) + _F32(self.domain.domain_b.boundary._volume_value())
+
+    def _fill_random(self, out, col, n):
+        if n == 0:
+            return
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+        vm = _F32(self._volume_value())
+        scaled = [int(_F32(n) * _F32(a._volume_value()) / vm) + 1, int(_F32(n) * _F32(b._volume_value()) / vm) + 1]
+        filled, use_b, rounds = 0, 0, 0
+        while filled < n:                          # sampler_helper.py:166-200
+            cand = torch.zeros((scaled[use_b], out.shape[1]), dtype=torch.float32, device=out.device)
+            (b if use_b else a)._fill_random(cand, col, scaled[use_b])
+            good = self._masked(cand, self._contains_rows(cand, col, out.device))[:n - filled]
+            out[filled:filled + len(good), col:col + self.space.dim] = good[:, col:col + self.space.dim]
+            filled += len(good)
+            use_b = 1 - use_b
+            rounds += 1
+            if rounds > 4000:
+                raise RuntimeError("Rejection sampling on the union boundary does not find enough points.")
+
+    def _parts_with_d(self, sample, d, params, device):
+        """density mode (union.py:215-224 / 250-259): A's boundary outside B, B's boundary not strictly inside A."""
+        dev = _compute_device(device)
+        a, b = self.domain.domain_a, self.domain.domain_b
+        pa = sample(a.boundary, d, dev).as_tensor
+        pa = self._masked(pa, ~b._contains_rows(pa, 0, dev))
+        pb = sample(b.boundary, d, dev).as_tensor
+        pb = self._masked(pb, a.boundary._contains_rows(pb, 0, dev) | ~a._contains_rows(pb, 0, dev))
+        return Points(torch.cat([pa, pb], dim=0).to(device), self.space)
+
+    def normal(self, points, params=Points.empty(), device="cpu"):
+        if not isinstance(points, Points):
+            points = Points(points, self.space)
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+        return torch.where(a._contains(points), a.normal(points), b.normal(points))
+
+
 class IntersectionDomain(_BooleanDomain):
     """domain_a and domain_b (reference ``domainoperations/intersection.py:14-109``)."""
 
@@ -883,6 +948,9 @@ class ProductDomain(Domain):
     def sample_grid(self, n=None, d=None, params=Points.empty(), device="cpu"):
         raise NotImplementedError("Grid sampling on a product domain is not implmented. Use a product "
                                   "sampler instead.")
+
+
+UnionDomain.boundary = property(lambda self: UnionBoundaryDomain(self))
 
 
 # function sets / function samplers live in the same namespaces as in the reference
