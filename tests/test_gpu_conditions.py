@@ -237,3 +237,27 @@ def test_native_adam_equals_torch_adam():
     trainer = tp.solver.Trainer(max_steps=3)
     trainer.fit(solver)
     assert isinstance(trainer.optimizer, tp.optim.Adam)
+
+
+def test_operator_on_a_function_of_the_model_output_fails_loudly():
+    """grad(x * u, x) through torch.autograd would silently miss du/dx (the native evaluation has no graph to the
+    coordinates): the operators refuse instead of returning a wrong derivative."""
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import _lib
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(16, 16)).cuda()
+    coords, pts = tp.spaces.Points(torch.rand(64, 2).cuda(), X).track_coord_gradients()
+    u = model(pts).as_tensor
+    x = coords["x"]
+    with pytest.raises(_lib.TpxError):
+        tp.utils.grad(x[:, :1] * u, x)
+    with pytest.raises(_lib.TpxError):
+        tp.utils.laplacian(u * u, x)
+    # the supported spelling of the same thing: operators on the model output, combined by the product rule
+    g = tp.utils.grad(u, x)
+    want = torch.cat([u + x[:, :1] * g[:, :1], x[:, :1] * g[:, 1:]], dim=1)
+    assert want.shape == (64, 2)
+    hc = tp.models.HardConstraint(model, lambda u, x: x[:, :1] * (1 - x[:, :1]) * u)
+    out = hc(pts).as_tensor
+    with pytest.raises(_lib.TpxError):
+        tp.utils.laplacian(out, x)

@@ -197,10 +197,36 @@ def jet_of(t):
     return None, None
 
 
+def _derives_from_native_evaluation(t, limit=512):
+    """True if the autograd graph of ``t`` contains a native jet evaluation (``_FcnJetFn``): such a tensor
+    depends on the coordinates THROUGH the network, but its graph only reaches the parameters."""
+    fn = getattr(t, "grad_fn", None)
+    if fn is None:
+        return False
+    seen, todo = set(), [fn]
+    while todo and len(seen) < limit:
+        node = todo.pop()
+        if node is None or node in seen:
+            continue
+        seen.add(node)
+        if type(node).__name__ == "_FcnJetFnBackward":
+            return True
+        todo.extend(n for n, _ in node.next_functions)
+    return False
+
+
 def plain_of(t):
     """tensor with a torch.autograd graph to the coordinate leaves (generic operator path)."""
     ev, cols = jet_of(t)
     if ev is None:
+        if isinstance(t, torch.Tensor) and _derives_from_native_evaluation(t):
+            # e.g. laplacian(u ** 2, x) or a HardConstraint output: torch.autograd would silently drop the
+            # dependence on x through the network
+            from . import _lib
+            raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED,
+                                "a differential operator was applied to a FUNCTION of a native model output (only the "
+                                "model output itself, or column slices of it, carry derivative streams); apply the "
+                                "operator to the model output and combine the results (product / chain rule)")
         return t
     full = ev.plain()
     if cols == list(range(full.shape[-1])) and t.dim() == full.dim():
