@@ -347,6 +347,38 @@ def union_boundary():
     save("union_boundary", **out)
 
 
+# ---------------------------------------------------------------------------- hard constraint
+def poisson_hard_constraint(hidden, n, name):
+    """Poisson residual on tp.models.HardConstraint(FCN, g): the output transform g(u, x) = x1 (1 - x1) x2 (1 - x2) u
+    + sin(x1) of reference models/model.py:186-217 (chain rule through the network AND the explicit x dependence)."""
+    torch.manual_seed(14)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    inner = tp.models.FCN(X, U, hidden=hidden)
+
+    def g(u, x):
+        return x[:, :1] * (1 - x[:, :1]) * x[:, 1:] * (1 - x[:, 1:]) * u + torch.sin(x[:, :1])
+
+    model = tp.models.HardConstraint(inner, g)
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    torch.manual_seed(15)
+    pts = tp.samplers.RandomUniformSampler(sq, n_points=n).make_static()
+    x = pts.sample_points().as_tensor.clone()
+    captured = {}
+
+    def residual(u, x):
+        captured["u"] = u
+        captured["grad"] = tp.utils.grad(u, x)
+        captured["lap"] = tp.utils.laplacian(u, x)
+        return captured["lap"] + 1.0
+
+    cond = tp.conditions.PINNCondition(model, pts, residual)
+    model.zero_grad()
+    loss = cond(device="cpu")
+    loss.backward()
+    save(name, x=x, params=params_of(inner), u=captured["u"], grad=captured["grad"], lap=captured["lap"], loss=loss,
+         dtheta=grads_of(inner), hidden=np.array(hidden))
+
+
 # ---------------------------------------------------------------------------- domains
 def domains():
     X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
@@ -395,6 +427,7 @@ if __name__ == "__main__":
     navier_stokes((32, 32, 32), 130, "ns_3x32")
     deep_ritz((40, 40, 40, 40), 150, "ritz_4x40")
     heat_normalized((48, 48, 48), 161, "heat_norm_3x48")
+    poisson_hard_constraint((32, 32, 32), 143, "poisson_hard_3x32")
     deeponet(6, 40, 16, "deeponet_2x32")
     deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50)
     domains()

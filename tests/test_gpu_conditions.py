@@ -257,7 +257,36 @@ def test_operator_on_a_function_of_the_model_output_fails_loudly():
     g = tp.utils.grad(u, x)
     want = torch.cat([u + x[:, :1] * g[:, :1], x[:, :1] * g[:, 1:]], dim=1)
     assert want.shape == (64, 2)
-    hc = tp.models.HardConstraint(model, lambda u, x: x[:, :1] * (1 - x[:, :1]) * u)
-    out = hc(pts).as_tensor
-    with pytest.raises(_lib.TpxError):
-        tp.utils.laplacian(out, x)
+
+
+def test_hard_constraint_streams_by_chain_rule_match_reference():
+    """tp.models.HardConstraint(FCN, g) -- value, gradient and Laplacian of g(x, u(x)) from the native
+    streams of u by the chain rule, loss and dL/dtheta against the real reference's autograd."""
+    import warnings
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import jets
+    G = load("poisson_hard_3x32")
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    inner = tp.models.FCN(X, U, hidden=(32,) * 3).cuda()
+    _load_params(inner, G["params"])
+    model = tp.models.HardConstraint(
+        inner, lambda u, x: x[:, :1] * (1 - x[:, :1]) * x[:, 1:] * (1 - x[:, 1:]) * u + torch.sin(x[:, :1]))
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["x"]), X))
+    cap = {}
+
+    def residual(u, x):
+        cap.update(u=u, grad=tp.utils.grad(u, x), lap=tp.utils.laplacian(u, x))
+        return cap["lap"] + 1.0
+
+    cond = tp.conditions.PINNCondition(model, sampler, residual)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", jets.TpxFallbackWarning)
+        for _ in range(2):
+            inner.zero_grad(set_to_none=True)
+            loss = cond(device="cuda")
+            loss.backward()
+    for k in ("u", "grad", "lap"):
+        assert relerr(cap[k].detach().cpu().numpy(), G[k]) < TOL, k
+    assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
+    for a, w in zip(_grads(inner), G["dtheta"]):
+        assert relerr(a, w) < TOL

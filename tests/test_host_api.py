@@ -173,3 +173,39 @@ def test_flat_gradient_allreduce_gloo_world2():
         assert torch.allclose(g, lin.weight.grad, rtol=1e-5, atol=1e-5)
         assert abs(l - float(loss)) < 1e-4 * abs(float(loss))
         assert unused_none
+
+
+def test_constrained_evaluation_chain_rule_cpu():
+    """jets.ConstrainedEvaluation (the HardConstraint path) against the real reference's outputs, with a torch
+    stand-in for the jet engine (the chain rule itself is host logic)."""
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import jets
+    from torchphysics_b200.engine import JetSpec
+    from torchphysics_b200.userfn import UserFunction
+    from tests.golden_io import load, relerr
+    from tests.test_host_deeponet import _TorchJetEngine
+    G = load("poisson_hard_3x32")
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    lins = []
+    for i in range(len(G["params"]) // 2):
+        W, b = torch.as_tensor(G["params"][2 * i]), torch.as_tensor(G["params"][2 * i + 1])
+        lin = torch.nn.Linear(W.shape[1], W.shape[0])
+        with torch.no_grad():
+            lin.weight.copy_(W)
+            lin.bias.copy_(b)
+        lins.append(lin)
+    x = torch.from_numpy(G["x"])
+    leaf = x.clone().requires_grad_(True)
+    inner = jets.JetEvaluation(_TorchJetEngine(lins), x, x.shape[:-1], {id(leaf): (leaf, [0, 1])}, {}, None, None,
+                               JetSpec((0, 1), (1.0, 1.0)))
+    g = UserFunction(lambda u, x: x[:, :1] * (1 - x[:, :1]) * x[:, 1:] * (1 - x[:, 1:]) * u + torch.sin(x[:, :1]))
+    cev = jets.ConstrainedEvaluation(inner, g, {"x": leaf}, X, U, U)
+    assert relerr(cev.value().detach().numpy(), G["u"]) < 1e-6
+    grad = torch.cat([cev.first([0], 0), cev.first([0], 1)], dim=1)
+    assert relerr(grad.detach().numpy(), G["grad"]) < 1e-6
+    lap = cev.second([0])
+    assert relerr(lap.detach().numpy(), G["lap"]) < 1e-6
+    loss = ((lap + 1.0) ** 2).sum(dim=1).mean()
+    loss.backward()
+    for lin, (w, b) in zip(lins, zip(G["dtheta"][0::2], G["dtheta"][1::2])):
+        assert relerr(lin.weight.grad.numpy(), w) < 5e-6 and relerr(lin.bias.grad.numpy(), b) < 5e-6

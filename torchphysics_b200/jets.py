@@ -134,6 +134,106 @@ class JetEvaluation:
         return self._plain
 
 
+class ConstrainedEvaluation:
+    """Streams of ``g(x, y(x))`` for a pointwise output transform g of a native evaluation y (the reference's
+    ``HardConstraint``, ``models/model.py:186-217``) -- same protocol as ``JetEvaluation``.
+
+    Chain rule to second order along a coordinate direction e_k, with the partials of g taken by torch.autograd
+    on the pointwise function (the network is never re-traversed):
+        d_k out   = phi_k'(0),   phi_k(eps) = g(x + eps e_k, y + eps d_k y)
+        d_kk out  = phi_k''(0) + g_y . d_kk y
+    so the weighted Laplacian is  sum_k c_k phi_k''(0) + psi'(0),  psi(eps) = g(x, y + eps L y).
+    Every result keeps its graph to the streams of y, hence to the parameters."""
+
+    def __init__(self, inner, constraint, coords, in_space, out_space, inner_space):
+        self.inner = inner                       # JetEvaluation of the wrapped model
+        self.constraint = constraint             # UserFunction(coordinates + model outputs) -> tensor / tuple
+        self.coords = coords                     # {variable: leaf tensor} of the tracked points
+        self.in_space, self.out_space, self.inner_space = in_space, out_space, inner_space
+        self.batch_shape = inner.batch_shape
+        self._cache = {}
+
+    # -- helpers -------------------------------------------------------------------------
+    def _apply(self, x_shift, y):
+        """g on coordinates shifted by ``x_shift`` (dict column -> eps tensor) and model output ``y``."""
+        sl = self.in_space.column_slices()
+        args = {}
+        for name, leaf in self.coords.items():
+            v = leaf.detach()
+            if name in sl and x_shift:
+                cols = range(sl[name].start, sl[name].stop)
+                if any(c in x_shift for c in cols):
+                    v = torch.cat([v[..., i:i + 1] + x_shift[c] if c in x_shift else v[..., i:i + 1]
+                                   for i, c in enumerate(cols)], dim=-1)
+            args[name] = v
+        osl = self.inner_space.column_slices()
+        for name in self.inner_space:
+            args[name] = y[..., osl[name]]
+        res = self.constraint(args)
+        if isinstance(res, (tuple, list)):
+            res = torch.column_stack(res)
+        return res
+
+    def _path(self, k_col, dy, order):
+        """(phi'(0), phi''(0)) of phi(eps) = g(x + eps e_k, y + eps dy); k_col None keeps x fixed."""
+        y = self.inner.value()
+        eps = torch.zeros((*self.batch_shape, 1), device=y.device, dtype=y.dtype, requires_grad=True)
+        out = self._apply({} if k_col is None else {k_col: eps}, y + eps * dy)
+        d1 = torch.stack([torch.autograd.grad(out[..., m].sum(), eps, create_graph=True)[0][..., 0]
+                          for m in range(out.shape[-1])], dim=-1)
+        if order == 1:
+            return d1, None
+        d2 = torch.stack([_grad_or_zero(d1[..., m].sum(), eps)[..., 0] for m in range(out.shape[-1])], dim=-1)
+        return d1, d2
+
+    # -- JetEvaluation protocol ----------------------------------------------------------------
+    def columns_of(self, var):
+        return self.inner.columns_of(var)
+
+    def ensure(self, need):
+        self._cache.clear()
+        return self.inner.ensure(need)
+
+    @property
+    def spec(self):
+        return self.inner.spec
+
+    def value(self):
+        if "value" not in self._cache:
+            self._cache["value"] = self._apply({}, self.inner.value())
+        return self._cache["value"]
+
+    def _inner_first(self, in_col):
+        return self.inner.first(list(range(self.inner.engine.d_out)), in_col)
+
+    def first(self, out_cols, in_col):
+        key = ("d", in_col)
+        if key not in self._cache:
+            self._cache[key] = self._path(in_col, self._inner_first(in_col), 1)[0]
+        return JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
+
+    def second(self, out_cols):
+        if "lap" not in self._cache:
+            spec = self.inner.spec
+            acc = self._path(None, self.inner.second(list(range(self.inner.engine.d_out))), 1)[0]
+            for c, w in zip(spec.dcols, spec.lap_w):
+                if w != 0.0:
+                    acc = acc + w * self._path(c, self._inner_first(c), 2)[1]
+            self._cache["lap"] = acc
+        return JetEvaluation._columns(self._cache["lap"], out_cols, self._cache["lap"].dim() - 1)
+
+    def plain(self):
+        raise NotImplementedError("a constrained native evaluation has no generic autograd graph to the coordinates")
+
+
+def _grad_or_zero(scalar, eps):
+    """d scalar / d eps with create_graph, zeros where the graph does not reach eps (g linear along the path)."""
+    if not scalar.requires_grad:
+        return torch.zeros_like(eps)
+    g = torch.autograd.grad(scalar, eps, create_graph=True, allow_unused=True)[0]
+    return torch.zeros_like(eps) if g is None else g
+
+
 class JetTensor(torch.Tensor):
     """A tensor of model outputs that remembers its JetEvaluation and output columns."""
 

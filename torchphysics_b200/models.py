@@ -273,6 +273,14 @@ class HardConstraint(Model):
 
     def forward(self, points):
         out = self.model(points)
+        ev, cols = jets.jet_of(out.as_tensor)
+        leaves = getattr(points, "_coord_leaves", None)
+        if ev is not None and leaves is not None and cols == list(range(out.as_tensor.shape[-1])):
+            # native model: the streams of g(x, u(x)) follow from those of u by the chain rule (jets.ConstrainedEvaluation)
+            cev = jets.ConstrainedEvaluation(ev, self.constraint, leaves, self.model.input_space, self.output_space,
+                                             self.model.output_space)
+            value = cev.value()
+            return Points(jets.JetTensor.wrap(value, cev, range(value.shape[-1])), self.output_space)
         res = self.constraint(points.join(out).coordinates)
         if isinstance(res, torch.Tensor):
             return Points(res, self.output_space)
