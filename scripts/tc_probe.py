@@ -84,3 +84,36 @@ def debug_bwd(N=1 << 18):
 
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbgb":
     debug_bwd()
+
+
+def debug_fwd(N=1 << 18):
+    import ctypes
+    from torchphysics_b200 import _lib
+    torch.manual_seed(0)
+    seq = ref_autograd.build_fcn(2, 1, (64,) * 4).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    spec = JetSpec((0, 1), (1.0, 1.0))
+    x = torch.rand(N, 2, device="cuda")
+    packed = eng.packed(eng.params())
+    buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
+    lib = _lib.lib()
+    eng.forward_raw(packed, x, spec)
+    lib.tpx_debug_set_timestamps(ctypes.c_void_p(buf.data_ptr()))
+    eng.forward_raw(packed, x, spec)
+    torch.cuda.synchronize()
+    lib.tpx_debug_set_timestamps(ctypes.c_void_p(0))
+    t = buf.cpu().numpy()
+    t0 = t[t > 0].min()
+    names = ["enter", "d_ready", "in_bar", "computed", "out_bar", "arrived"]
+    for w, off in ((0, 0), (11, 256)):
+        for l in range(4):
+            row = t[off + l * 8: off + l * 8 + 6]
+            print(f"warp{w} l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
+    for l in range(1, 4):
+        for s in range(2):
+            row = t[512 + (l * 2 + s) * 2: 512 + (l * 2 + s) * 2 + 2]
+            print(f"mma l{l} slot{s}: a_ready={int(row[0] - t0)} issued={int(row[1] - t0)}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbgf":
+    debug_fwd()

@@ -163,8 +163,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       mbar_wait(&bar_w, ph_w);
       ph_w ^= 1;
       fence_after();
+#ifdef TPX_TIMELINE
       const bool mdbg = a.dbg && blockIdx.x == 0 && g >= 2 * nphase && g < 3 * nphase && lane == 0;
       if (mdbg) a.dbg[512 + l * 4 + 0] = clock64();
+#endif
       if (elect_one()) {
         const uint32_t wh = ring, wl = wh + 16384u;
         const uint32_t tD = tmem + T_D, tAh = tmem + T_AH, tAl = tmem + T_AL;
@@ -183,7 +185,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       // the weight image is free once the adjoint product is done: fetch the next image behind the activation warps' work
       mbar_wait(&bar_d, ph_d);
       ph_d ^= 1;
+#ifdef TPX_TIMELINE
       if (mdbg) a.dbg[512 + l * 4 + 1] = clock64();
+#endif
       if (g + 1 < total_phases) {
         if (elect_one()) bulk_load(sm + so.wring, phase_src(g + 1), 32768u, &bar_w);
         __syncwarp();
@@ -214,7 +218,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         mma_commit(&bar_f);                  // the gradient product only gates the reuse of its operands
       }
       __syncwarp();
+#ifdef TPX_TIMELINE
       if (mdbg) a.dbg[512 + l * 4 + 2] = clock64();
+#endif
     }
   } else {
     // =========================== activation warps ===========================
@@ -311,8 +317,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     };
     // in: adjoint product of the previous step, rows of this warp's stream -> exchange buffer -> all streams of
     // this thread's neurons
+#ifdef TPX_TIMELINE
     long long* dbgp = nullptr;
+#endif
+#ifdef TPX_TIMELINE
 #define TPX_STAMP(e) do { if (dbgp) dbgp[e] = clock64(); } while (0)
+#else
+#define TPX_STAMP(e) do { } while (0)
+#endif
     auto fetch_adjoint = [&](float (&ga)[S][B_NW]) {
       TPX_STAMP(0);
       mbar_wait(&bar_d, ph_d);
@@ -389,7 +401,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_z);
       TPX_STAMP(7);
+#ifdef TPX_TIMELINE
       if (dbgp) dbgp -= 16;
+#endif
     };
     auto add_bias = [&](int l, const float (&zb)[S][B_NW]) {
       const float r = reduce4(zb[0][0], zb[0][1], zb[0][2], zb[0][3], lane);
@@ -399,8 +413,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t gp = tile * TILE + lane;
       const bool valid = gp < a.n;
+#ifdef TPX_TIMELINE
       dbgp = (a.dbg && blockIdx.x == 0 && tile == blockIdx.x + 2 * (int64_t)gridDim.x && lane == 0 && (warp == 0 || warp == 7))
                  ? a.dbg + (warp == 0 ? 0 : 256) + (L - 1) * 16 : nullptr;
+#endif
       const float* ck_tile = a.ckpt + (size_t)tile * ((size_t)L * 4 * HP * TILE);
       float ck[S][B_NW], ckn[S][B_NW];       // checkpoints of the current layer and of the one below (prefetched)
       load_ck(ck_tile, L - 1, ck);

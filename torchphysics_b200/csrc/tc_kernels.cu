@@ -127,6 +127,7 @@ struct FwdArgs {
   int64_t n;
   float *u, *du, *lap;
   float* ckpt;      // optional: [tile][layer][4 arrays][64][32] checkpoints for the reverse kernel: tanh(z), d_k z, L z
+  long long* dbg;   // development: clock64 stamps of one tile (scripts/tc_probe.py N dbgf)
 };
 
 template <int ND, int LAP>
@@ -180,6 +181,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           mbar_wait(&bar_a[s], ph[s]);
           ph[s] ^= 1;
           fence_after();
+#ifdef TPX_TIMELINE
+          const bool mdbg = a.dbg && blockIdx.x == 0 && pair == blockIdx.x + 2 * (int64_t)gridDim.x && lane == 0;
+          if (mdbg) a.dbg[512 + (l * 2 + s) * 2] = clock64();
+#endif
           if (elect_one()) {
             const uint32_t tD = tmem + s * SLOT_COLS, tAh = tD + 64, tAl = tD + 128;
             const uint32_t wh = wbase + (uint32_t)((l - 1) * 2) * 16384u, wl = wh + 16384u;
@@ -195,6 +200,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             mma_commit(&bar_d[s]);
           }
           __syncwarp();
+#ifdef TPX_TIMELINE
+          if (mdbg) a.dbg[512 + (l * 2 + s) * 2 + 1] = clock64();
+#endif
         }
       }
     }
@@ -246,7 +254,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
 #pragma unroll
       for (int cc = 0; cc < TPX_MAX_DIN; ++cc) xr[cc] = (valid && cc < d_in) ? __ldg(a.x + gp * d_in + cc) : 0.0f;
 
+#ifdef TPX_TIMELINE
+      long long* dbgp = (a.dbg && blockIdx.x == 0 && pair == blockIdx.x + 2 * (int64_t)gridDim.x && lane == 0 && (warp == 0 || warp == 11))
+                            ? a.dbg + (warp == 0 ? 0 : 256) : nullptr;
+#endif
+#ifdef TPX_TIMELINE
+#define TPX_FSTAMP(e) do { if (dbgp) dbgp[l * 8 + (e)] = clock64(); } while (0)
+#else
+#define TPX_FSTAMP(e) do { } while (0)
+#endif
       for (int l = 0; l < L; ++l) {
+        TPX_FSTAMP(0);
         const float* bias = sm + so.small + lay.bias(l) + jw;
         const bool last = (l == L - 1);
         float z[S][8];                         // pre-activation streams, then activation streams, of 8 neurons
@@ -272,6 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           mbar_wait(&bar_d[slot], ph_d);
           ph_d ^= 1;
           fence_after();
+          TPX_FSTAMP(1);
           if (owner) {
 #pragma unroll
             for (int c = 0; c < NB / CH; ++c) {
@@ -283,6 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             }
           }
           named_bar_sync(barid, 128);
+          TPX_FSTAMP(2);
 #pragma unroll
           for (int s = 0; s < S; ++s) {
             const float4 lo4 = *reinterpret_cast<const float4*>(ex_cmp + s * TILE * EXP);
@@ -315,6 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             if (ckl) __stcs(ckl + ((S - 1) * HP + i) * TILE, lz);
           }
         }
+        TPX_FSTAMP(3);
         if (!last) {
           // ---- out: activation streams -> exchange buffer -> owners split hi / lo into the next A operand
 #pragma unroll
@@ -323,6 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             *reinterpret_cast<float4*>(ex_cmp + s * TILE * EXP + 4) = make_float4(z[s][4], z[s][5], z[s][6], z[s][7]);
           }
           named_bar_sync(barid, 128);
+          TPX_FSTAMP(4);
           if (owner) {
 #pragma unroll
             for (int c = 0; c < NB / CH; ++c) {
@@ -346,6 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_a[slot]);
+          TPX_FSTAMP(5);
         } else if (a.u != nullptr) {
           // ---- output layer (skipped by the checkpoint-only pass of the reverse sweep): every warp holds partial dot products over its 8 neurons for all streams; the 8
           // warps of the slot meet in shared memory, OC output columns per pass
@@ -458,6 +481,7 @@ int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float
   a.jet = jet;
   a.img = img; a.x = x; a.n = n; a.u = u; a.du = du; a.lap = lapo;
   a.ckpt = saved;
+  a.dbg = g_tc_debug;
   switch (jet.nd * 2 + lap) {
     case 0: return launch_tc_fwd<0, 0>(a, sm_count, stream);
     case 2: return launch_tc_fwd<1, 0>(a, sm_count, stream);
