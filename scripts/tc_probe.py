@@ -78,8 +78,8 @@ def debug_bwd(N=1 << 18):
             row = t[off + l * 16: off + l * 16 + 8]
             print(f"warp{w} l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(names, row) if v > 0))
     for l in (3, 2, 1):
-        row = t[512 + l * 4: 512 + l * 4 + 3]
-        print(f"mma l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(["a_w_ready", "issued", "d_done"], row) if v > 0))
+        row = t[512 + l * 4: 512 + l * 4 + 4]
+        print(f"mma l{l}: " + " ".join(f"{n}={int(v - t0)}" for n, v in zip(["a_w_ready", "adjoint_done", "dw_issued", "a_ready"], row) if v > 0))
 
 
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "dbgb":

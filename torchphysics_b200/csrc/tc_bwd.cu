@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       const bool first_tile = g < nphase;
       mbar_wait(&bar_a, ph_a);
       ph_a ^= 1;
+#ifdef TPX_TIMELINE
+      if (a.dbg && blockIdx.x == 0 && g >= 2 * nphase && g < 3 * nphase && lane == 0) a.dbg[512 + l * 4 + 3] = clock64();
+#endif
       mbar_wait(&bar_w, ph_w);
       ph_w ^= 1;
       fence_after();
