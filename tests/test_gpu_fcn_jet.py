@@ -113,6 +113,15 @@ CASES = [
     (4, 2, (20, 50, 30), "tanh", (3, 1), (0.0, 2.0), 77),
     (3, 1, (17,), "sin", (), None, 65),
     (2, 1, (32, 32), "tanh", (1,), None, 1),
+    # more shapes of the tensor-core path (width <= 64, tanh): 3 streams incl. an idle quadrant, value only,
+    # three directions without Laplacian, 6 hidden layers, 4 outputs, one input column, ragged tile counts
+    (1, 1, (64,) * 6, "tanh", (0,), (1.0,), 500),            # 6 hidden layers: beyond the resident-weight budget -> FP32 kernels
+    (1, 1, (64,) * 5, "tanh", (0,), (1.0,), 500),            # deepest tensor-core network (1 wide + 3 narrow dW accumulators)
+    (2, 1, (64,) * 2, "tanh", (0, 1), (1.0, 1.0), 700),       # shallowest (1 hidden matrix)
+    (2, 4, (48,) * 3, "tanh", (0, 1), None, 129),
+    (3, 2, (64, 64), "tanh", (), None, 95),
+    (3, 1, (40,) * 5, "tanh", (0, 1, 2), None, 257),
+    (4, 1, (64,) * 4, "tanh", (2, 0), (0.5, 1.5), 4099),
 ]
 
 

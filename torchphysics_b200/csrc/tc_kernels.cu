@@ -430,6 +430,9 @@ bool tc_net_supported(const tpx_fcn_desc* net) {
   for (int l = 0; l < net->n_hidden; ++l)
     if (net->widths[l] > HP) return false;
   if (net->d_out > 8) return false;
+  // all weight images stay resident in shared memory next to the exchange buffers: up to 4 hidden matrices
+  const TcLayout lay{net->n_hidden, net->d_in, net->d_out};
+  if ((size_t)fwd_smem(lay).total * sizeof(float) + 1024 > 227 * 1024) return false;
   return true;
 }
 
