@@ -118,6 +118,9 @@ CASES = [
     (1, 1, (64,) * 6, "tanh", (0,), (1.0,), 500),            # 6 hidden layers: beyond the resident-weight budget -> FP32 kernels
     (1, 1, (64,) * 5, "tanh", (0,), (1.0,), 500),            # deepest tensor-core network (1 wide + 3 narrow dW accumulators)
     (2, 1, (64,) * 2, "tanh", (0, 1), (1.0, 1.0), 700),       # shallowest (1 hidden matrix)
+    (6, 1, (32, 32), "tanh", (0, 5), None, 301),               # d_in > 4: tensor-core forward, FP32 reverse
+    (2, 6, (48, 48), "tanh", (0, 1), (1.0, 1.0), 222),         # d_out > 4: tensor-core forward, FP32 reverse
+    (8, 8, (64, 64, 64), "tanh", (7,), (3.0,), 64),
     (2, 4, (48,) * 3, "tanh", (0, 1), None, 129),
     (3, 2, (64, 64), "tanh", (), None, 95),
     (3, 1, (40,) * 5, "tanh", (0, 1, 2), None, 257),
