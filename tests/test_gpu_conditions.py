@@ -290,3 +290,68 @@ def test_hard_constraint_streams_by_chain_rule_match_reference():
     assert abs(float(loss) - float(G["loss"])) < TOL * abs(float(G["loss"]))
     for a, w in zip(_grads(inner), G["dtheta"]):
         assert relerr(a, w) < TOL
+
+
+def test_inverse_problem_parameter_and_parallel_models():
+    """a learnable tp.models.Parameter in the residual (reference models/parameter.py, condition.py:268,295-299) and
+    tp.models.Parallel of two native networks (model.py:95-146): loss and every gradient against torch autograd on
+    the same weights (oracle call sites)."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(21)
+    X, U, V, Dsp = tp.spaces.R2("x"), tp.spaces.R1("u"), tp.spaces.R1("v"), tp.spaces.R1("D")
+    net_u = tp.models.FCN(X, U, hidden=(32, 32)).cuda()
+    net_v = tp.models.FCN(X, V, hidden=(24, 24, 24)).cuda()
+    model = tp.models.Parallel(net_u, net_v)
+    D = tp.models.Parameter(init=0.7, space=Dsp)
+    x_np = np.random.default_rng(3).uniform(0, 1, size=(300, 2)).astype(np.float32)
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(x_np), X))
+
+    def residual(u, v, x, D):
+        return D * tp.utils.laplacian(u, x) + tp.utils.grad(v, x)[:, :1] * u - v
+
+    cond = tp.conditions.PINNCondition(model, sampler, residual, parameter=D, name="inverse")
+    assert any(n.endswith("inverse_params") for n, _ in cond.named_parameters())
+    cond = cond.cuda()
+    for _ in range(2):
+        cond.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+    # oracle: the same two networks and D with torch autograd on the CPU
+    su = ref_autograd.fcn_from_params([p.detach().cpu().numpy() for p in net_u._native_engine().params()])
+    sv = ref_autograd.fcn_from_params([p.detach().cpu().numpy() for p in net_v._native_engine().params()])
+    Dc = torch.tensor([[0.7]], requires_grad=True)
+    cols, xin = ref_autograd.track(torch.from_numpy(x_np), [("x", 2)])
+    u, v = su(xin), sv(xin)
+    r = Dc * ref_autograd.laplacian(u, cols["x"]) + ref_autograd.grad(v, cols["x"])[:, :1] * u - v
+    want = ref_autograd.pinn_loss(r)
+    ps = ref_autograd.linear_params(su) + ref_autograd.linear_params(sv) + [Dc]
+    gs = torch.autograd.grad(want, ps)
+    assert abs(float(loss) - float(want)) < TOL * abs(float(want))
+    got = [p.grad for p in net_u._native_engine().params()] + [p.grad for p in net_v._native_engine().params()]
+    for a, w in zip(got, gs[:-1]):
+        assert relerr(a.cpu().numpy(), w.numpy()) < TOL
+    dgrad = [p.grad for n, p in cond.named_parameters() if n.endswith("inverse_params")][0]
+    assert relerr(dgrad.cpu().numpy(), gs[-1].numpy()) < TOL
+
+
+def test_solver_sums_weighted_conditions():
+    """Solver.training_step = sum_c weight_c * loss_c (reference solver.py:100-109) over a PDE and a boundary condition."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(5)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(16, 16)).cuda()
+    sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
+    pde = tp.conditions.PINNCondition(model, tp.samplers.RandomUniformSampler(sq, n_points=200).make_static(),
+                                      lambda u, x: tp.utils.laplacian(u, x) + 1.0, weight=0.5, name="pde")
+    bc = tp.conditions.PINNCondition(model, tp.samplers.GridSampler(sq.boundary, n_points=64).make_static(),
+                                     lambda u: u, weight=3.0, name="bc")
+    solver = tp.solver.Solver([pde, bc])
+    solver.to("cuda")
+    solver._device = torch.device("cuda")
+    solver.on_train_start()
+    total = solver.training_step()
+    lp, lb = pde(device="cuda"), bc(device="cuda")
+    assert abs(float(total) - (0.5 * float(lp) + 3.0 * float(lb))) < 1e-6 * abs(float(total))
+    assert set(solver.logged) >= {"train/pde", "train/bc", "train/loss"}
+    total.backward()
+    assert all(p.grad is not None for p in model.parameters())

@@ -134,6 +134,51 @@ class JetEvaluation:
         return self._plain
 
 
+class JoinedEvaluation:
+    """Column-wise join of several native evaluations on the same tracked points (``tp.models.Parallel``,
+    reference ``models/model.py:95-146``): output column c belongs to ``parts[i]``'s column ``c - offset_i``."""
+
+    def __init__(self, parts):
+        self.parts = parts                       # [(evaluation, [its columns])]
+        self.index = [(ev, c) for ev, cols in parts for c in cols]
+        self.batch_shape = parts[0][0].batch_shape
+
+    def columns_of(self, var):
+        for ev, _ in self.parts:
+            cols = ev.columns_of(var)
+            if cols is not None:
+                return cols
+        return None
+
+    def ensure(self, need):
+        return all(ev.ensure(need) for ev, _ in self.parts)
+
+    def _gather(self, out_cols, fn):
+        pieces, run_ev, run_cols = [], None, []
+        for c in out_cols:                       # consecutive columns of one part -> one look-up
+            ev, sub = self.index[c]
+            if ev is not run_ev and run_cols:
+                pieces.append(fn(run_ev, run_cols))
+                run_cols = []
+            run_ev = ev
+            run_cols.append(sub)
+        if run_cols:
+            pieces.append(fn(run_ev, run_cols))
+        return pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=-1)
+
+    def value(self):
+        return self._gather(range(len(self.index)), lambda ev, cols: JetEvaluation._columns(ev.value(), cols, ev.value().dim() - 1))
+
+    def first(self, out_cols, in_col):
+        return self._gather(out_cols, lambda ev, cols: ev.first(cols, in_col))
+
+    def second(self, out_cols):
+        return self._gather(out_cols, lambda ev, cols: ev.second(cols))
+
+    def plain(self):
+        return torch.cat([JetEvaluation._columns(ev.plain(), cols, ev.plain().dim() - 1) for ev, cols in self.parts], dim=-1)
+
+
 class ConstrainedEvaluation:
     """Streams of ``g(x, y(x))`` for a pointwise output transform g of a native evaluation y (the reference's
     ``HardConstraint``, ``models/model.py:186-217``) -- same protocol as ``JetEvaluation``.

@@ -220,7 +220,17 @@ class Parallel(Model):
             if leaves is not None:
                 sub._coord_leaves = leaves
             outs.append(m(sub))
-        return Points.joined(*outs)
+        joined = Points.joined(*outs)
+        parts = [jets.jet_of(o.as_tensor) for o in outs]
+        leaves = getattr(points, "_coord_leaves", None) or {}
+        same_layout = all(ev is not None for ev, _ in parts) and all(
+            len({tuple(ev.columns_of(leaf) or ()) for ev, _ in parts}) == 1 and parts[0][0].columns_of(leaf) is not None
+            for leaf in leaves.values())
+        if same_layout:
+            # every member is a native evaluation: the joined output keeps its derivative streams
+            jev = jets.JoinedEvaluation(parts)
+            joined = Points(jets.JetTensor.wrap(joined.as_tensor, jev, range(joined.as_tensor.shape[-1])), joined.space)
+        return joined
 
 
 class Sequential(Model):
