@@ -355,3 +355,36 @@ def test_solver_sums_weighted_conditions():
     assert set(solver.logged) >= {"train/pde", "train/bc", "train/loss"}
     total.backward()
     assert all(p.grad is not None for p in model.parameters())
+
+
+def test_reference_flagship_example_runs_unchanged():
+    """examples/heat_equation.py = the code cells of the reference's examples/pinn/heat-equation.ipynb with only the
+    import changed (product domains with density sampling, adaptive sampler, boundary / boundary_left,
+    Sequential(NormalizationLayer, FCN), data functions, three conditions, Adam): it trains."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("heat_equation", os.path.join(root, "examples", "heat_equation.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(0)
+    losses = mod.main(60)
+    assert len(losses) == 60 and losses[-1] < 0.2 * losses[0]
+
+
+@pytest.mark.parametrize("kind", ["pinn", "ritz"])
+def test_reference_poisson_examples_run_unchanged(kind):
+    """examples/poisson_equation.py = the reference's examples/pinn/poisson-equation.ipynb and
+    examples/deepritz/poisson-equation.ipynb (disc with a square hole, `D.boundary`, density sampling)."""
+    import importlib.util
+    import os
+    import warnings
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("poisson_equation", os.path.join(root, "examples", "poisson_equation.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        losses, err = mod.main(kind, 150)
+    assert losses[-1] < 0.3 * losses[0] and err < 1.0
