@@ -86,6 +86,22 @@ def test_points_and_spaces():
         tp.spaces.Points(torch.ones(4, 2), sp)
 
 
+def test_integer_spaces_and_function_space_product():
+    """reference spaces/space.py:189-251 (cast_tensor_into_space) and functionspace.py (product)."""
+    import torchphysics_b200 as tp
+    z = tp.spaces.Z2("k")
+    assert z.dim == 2 and z.cast_tensor_into_space(torch.tensor([[-1.6, 2.4]])).tolist() == [[-2.0, 2.0]]
+    n = tp.spaces.N1("n")
+    assert n.cast_tensor_into_space(torch.tensor([[-1.6]])).tolist() == [[2.0]]
+    T, X = tp.spaces.R1("t"), tp.spaces.R2("x")
+    fa = tp.spaces.FunctionSpace(T, tp.spaces.R1("f"))
+    fb = tp.spaces.FunctionSpace(T * X, tp.spaces.R1("g"))
+    prod = fa * fb
+    assert list(prod.output_space.keys()) == ["f", "g"] and list(prod.input_space.keys()) == ["t", "x"]
+    with pytest.raises(AssertionError):
+        fa * fa
+
+
 def test_user_function_binds_by_name():
     import torchphysics_b200 as tp
     f = tp.utils.UserFunction(lambda u, x, k=2.0: u + k * x)

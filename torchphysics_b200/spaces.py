@@ -98,13 +98,86 @@ class Rn(Space):
         super().__init__({variable_name: int(n)})
 
 
+class IntegerSpace(Space):
+    """values are rounded to integers, the dtype stays (reference ``space.py:189-220``)."""
+
+    def __init__(self, variable_name, dim):
+        super().__init__({variable_name: int(dim)})
+
+    def cast_tensor_into_space(self, tensor):
+        return torch.round(tensor)
+
+
+class Z1(IntegerSpace):
+    def __init__(self, variable_name):
+        super().__init__(variable_name, 1)
+
+
+class Z2(IntegerSpace):
+    def __init__(self, variable_name):
+        super().__init__(variable_name, 2)
+
+
+class Z3(IntegerSpace):
+    def __init__(self, variable_name):
+        super().__init__(variable_name, 3)
+
+
+class Zn(IntegerSpace):
+    def __init__(self, variable_name, n):
+        super().__init__(variable_name, n)
+
+
+class NaturalNumberSpace(Space):
+    """rounded absolute values (reference ``space.py:223-251``)."""
+
+    def __init__(self, variable_name, dim):
+        super().__init__({variable_name: int(dim)})
+
+    def cast_tensor_into_space(self, tensor):
+        return torch.round(tensor).abs()
+
+
+class N1(NaturalNumberSpace):
+    def __init__(self, variable_name):
+        super().__init__(variable_name, 1)
+
+
+class N2(NaturalNumberSpace):
+    def __init__(self, variable_name):
+        super().__init__(variable_name, 2)
+
+
+class N3(NaturalNumberSpace):
+    def __init__(self, variable_name):
+        super().__init__(variable_name, 3)
+
+
+class Nn(NaturalNumberSpace):
+    def __init__(self, variable_name, n):
+        super().__init__(variable_name, n)
+
+
 class FunctionSpace:
-    """Space of functions input_space -> output_space (reference ``functionspace.py``)."""
+    """Space of functions input_space -> output_space (reference ``functionspace.py:1-35``)."""
 
     def __init__(self, input_domain, output_space):
         self.input_domain = input_domain
         self.input_space = input_domain.space if hasattr(input_domain, "space") else input_domain
         self.output_space = output_space
+
+    def __mul__(self, other):
+        """product: outputs side by side; the input space is the common one, the larger one, or the product."""
+        assert isinstance(other, FunctionSpace), "Can only multiply FunctionSpaces"
+        assert not (self.output_space == other.output_space), "Output spaces must be different"
+        out = self.output_space * other.output_space
+        if self.input_space == other.input_space:
+            return FunctionSpace(self.input_space, out)
+        if self.input_space in other.input_space:
+            return FunctionSpace(other.input_space, out)
+        if other.input_space in self.input_space:
+            return FunctionSpace(self.input_space, out)
+        return FunctionSpace(self.input_space * other.input_space, out)
 
 
 class Points:
