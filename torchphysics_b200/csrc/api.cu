@@ -250,6 +250,8 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
     if (rc) return cuda_fail("tc_fwd_kernel");
     return 0;
   }
+  if (saved && tcw_supported(net, jet->nd, a.lap))     // the launcher recorded the message
+    return tcw_forward(a.lay, a.jet, a.lap, packed, x, n, u, du, lap, saved, a.sm_count, a.stream);
   switch (a.lay.HP) {
     case 32: rc = launch_fwd<32>(a); break;
     case 64: rc = launch_fwd<64>(a); break;
@@ -275,7 +277,10 @@ int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_
   rc = check_jet(net, jet, &ja);
   if (rc) return rc;
   if (!bytes || n < 0) return fail(TPX_E_ARG, "bad argument");
-  *bytes = tc_bwd_supported(net, jet->nd, jet->lap ? 1 : 0) ? tc_saved_bytes(net, n) : 0;
+  const int lap = jet->lap ? 1 : 0;
+  if (tc_bwd_supported(net, jet->nd, lap)) *bytes = tc_saved_bytes(net, n);
+  else if (tcw_supported(net, jet->nd, lap)) *bytes = tcw_saved_bytes(net, jet->nd, lap, n);
+  else *bytes = 0;
   return 0;
 }
 
@@ -326,7 +331,12 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   a.gu = gu; a.gdu = jet->nd > 0 ? gdu : nullptr; a.glap = jet->lap ? glap : nullptr;
   a.gacc = grad_acc; a.ckpt = (float*)workspace; a.ckpt_bytes = workspace_bytes;
   a.stream = (cudaStream_t)stream;
-  if (saved && !tc_bwd_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel that reads saved checkpoints");
+  if (saved && !tc_bwd_supported(net, jet->nd, a.lap)) {
+    if (!tcw_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel that reads saved checkpoints");
+    const size_t need = tcw_saved_bytes(net, jet->nd, a.lap, n);
+    if (workspace_bytes < need) return fail(TPX_E_WORKSPACE, "saved buffer of %zu bytes < %zu", workspace_bytes, need);
+    return tcw_backward(a.lay, a.jet, a.lap, packed, x, n, a.gu, a.gdu, a.glap, grad_acc, (float*)workspace, a.sm_count, a.stream);
+  }
   if (tc_bwd_supported(net, jet->nd, a.lap)) {
     rc = tc_backward(net, a.lay, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
                      (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);

@@ -114,5 +114,27 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// tanh|x| = (1 - e) / (1 + e), e = e^{-2|x|}: ex2.approx (2^-22 relative) and rcp.approx refined by one Newton step;
+// absolute error <= 3e-7, which is what the next layer's sums see (measured parity: tests/test_gpu_fcn_jet.py)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -2.885390081777927f));   // e^{-2|x|} in (0, 1]
+  const float d = e + 1.0f;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  r = r * fmaf(-d, r, 2.0f);
+  return copysignf((1.0f - e) * r, x);
+}
+
 }  // namespace tc
 }  // namespace tpx

@@ -36,17 +36,6 @@ constexpr int CH = 16;             // neurons per register chunk
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SLOT_COLS = 192;  // D | A_hi | A_lo
 
-// tanh|x| = (1 - e) / (1 + e), e = e^{-2|x|}: ex2.approx (2^-22 relative) and rcp.approx refined by one Newton step;
-// absolute error <= 3e-7, which is what the next layer's sums see (measured parity: tests/test_gpu_fcn_jet.py)
-__device__ __forceinline__ float tanh_fast(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -2.885390081777927f));   // e^{-2|x|} in (0, 1]
-  const float d = e + 1.0f;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  r = r * fmaf(-d, r, 2.0f);
-  return copysignf((1.0f - e) * r, x);
-}
-
 struct TcPackArgs {
   const float* W[TPX_MAX_HIDDEN + 1];
   const float* b[TPX_MAX_HIDDEN + 1];

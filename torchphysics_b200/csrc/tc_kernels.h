@@ -20,5 +20,13 @@ int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet
                 int64_t n, const float* gu, const float* gdu, const float* glap, double* gacc, float* ckpt, size_t ckpt_bytes,
                 int saved, int sm_count, cudaStream_t stream);
 size_t tc_saved_bytes(const tpx_fcn_desc* net, int64_t n);   // activation-jet checkpoints of n points
+// wide path (hidden width 65..128, tcw_kernels.cu): layer-major launches through a saved-activation buffer
+bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap);
+size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n);   // checkpoints + reverse scratch
+int tcw_forward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
+                float* u, float* du, float* lapo, float* saved, int sm_count, cudaStream_t stream);
+int tcw_backward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
+                 const float* gu, const float* gdu, const float* glap, double* gacc, float* saved, int sm_count,
+                 cudaStream_t stream);
 extern long long* g_tc_debug;   // development: device buffer of >= 512 int64 timestamps, or NULL
 }  // namespace tpx

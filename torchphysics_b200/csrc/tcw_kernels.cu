@@ -1,0 +1,890 @@
+// Tensor-core (tcgen05 / TMEM) jet kernels for hidden widths 65..128 ("wide" path), tanh, <= 5 streams.
+//
+// Formulation: NEURONS ARE THE UMMA ROWS.  For a hidden matrix W (128 x 128, zero padded) and a tile of
+// P = 16 collocation points with S streams (value, d_k, weighted Laplacian), N = S * P columns:
+//     D[j][n] = sum_i W[j][i] B[n][i]          M = 128 (output neuron j), N = 16 S, K = 128 (input neuron i)
+//   * A = W lives in TMEM for the whole launch (hi | lo tf32 parts, 256 columns), so it costs no shared-memory
+//     bandwidth; B = the activation streams of the tile in shared memory (K-major, 128-byte swizzle, hi | lo);
+//     three tf32 products  W_hi B_hi + W_lo B_hi + W_hi B_lo  give fp32-grade accuracy (tc_common.cuh).
+//   * TMEM lane = neuron: the thread that reads row j of D owns ALL streams of ALL points of the tile for its
+//     neuron, so tanh, the jet formulas and their adjoints are thread-local -- no stream exchange through shared
+//     memory (the width-64 kernels, whose UMMA rows are (stream, point), need one per layer).
+//   * activations in HBM are [tile][n = s * 16 + p][128 neurons]: a warp of 32 consecutive neurons reads / writes
+//     128-byte rows, and the same rows are 128-byte rows of the K-major B operand (conflict-free scalar stores).
+//
+// The sweep is LAYER-MAJOR: one launch per hidden matrix and direction (a 128 x 128 matrix in split tf32 is
+// 128 KB: one matrix fills half of TMEM, and the reverse sweep's dW accumulators of all layers do not fit
+// on chip).  Per launch every CTA (persistent, one per SM) keeps the matrix in TMEM and streams tiles through a
+// two-stage pipeline: producer warps (global -> jets -> split -> shared), one MMA-issuer warp, four epilogue
+// warps (TMEM -> jets / adjoint jets -> global).  Kernels:
+//   w_layer_kernel<FWD>  ckpt_{l-1} (or x for l = 1) -> a_{l-1} -> z_l = W_l a_{l-1} + b_l -> ckpt_l = (tanh z, d_k z, L z)
+//   w_out_fwd_kernel     ckpt_{L-1} -> u, du, lap      (linear output layer, CUDA cores: d_out x 128 per stream)
+//   w_out_bwd_kernel     output adjoints -> dWL, dbL, Zbar_{L-1} (adjoint of the pre-activation streams), db_{L-1}
+//   w_dw_kernel          dW_l[j][i] += sum_n Zbar_l[n][j] a_{l-1}[n][i]   (A = Zbar^T in TMEM, written by its lane-bound
+//                        loader warps; B = a^T in shared memory, 16-byte stores of a thread's own row; K = n)
+//   w_layer_kernel<ADJ>  Abar_{l-1} = W_l^T Zbar_l -> adjoint jets with ckpt_{l-1} -> Zbar_{l-1}, db_{l-1} (l = 1: dW0, db0)
+// HBM traffic per point and hidden matrix: forward 2, adjoint 3, dW 2 activation rows of S * 512 bytes: these
+// kernels are HBM-bound, the tensor pipe is roughly half busy.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "fcn_common.cuh"
+#include "tc_common.cuh"
+#include "tc_kernels.h"
+#include "tpx_internal.h"
+
+namespace tpx {
+namespace tcw {
+
+using namespace tc;
+
+constexpr int HW = 128;            // padded hidden width = UMMA M
+constexpr int P = 16;              // points per tile
+constexpr int EPI_WARPS = 4;       // one per TMEM quadrant (lane = neuron)
+constexpr int PROD_WARPS = 8;
+constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;
+constexpr int THREADS = 32 * (MMA_WARP + 1);
+constexpr int MAXD = 4;            // d_in supported by the layer-0 code
+constexpr int MAXO = 8;            // d_out supported by the output-layer kernels
+constexpr int FWD = 0, ADJ = 1;
+
+// the wide kernels are HBM-bound: they can afford the library tanh (<= 2 ulp) instead of tc::tanh_fast
+#ifdef TPX_TCW_FAST_TANH
+__device__ __forceinline__ float tanh_w(float x) { return tanh_fast(x); }
+#else
+__device__ __forceinline__ float tanh_w(float x) { return tanhf(x); }
+#endif
+
+struct WArgs {
+  Layout lay;            // FP32 parameter image (HP = 128)
+  JetArgs jet;
+  const float* packed;
+  const float* x;
+  int64_t n;
+  int l;                 // hidden matrix 1..L-1
+  const float* in;       // FWD: ckpt_{l-1} (unused for l = 1); ADJ / DW: Zbar_l
+  const float* ck;       // ADJ / DW: ckpt_{l-1} (unused for l = 1)
+  float* out;            // FWD: ckpt_l; ADJ: Zbar_{l-1} (unused for l = 1)
+  double* gacc;
+};
+
+// layer-0 pre-activation of neuron i at one point: z = b0 + W0 x
+struct Layer0 {
+  float w[MAXD], b;
+  int d_in;
+  __device__ __forceinline__ void load(const Layout& lay, const float* __restrict__ packed, int i) {
+    d_in = lay.d_in;
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) w[c] = (c < d_in) ? __ldg(packed + lay.w0() + (size_t)c * HW + i) : 0.0f;
+    b = __ldg(packed + lay.b0() + i);
+  }
+  __device__ __forceinline__ float col(int c) const {
+    float r = w[0];
+#pragma unroll
+    for (int k = 1; k < MAXD; ++k) r = (c == k) ? w[k] : r;
+    return r;
+  }
+};
+
+// checkpoint streams (t = tanh z, d_k z, L z) -> activation streams, in place
+template <int ND, int LAP>
+__device__ __forceinline__ void jets_from_ckpt(float (&v)[1 + ND + LAP], const float (&lapw)[ND > 0 ? ND : 1]) {
+  const float t = v[0];
+  const float s1 = fmaf(-t, t, 1.0f);
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    const float dz = v[1 + k];
+    if (LAP) q = fmaf(lapw[k] * dz, dz, q);
+    v[1 + k] = s1 * dz;
+  }
+  if (LAP) v[ND + 1] = fmaf(-2.0f * t * s1, q, s1 * v[ND + 1]);
+}
+
+// adjoint of the activation jets: hb = adjoints of the activation streams (in), ck = checkpoint streams;
+// on return hb holds the adjoints of the pre-activation streams (oracle/jet_numpy.py jet_backward)
+template <int ND, int LAP>
+__device__ __forceinline__ void adjoint_jets(float (&hb)[1 + ND + LAP], const float (&ck)[1 + ND + LAP],
+                                             const float (&lapw)[ND > 0 ? ND : 1]) {
+  const float t = ck[0];
+  const float s1 = fmaf(-t, t, 1.0f);
+  const float s2 = -2.0f * t * s1;
+  float dot = 0.0f, q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    dot = fmaf(hb[1 + k], ck[1 + k], dot);
+    if (LAP) q = fmaf(lapw[k] * ck[1 + k], ck[1 + k], q);
+  }
+  float zb = fmaf(hb[0], s1, dot * s2);
+  if (LAP) {
+    const float lhb = hb[ND + 1];
+    const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
+    zb = fmaf(lhb, fmaf(s3, q, s2 * ck[ND + 1]), zb);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) hb[1 + k] = fmaf(hb[1 + k], s1, 2.0f * lhb * s2 * lapw[k] * ck[1 + k]);
+    hb[ND + 1] = lhb * s1;
+  } else {
+#pragma unroll
+    for (int k = 0; k < ND; ++k) hb[1 + k] *= s1;
+  }
+  hb[0] = zb;
+}
+
+// =============================================================================================================
+// forward / adjoint layer kernel
+// =============================================================================================================
+template <int ND, int LAP, int MODE>
+__global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  constexpr int NDX = ND > 0 ? ND : 1;
+  constexpr int STAGE = 2 * N * HW;          // floats: hi | lo
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[2], bar_empty[2], bar_dfull[2], bar_dempty[2];
+  __shared__ uint32_t tmem_slot;
+  float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const Layout lay = a.lay;
+  const int l = a.l;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.n + P - 1) / P;
+
+  if (warp == MMA_WARP) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_full[s], PROD_WARPS);
+      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bar_dfull[s], 1);
+      mbar_init(&bar_dempty[s], EPI_WARPS);
+    }
+    mbar_init_fence();
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+  // ---- the matrix (A operand) into TMEM: lane = row, columns [0,128) hi, [128,256) lo
+  if (warp < EPI_WARPS) {
+    const float* Wrow = a.packed + (MODE == FWD ? lay.w(l) : lay.wt(l)) + (size_t)(warp * 32 + lane) * HW;
+    const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < HW / 16; ++c) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wrow + c * 16) + v);
+        hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float h = tf32_hi(hi[e]);
+        lo[e] = tf32_hi(hi[e] - h);
+        hi[e] = h;
+      }
+      tmem_st16(tw + c * 16, hi);
+      tmem_st16(tw + HW + c * 16, lo);
+    }
+    tmem_wait_st();
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+
+  float lapw[NDX];
+  int dcol[NDX];
+#pragma unroll
+  for (int k = 0; k < NDX; ++k) {
+    lapw[k] = (k < ND) ? a.jet.lap_w[k] : 0.0f;
+    dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
+  }
+
+  if (warp == MMA_WARP) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t sbase = smem_u32(sm);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&bar_full[st], ph);
+      if (it >= 2) mbar_wait(&bar_dempty[st], ph ^ 1);
+      fence_after();
+      if (elect_one()) {
+        const uint32_t tD = tmem + 256 + st * 128;
+        const uint32_t bh = sbase + (uint32_t)st * (STAGE * 4), bl = bh + N * HW * 4;
+        // the small correction products first: the accumulator rounds toward zero on every add, and an add
+        // costs up to one ulp of the running sum (measured: interleaving the products triples the bias)
+#pragma unroll
+        for (int ks = 0; ks < HW / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (N * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tD, tmem + HW + ks * 8, desc_k_sw128(bh + off), idesc, ks > 0);
+          mma_tf32_ts(tD, tmem + ks * 8, desc_k_sw128(bl + off), idesc, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < HW / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (N * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tD, tmem + ks * 8, desc_k_sw128(bh + off), idesc, 1);
+        }
+        mma_commit(&bar_empty[st]);
+        mma_commit(&bar_dfull[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= EPI_WARPS) {
+    // =========================== producers: B operand of the tile ===========================
+    const int w = warp - EPI_WARPS, kb = w & 3, half = w >> 2;
+    const int i = kb * 32 + lane;
+    Layer0 l0;
+    float dz0[NDX];
+    if (MODE == FWD && l == 1) {
+      l0.load(lay, a.packed, i);
+#pragma unroll
+      for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
+    }
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      float* bh = sm + st * STAGE;
+      float* bl = bh + N * HW;
+      if (MODE == FWD) {
+        // rows n = s * P + p for this warp's 8 points
+        float v[8][S];
+        if (l == 1) {
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            const int64_t gp = tile * P + half * 8 + pp;
+            float z = l0.b;
+            if (gp < a.n) {
+#pragma unroll
+              for (int c = 0; c < MAXD; ++c)
+                if (c < l0.d_in) z = fmaf(l0.w[c], __ldg(a.x + gp * l0.d_in + c), z);
+            }
+            v[pp][0] = tanh_w(z);
+#pragma unroll
+            for (int k = 0; k < ND; ++k) v[pp][1 + k] = dz0[k];
+            if (LAP) v[pp][S - 1] = 0.0f;
+          }
+        } else {
+          const float* src = a.in + ((size_t)tile * N + half * 8) * HW + i;
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+            for (int s = 0; s < S; ++s) v[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
+        }
+        if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const int p = half * 8 + pp;
+          jets_from_ckpt<ND, LAP>(v[pp], lapw);
+          const bool valid = tile * P + p < a.n;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const float val = valid ? v[pp][s] : 0.0f;
+            const float h = tf32_hi(val);
+            const int o = swz128(s * P + p, i, N);
+            bh[o] = h;
+            bl[o] = tf32_hi(val - h);
+          }
+        }
+      } else {
+        // rows n in [half * N / 2, (half + 1) * N / 2): plain copy + split of Zbar_l
+        constexpr int RH = N / 2;
+        float v[RH];
+        const float* src = a.in + ((size_t)tile * N + half * RH) * HW + i;
+#pragma unroll
+        for (int r = 0; r < RH; ++r) v[r] = __ldcs(src + (size_t)r * HW);
+        if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+#pragma unroll
+        for (int r = 0; r < RH; ++r) {
+          const float h = tf32_hi(v[r]);
+          const int o = swz128(half * RH + r, i, N);
+          bh[o] = h;
+          bl[o] = tf32_hi(v[r] - h);
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[st]);
+    }
+  } else {
+    // =========================== epilogue: row j of D = all streams / points of neuron j ===========================
+    const int j = warp * 32 + lane;
+    const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + 256;
+    if (MODE == FWD) {
+      const float bias = __ldg(a.packed + lay.b(l) + j);
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        mbar_wait(&bar_dfull[st], (it >> 1) & 1);
+        fence_after();
+        float* dst = a.out + (size_t)tile * N * HW + j;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float d[16];
+          tmem_ld16(tq + st * 128 + s * P, d);
+          if (s == S - 1) {                    // D of this stage is in registers: hand it back to the MMA warp
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_dempty[st]);
+          }
+          if (s == 0) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) d[p] = tanh_w(d[p] + bias);
+          }
+#pragma unroll
+          for (int p = 0; p < P; ++p) __stcs(dst + (size_t)(s * P + p) * HW, d[p]);
+        }
+      }
+    } else {
+      // adjoint jets with the checkpoints of layer l-1; for l = 1 the gradient of the first layer
+      Layer0 l0;
+      float dz0[NDX];
+      if (l == 1) {
+        l0.load(lay, a.packed, j);
+#pragma unroll
+        for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
+      }
+      double acc_db = 0.0, acc_w0[MAXD];
+#pragma unroll
+      for (int c = 0; c < MAXD; ++c) acc_w0[c] = 0.0;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int st = it & 1;
+        float part_db = 0.0f, part_w0[MAXD];
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) part_w0[c] = 0.0f;
+        const float* cks = a.ck + (size_t)tile * N * HW + j;
+        float* dst = a.out + (size_t)tile * N * HW + j;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float ck[8][S], xr[8][MAXD];
+          if (l == 1) {
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp) {
+              const int64_t gp = tile * P + h * 8 + pp;
+              float z = l0.b;
+#pragma unroll
+              for (int c = 0; c < MAXD; ++c) {
+                xr[pp][c] = (gp < a.n && c < l0.d_in) ? __ldg(a.x + gp * l0.d_in + c) : 0.0f;
+                z = fmaf(l0.w[c], xr[pp][c], z);
+              }
+              ck[pp][0] = tanh_w(z);
+#pragma unroll
+              for (int k = 0; k < ND; ++k) ck[pp][1 + k] = dz0[k];
+              if (LAP) ck[pp][S - 1] = 0.0f;
+            }
+          } else {
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+              for (int s = 0; s < S; ++s) ck[pp][s] = __ldcs(cks + (size_t)(s * P + h * 8 + pp) * HW);
+          }
+          if (h == 0) {
+            mbar_wait(&bar_dfull[st], (it >> 1) & 1);
+            fence_after();
+          }
+          float ab[S][8];
+#pragma unroll
+          for (int s = 0; s < S; ++s) tmem_ld8(tq + st * 128 + s * P + h * 8, ab[s]);
+          if (h == 1) {
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_dempty[st]);
+          }
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) {
+            float hb[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) hb[s] = ab[s][pp];
+            adjoint_jets<ND, LAP>(hb, ck[pp], lapw);
+            part_db += hb[0];
+            if (l == 1) {
+#pragma unroll
+              for (int c = 0; c < MAXD; ++c) {
+                float g = hb[0] * xr[pp][c];
+#pragma unroll
+                for (int k = 0; k < ND; ++k) g += (dcol[k] == c) ? hb[1 + k] : 0.0f;
+                part_w0[c] += g;
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < S; ++s) __stcs(dst + (size_t)(s * P + h * 8 + pp) * HW, hb[s]);
+            }
+          }
+        }
+        acc_db += (double)part_db;
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c) acc_w0[c] += (double)part_w0[c];
+      }
+      atomicAdd(a.gacc + (l == 1 ? lay.b0() : lay.b(l - 1)) + j, acc_db);
+      if (l == 1) {
+#pragma unroll
+        for (int c = 0; c < MAXD; ++c)
+          if (c < lay.d_in) atomicAdd(a.gacc + lay.w0() + (size_t)c * HW + j, acc_w0[c]);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================================
+// dW kernel: dW_l[j][i] += sum_n Zbar_l[n][j] a_{l-1}[n][i]
+// =============================================================================================================
+template <int ND, int LAP>
+__global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  constexpr int NDX = ND > 0 ? ND : 1;
+  constexpr int KA = (N + 31) / 32;          // 32-float K atoms of the a^T operand
+  constexpr int HALF = KA * HW * 32;         // floats of its hi (or lo) part
+  constexpr int STAGE = 2 * HALF;
+  constexpr uint32_t ZCOLS = 160;            // TMEM columns of one Zbar^T stage (hi N | lo N), N <= 80
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_fa[2], bar_fz[2], bar_empty[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const Layout lay = a.lay;
+  const int l = a.l;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t ntiles = (a.n + P - 1) / P;
+
+  if (warp == MMA_WARP) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_fa[s], PROD_WARPS);
+      mbar_init(&bar_fz[s], EPI_WARPS);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    mbar_init_fence();
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  float lapw[NDX];
+  int dcol[NDX];
+#pragma unroll
+  for (int k = 0; k < NDX; ++k) {
+    lapw[k] = (k < ND) ? a.jet.lap_w[k] : 0.0f;
+    dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
+  }
+
+  if (warp == MMA_WARP) {
+    constexpr uint32_t idesc = idesc_tf32(128, HW);
+    const uint32_t sbase = smem_u32(sm);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&bar_fa[st], ph);
+      mbar_wait(&bar_fz[st], ph);
+      fence_after();
+      if (elect_one()) {
+        const uint32_t zh = tmem + HW + st * ZCOLS, zl = zh + N;
+        const uint32_t ah = sbase + (uint32_t)st * (STAGE * 4), al = ah + HALF * 4;
+#pragma unroll
+        for (int ks = 0; ks < N / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (HW * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tmem, zh + ks * 8, desc_k_sw128(ah + off), idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32_ts(tmem, zl + ks * 8, desc_k_sw128(ah + off), idesc, 1);
+          mma_tf32_ts(tmem, zh + ks * 8, desc_k_sw128(al + off), idesc, 1);
+        }
+        mma_commit(&bar_empty[st]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&bar_done);
+    __syncwarp();
+  } else if (warp >= EPI_WARPS) {
+    // =========================== producers: a_{l-1}^T, row = neuron i, K = n ===========================
+    const int w = warp - EPI_WARPS, kb = w & 3, half = w >> 2;
+    const int i = kb * 32 + lane;
+    Layer0 l0;
+    float dz0[NDX];
+    if (l == 1) {
+      l0.load(lay, a.packed, i);
+#pragma unroll
+      for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
+    }
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      float* ah = sm + st * STAGE;
+      float* al = ah + HALF;
+      float v[8][S];
+      if (l == 1) {
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const int64_t gp = tile * P + half * 8 + pp;
+          float z = l0.b;
+          if (gp < a.n) {
+#pragma unroll
+            for (int c = 0; c < MAXD; ++c)
+              if (c < l0.d_in) z = fmaf(l0.w[c], __ldg(a.x + gp * l0.d_in + c), z);
+          }
+          v[pp][0] = tanh_w(z);
+#pragma unroll
+          for (int k = 0; k < ND; ++k) v[pp][1 + k] = dz0[k];
+          if (LAP) v[pp][S - 1] = 0.0f;
+        }
+      } else {
+        const float* src = a.ck + ((size_t)tile * N + half * 8) * HW + i;
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+          for (int s = 0; s < S; ++s) v[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
+      }
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) jets_from_ckpt<ND, LAP>(v[pp], lapw);
+      if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int n0 = s * P + half * 8;                 // 8 consecutive K positions = two 16-byte chunks
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float4 h4, l4;
+          float vv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) vv[e] = v[c * 4 + e][s];
+          h4.x = tf32_hi(vv[0]); h4.y = tf32_hi(vv[1]); h4.z = tf32_hi(vv[2]); h4.w = tf32_hi(vv[3]);
+          l4.x = tf32_hi(vv[0] - h4.x); l4.y = tf32_hi(vv[1] - h4.y); l4.z = tf32_hi(vv[2] - h4.z); l4.w = tf32_hi(vv[3] - h4.w);
+          const int o = swz128(i, n0 + c * 4, HW);
+          *reinterpret_cast<float4*>(ah + o) = h4;
+          *reinterpret_cast<float4*>(al + o) = l4;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_fa[st]);
+    }
+  } else {
+    // =========================== Zbar^T loaders (lane = neuron j), then the dW read-out ===========================
+    const int j = warp * 32 + lane;
+    const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const float* src = a.in + (size_t)tile * N * HW + j;
+      const uint32_t zh = tq + HW + st * ZCOLS, zl = zh + N;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int p = 0; p < P; ++p) hi[p] = __ldcs(src + (size_t)(s * P + p) * HW);
+        if (s == 0 && it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const float h = tf32_hi(hi[p]);
+          lo[p] = tf32_hi(hi[p] - h);
+          hi[p] = h;
+        }
+        tmem_st16(zh + s * P, hi);
+        tmem_st16(zl + s * P, lo);
+      }
+      tmem_wait_st();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_fz[st]);
+    }
+    mbar_wait(&bar_done, 0);
+    fence_after();
+    double* g = a.gacc + lay.w(l) + (size_t)j * HW;
+#pragma unroll 1
+    for (int c = 0; c < HW / 16; ++c) {
+      float d[16];
+      tmem_ld16(tq + c * 16, d);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) atomicAdd(g + c * 16 + e, (double)d[e]);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================================
+// output layer (CUDA cores): one warp per point, lane owns neurons lane + 32 c
+// =============================================================================================================
+constexpr int OUT_THREADS = 256;
+
+template <int ND, int LAP>
+__global__ void __launch_bounds__(OUT_THREADS) w_out_fwd_kernel(WArgs a, float* __restrict__ u, float* __restrict__ du,
+                                                                float* __restrict__ lapo) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  constexpr int NDX = ND > 0 ? ND : 1;
+  __shared__ float WL[MAXO * HW];
+  const Layout lay = a.lay;
+  const int d_out = lay.d_out;
+  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + v);
+  __syncthreads();
+  float lapw[NDX];
+#pragma unroll
+  for (int k = 0; k < NDX; ++k) lapw[k] = (k < ND) ? a.jet.lap_w[k] : 0.0f;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (OUT_THREADS / 32);
+  for (int64_t pt = (int64_t)blockIdx.x * (OUT_THREADS / 32) + (threadIdx.x >> 5); pt < a.n; pt += nwarps) {
+    const int64_t tile = pt / P;
+    const int p = (int)(pt % P);
+    const float* src = a.in + ((size_t)tile * N + p) * HW + lane;
+    float v[4][S];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int s = 0; s < S; ++s) v[c][s] = __ldcs(src + (size_t)s * P * HW + c * 32);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) jets_from_ckpt<ND, LAP>(v[c], lapw);
+    for (int o = 0; o < d_out; ++o) {
+      float r[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc = fmaf(WL[o * HW + c * 32 + lane], v[c][s], acc);
+        r[s] = acc;
+      }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1)
+#pragma unroll
+        for (int s = 0; s < S; ++s) r[s] += __shfl_xor_sync(0xFFFFFFFFu, r[s], m);
+      if (lane == 0) {
+        u[pt * d_out + o] = r[0] + __ldg(a.packed + lay.bl() + o);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) du[(pt * d_out + o) * ND + k] = r[1 + k];
+        if (LAP) lapo[pt * d_out + o] = r[S - 1];
+      }
+    }
+  }
+}
+
+// output adjoints -> Zbar_{L-1} (written for every row of every tile, zeros for the padding points), dWL, dbL, db_{L-1}
+template <int ND, int LAP>
+__global__ void __launch_bounds__(OUT_THREADS) w_out_bwd_kernel(WArgs a, const float* __restrict__ gu, const float* __restrict__ gdu,
+                                                                const float* __restrict__ glap) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  constexpr int NDX = ND > 0 ? ND : 1;
+  __shared__ float WL[MAXO * HW];
+  __shared__ float red[(MAXO + 1) * HW + MAXO];
+  const Layout lay = a.lay;
+  const int d_out = lay.d_out;
+  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + v);
+  for (int v = threadIdx.x; v < (MAXO + 1) * HW + MAXO; v += OUT_THREADS) red[v] = 0.0f;
+  __syncthreads();
+  float lapw[NDX];
+#pragma unroll
+  for (int k = 0; k < NDX; ++k) lapw[k] = (k < ND) ? a.jet.lap_w[k] : 0.0f;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (OUT_THREADS / 32);
+  const int64_t npad = (a.n + P - 1) / P * P;
+  float acc_wl[MAXO][4], acc_db[4], acc_bl = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    acc_db[c] = 0.0f;
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) acc_wl[o][c] = 0.0f;
+  }
+  for (int64_t pt = (int64_t)blockIdx.x * (OUT_THREADS / 32) + (threadIdx.x >> 5); pt < npad; pt += nwarps) {
+    const int64_t tile = pt / P;
+    const int p = (int)(pt % P);
+    const bool valid = pt < a.n;
+    const float* src = a.in + ((size_t)tile * N + p) * HW + lane;
+    float* dst = a.out + ((size_t)tile * N + p) * HW + lane;
+    float ck[4][S];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int s = 0; s < S; ++s) ck[c][s] = __ldcs(src + (size_t)s * P * HW + c * 32);
+    float g[MAXO][S];
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      const bool on = valid && o < d_out;
+      g[o][0] = (on && gu) ? __ldg(gu + pt * d_out + o) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) g[o][1 + k] = (on && gdu) ? __ldg(gdu + (pt * d_out + o) * ND + k) : 0.0f;
+      if (LAP) g[o][S - 1] = (on && glap) ? __ldg(glap + pt * d_out + o) : 0.0f;
+    }
+    if (lane < MAXO) {
+      float t = 0.0f;
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o) t = (lane == o) ? g[o][0] : t;
+      acc_bl += t;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float act[S], hb[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) { act[s] = ck[c][s]; hb[s] = 0.0f; }
+      jets_from_ckpt<ND, LAP>(act, lapw);
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o) {
+        if (o < d_out) {
+          const float w = WL[o * HW + c * 32 + lane];
+          float dw = 0.0f;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            hb[s] = fmaf(w, g[o][s], hb[s]);
+            dw = fmaf(g[o][s], act[s], dw);
+          }
+          acc_wl[o][c] += dw;
+        }
+      }
+      adjoint_jets<ND, LAP>(hb, ck[c], lapw);
+      acc_db[c] += hb[0];
+#pragma unroll
+      for (int s = 0; s < S; ++s) __stcs(dst + (size_t)s * P * HW + c * 32, hb[s]);
+    }
+  }
+  // CTA-level reduction in shared memory, then one float64 atomic per element and CTA
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    atomicAdd(&red[MAXO * HW + c * 32 + lane], acc_db[c]);
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o)
+      if (o < d_out) atomicAdd(&red[o * HW + c * 32 + lane], acc_wl[o][c]);
+  }
+  if (lane < MAXO) atomicAdd(&red[(MAXO + 1) * HW + lane], acc_bl);
+  __syncthreads();
+  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.wl() + v, (double)red[v]);
+  for (int v = threadIdx.x; v < HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.b(lay.L - 1) + v, (double)red[MAXO * HW + v]);
+  if (threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(MAXO + 1) * HW + threadIdx.x]);
+}
+
+static int env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
+template <int ND, int LAP>
+struct Launch {
+  static constexpr int S = 1 + ND + LAP, N = S * P;
+  static size_t layer_smem() { return (size_t)2 * 2 * N * HW * sizeof(float) + 1024; }
+  static size_t dw_smem() { return (size_t)2 * 2 * ((N + 31) / 32) * HW * 32 * sizeof(float) + 1024; }
+
+  template <class K>
+  static int set_smem(K kernel, size_t bytes, const char* what) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(TPX_E_CUDA, "%s: shared memory attribute (%zu bytes): %s", what, bytes, cudaGetErrorString(e));
+    return 0;
+  }
+  static int check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(TPX_E_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    return 0;
+  }
+  static unsigned grid(const WArgs& a, int sm_count) {
+    const int64_t ntiles = (a.n + P - 1) / P;
+    return (unsigned)(sm_count < ntiles ? sm_count : ntiles);
+  }
+
+  static int forward(WArgs a, float* saved, float* u, float* du, float* lapo, int sm_count, cudaStream_t stream) {
+    const int L = a.lay.L;
+    const size_t per = (size_t)((a.n + P - 1) / P) * N * HW;     // floats of one activation array
+    int rc = set_smem(w_layer_kernel<ND, LAP, FWD>, layer_smem(), "w_layer_kernel<FWD>");
+    if (rc) return rc;
+    for (int l = 1; l < L; ++l) {
+      a.l = l;
+      a.in = (l == 1) ? nullptr : saved + (size_t)(l - 2) * per;
+      a.out = saved + (size_t)(l - 1) * per;
+      w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
+      if ((rc = check("w_layer_kernel<FWD>"))) return rc;
+    }
+    if (u) {
+      a.in = saved + (size_t)(L - 2) * per;
+      int64_t blocks = (a.n + OUT_THREADS / 32 - 1) / (OUT_THREADS / 32);
+      if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+      w_out_fwd_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, u, du, lapo);
+      if ((rc = check("w_out_fwd_kernel"))) return rc;
+    }
+    return 0;
+  }
+
+  static int backward(WArgs a, float* saved, const float* gu, const float* gdu, const float* glap, int sm_count, cudaStream_t stream) {
+    const int L = a.lay.L;
+    const size_t per = (size_t)((a.n + P - 1) / P) * N * HW;
+    float* zb[2] = {saved + (size_t)(L - 1) * per, saved + (size_t)L * per};
+    int rc = set_smem(w_layer_kernel<ND, LAP, ADJ>, layer_smem(), "w_layer_kernel<ADJ>");
+    if (rc) return rc;
+    if ((rc = set_smem(w_dw_kernel<ND, LAP>, dw_smem(), "w_dw_kernel"))) return rc;
+    a.in = saved + (size_t)(L - 2) * per;
+    a.out = zb[0];
+    {
+      const int64_t npad = (a.n + P - 1) / P * P;
+      int64_t blocks = (npad + OUT_THREADS / 32 - 1) / (OUT_THREADS / 32);
+      if (blocks > (int64_t)sm_count * 4) blocks = (int64_t)sm_count * 4;
+      w_out_bwd_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+      if ((rc = check("w_out_bwd_kernel"))) return rc;
+    }
+    int cur = 0;
+    for (int l = L - 1; l >= 1; --l) {
+      a.l = l;
+      a.in = zb[cur];
+      a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * per;
+      a.out = zb[cur ^ 1];
+      w_dw_kernel<ND, LAP><<<grid(a, sm_count), THREADS, dw_smem(), stream>>>(a);
+      if ((rc = check("w_dw_kernel"))) return rc;
+      w_layer_kernel<ND, LAP, ADJ><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
+      if ((rc = check("w_layer_kernel<ADJ>"))) return rc;
+      cur ^= 1;
+    }
+    return 0;
+  }
+};
+
+}  // namespace tcw
+
+using namespace tcw;
+
+bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
+  static const int disabled = tcw::env_flag("TPX_DISABLE_TCW");
+  if (disabled) return false;
+  if (net->activation != TPX_ACT_TANH) return false;
+  if (net->n_hidden < 2) return false;
+  int wmax = 0;
+  for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
+  if (wmax <= 64 || wmax > HW) return false;
+  if (net->d_in > MAXD || net->d_out > MAXO) return false;
+  if (lap && nd == 0) return false;
+  if (nd < 0 || nd > 3) return false;
+  return true;
+}
+
+// checkpoints of hidden layers 1..L-1 plus the two Zbar buffers of the reverse sweep
+size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n) {
+  const size_t per = (size_t)((n + P - 1) / P) * (size_t)((1 + nd + lap) * P) * HW * sizeof(float);
+  return (size_t)(net->n_hidden + 1) * per;
+}
+
+#define TCW_DISPATCH(CALL)                                     \
+  switch (jet.nd * 2 + lap) {                                  \
+    case 0: return Launch<0, 0>::CALL;                         \
+    case 2: return Launch<1, 0>::CALL;                         \
+    case 3: return Launch<1, 1>::CALL;                         \
+    case 4: return Launch<2, 0>::CALL;                         \
+    case 5: return Launch<2, 1>::CALL;                         \
+    case 6: return Launch<3, 0>::CALL;                         \
+    case 7: return Launch<3, 1>::CALL;                         \
+    default: return fail(TPX_E_UNSUPPORTED, "wide tensor-core path: nd=%d lap=%d", jet.nd, lap); \
+  }
+
+int tcw_forward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
+                float* u, float* du, float* lapo, float* saved, int sm_count, cudaStream_t stream) {
+  WArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lay = lay; a.jet = jet; a.packed = packed; a.x = x; a.n = n;
+  TCW_DISPATCH(forward(a, saved, u, du, lapo, sm_count, stream))
+}
+
+int tcw_backward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
+                 const float* gu, const float* gdu, const float* glap, double* gacc, float* saved, int sm_count,
+                 cudaStream_t stream) {
+  WArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lay = lay; a.jet = jet; a.packed = packed; a.x = x; a.n = n; a.gacc = gacc;
+  TCW_DISPATCH(backward(a, saved, gu, gdu, glap, sm_count, stream))
+}
+
+}  // namespace tpx
