@@ -1,5 +1,6 @@
 """Development aid: step time (condition.forward + backward through the public API, sampler included) of the
-parity configurations 2, 3 and 5 of BASELINE.json, which run on the FP32 CUDA-core kernels (hidden width > 64)."""
+parity configurations 2, 3 and 5 of BASELINE.json (width 128: wide tensor-core kernels; width 256: FP32 CUDA-core kernels).
+usage: config_bench.py [N [config]]"""
 import os
 import sys
 import time
@@ -39,8 +40,11 @@ def cfg5():
         model, s, lambda u, x: 0.5 * (tp.utils.grad(u, x) ** 2).sum(dim=1, keepdim=True) - u)
 
 
+ONLY = sys.argv[2] if len(sys.argv) > 2 else None      # "2", "3" or "5": one configuration only
 for name, make in (("config 2 (heat, 6x128, S=5)", cfg2), ("config 3 (Navier-Stokes, 6x128, 3 outputs, S=4)", cfg3),
                    ("config 5 (Deep Ritz on Circle - square, 8x256, S=3)", cfg5)):
+    if ONLY is not None and not name.startswith("config " + ONLY):
+        continue
     model, cond = make()
 
     def step():

@@ -125,6 +125,16 @@ CASES = [
     (3, 2, (64, 64), "tanh", (), None, 95),
     (3, 1, (40,) * 5, "tanh", (0, 1, 2), None, 257),
     (4, 1, (64,) * 4, "tanh", (2, 0), (0.5, 1.5), 4099),
+    # wide tensor-core path (hidden width 65..128, tanh, d_in <= 4, d_out <= 8; csrc/tcw_kernels.cu): ragged widths,
+    # every stream count 1..5, one hidden matrix, 8 outputs, tile counts below / above the SM count, a single point
+    (2, 1, (128,) * 2, "tanh", (0, 1), (1.0, 1.0), 16),
+    (2, 3, (100, 128, 96), "tanh", (0, 1), (1.0, 1.0), 200),
+    (4, 8, (128,) * 3, "tanh", (), None, 777),
+    (1, 2, (96,) * 4, "tanh", (0,), None, 5000),
+    (3, 2, (65, 80), "tanh", (2, 0), None, 1),
+    (4, 1, (128, 72, 128, 90), "tanh", (3, 0, 1), None, 2371),
+    (2, 4, (112,) * 3, "tanh", (1,), (0.75,), 2500),
+    (5, 1, (128,) * 3, "tanh", (0, 4), (1.0, 1.0), 150),       # d_in > 4: FP32 kernels
 ]
 
 
@@ -243,3 +253,70 @@ def test_saved_checkpoints_equal_recompute(hidden, dcols, lap_w, d_out):
     n32 = min(g_fp32.numel(), g_saved.numel())
     # both packed buffers start with the FP32-kernel image (same indexing)
     assert float((g_saved[:n32] - g_fp32[:n32]).abs().max() / den) < 5e-6
+
+
+@pytest.mark.parametrize("hidden,dcols,lap_w,d_out,d_in", [((128,) * 4, (0, 1, 2), (1.0, 1.0, 0.0), 1, 3),
+                                                            ((96, 128, 80), (0, 1), (1.0, 1.0), 3, 2)])
+def test_wide_path_equals_fp32_kernels(hidden, dcols, lap_w, d_out, d_in):
+    """wide tensor-core path (checkpoint-saving forward + layer-major reverse, used when the engine hands the
+    kernels a saved buffer) against the FP32 CUDA-core kernels (plain forward / workspace reverse) on the same
+    inputs; the saved buffer holds the checkpoints of hidden layers 1..L-1 and the two Zbar buffers of the reverse."""
+    from torchphysics_b200.engine import FcnEngine, JetSpec
+    torch.manual_seed(7)
+    seq = ref_autograd.build_fcn(d_in, d_out, hidden).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    spec = JetSpec(dcols, lap_w)
+    N = 40001                                  # not a multiple of the 16-point tile, more tiles than SMs
+    S = 1 + len(dcols) + (lap_w is not None)
+    x = torch.rand(N, d_in, device="cuda")
+    packed = eng.packed(eng.params())
+    gu = torch.randn(N, d_out, device="cuda")
+    gdu = torch.randn(N, d_out, len(dcols), device="cuda")
+    glap = torch.randn(N, d_out, device="cuda") if lap_w else None
+    nbytes = eng.saved_bytes(spec, N)
+    assert nbytes == ((N + 15) // 16) * (len(hidden) + 1) * S * 16 * 128 * 4
+    saved = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    u1, du1, lap1 = eng.forward_raw(packed, x, spec, saved)
+    u0, du0, lap0 = eng.forward_raw(packed, x, spec)          # FP32 kernels
+    assert float((u1 - u0).abs().max() / u0.abs().max()) < 6e-6      # two fp32 evaluations, each ~2e-6 from the truth
+    assert float((du1 - du0).abs().max() / du0.abs().max()) < 6e-6
+    if lap_w:
+        assert float((lap1 - lap0).abs().max() / lap0.abs().max()) < 6e-6
+    g_wide = eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
+    g_fp32 = eng.backward_raw(packed, x, spec, gu, gdu, glap)
+    den = g_fp32.abs().max()
+    assert float((g_wide - g_fp32).abs().max() / den) < 6e-6
+    # a second reverse sweep over the same saved buffer (the checkpoints are not consumed) gives the same result up to
+    # the order of the atomics (fp32 in shared memory for the output layer, float64 across CTAs)
+    g_again = eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
+    assert float((g_again - g_wide).abs().max() / den) < 1e-6
+
+
+def test_wide_path_reverse_is_linear_at_scale():
+    """size-independent property at a BASELINE-sized batch (config 2 network, 2^18 points): dtheta is additive
+    over a split of the points and linear in the adjoints."""
+    from torchphysics_b200.engine import FcnEngine, JetSpec
+    torch.manual_seed(0)
+    seq = ref_autograd.build_fcn(3, 1, (128,) * 6).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    spec = JetSpec((0, 1, 2), (1.0, 1.0, 0.0))
+    N = 1 << 18
+    x = torch.rand(N, 3, device="cuda")
+    gdu = torch.randn(N, 1, 3, device="cuda")
+    glap = torch.randn(N, 1, device="cuda")
+    packed = eng.packed(eng.params())
+
+    def sweep(lo, hi, scale=1.0):
+        xs = x[lo:hi].contiguous()
+        saved = torch.empty(eng.saved_bytes(spec, hi - lo), dtype=torch.uint8, device="cuda")
+        eng.forward_raw(packed, xs, spec, saved)
+        return eng.backward_raw(packed, xs, spec, None, (scale * gdu[lo:hi]).contiguous(), (scale * glap[lo:hi]).contiguous(), saved)
+
+    full = sweep(0, N)
+    a, b = sweep(0, N // 3), sweep(N // 3, N)
+    twice = sweep(0, N, 2.0)
+    den = full.abs().max()
+    # dW accumulates in fp32 TMEM accumulators per CTA (round toward zero, ~1.8e3 points per CTA here) before the float64
+    # reduction over CTAs; random-sign adjoints are the worst case (see test_linearity_of_reverse_at_scale)
+    assert float((a + b - full).abs().max() / den) < 2e-4
+    assert float((twice - 2 * full).abs().max() / den) < 1e-6

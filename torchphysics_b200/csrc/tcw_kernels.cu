@@ -49,11 +49,13 @@ constexpr int MAXD = 4;            // d_in supported by the layer-0 code
 constexpr int MAXO = 8;            // d_out supported by the output-layer kernels
 constexpr int FWD = 0, ADJ = 1;
 
-// the wide kernels are HBM-bound: they can afford the library tanh (<= 2 ulp) instead of tc::tanh_fast
-#ifdef TPX_TCW_FAST_TANH
-__device__ __forceinline__ float tanh_w(float x) { return tanh_fast(x); }
-#else
+// tc::tanh_fast (ex2 + rcp + one Newton step, absolute error <= 3e-7).  The library tanhf gives the same parity
+// margins (measured: the error of these kernels comes from the accumulator's round-toward-zero adds, not from tanh)
+// and makes the l = 1 launches, which recompute layer 0 from x, compute-bound; -DTPX_TCW_LIBM_TANH selects it.
+#ifdef TPX_TCW_LIBM_TANH
 __device__ __forceinline__ float tanh_w(float x) { return tanhf(x); }
+#else
+__device__ __forceinline__ float tanh_w(float x) { return tanh_fast(x); }
 #endif
 
 struct WArgs {
@@ -139,6 +141,11 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
   constexpr int S = 1 + ND + LAP, N = S * P;
   constexpr int NDX = ND > 0 ? ND : 1;
   constexpr int STAGE = 2 * N * HW;          // floats: hi | lo
+  // the heavy role gets 8 warps: forward = producers (jets + split), adjoint = epilogue (checkpoint reads, adjoint
+  // jets, Zbar stores; two warps per TMEM quadrant, 8 points each, so that one batch of checkpoint loads per tile
+  // is in flight while the warp waits for the tile's product)
+  constexpr int NEPI = (MODE == FWD) ? 4 : 8;
+  constexpr int NPROD = MMA_WARP - NEPI;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[2], bar_empty[2], bar_dfull[2], bar_dempty[2];
   __shared__ uint32_t tmem_slot;
@@ -151,10 +158,10 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
   if (warp == MMA_WARP) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_full[s], PROD_WARPS);
+      mbar_init(&bar_full[s], NPROD);
       mbar_init(&bar_empty[s], 1);
       mbar_init(&bar_dfull[s], 1);
-      mbar_init(&bar_dempty[s], EPI_WARPS);
+      mbar_init(&bar_dempty[s], NEPI);
     }
     mbar_init_fence();
   }
@@ -229,9 +236,9 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
       }
       __syncwarp();
     }
-  } else if (warp >= EPI_WARPS) {
+  } else if (warp >= NEPI) {
     // =========================== producers: B operand of the tile ===========================
-    const int w = warp - EPI_WARPS, kb = w & 3, half = w >> 2;
+    const int w = warp - NEPI, kb = w & 3, half = w >> 2;
     const int i = kb * 32 + lane;
     Layer0 l0;
     float dz0[NDX];
@@ -287,17 +294,16 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
           }
         }
       } else {
-        // rows n in [half * N / 2, (half + 1) * N / 2): plain copy + split of Zbar_l
-        constexpr int RH = N / 2;
-        float v[RH];
-        const float* src = a.in + ((size_t)tile * N + half * RH) * HW + i;
+        // all N rows of this warp's 32 neurons: plain copy + split of Zbar_l (half == 0: 4 producer warps)
+        float v[N];
+        const float* src = a.in + (size_t)tile * N * HW + i;
 #pragma unroll
-        for (int r = 0; r < RH; ++r) v[r] = __ldcs(src + (size_t)r * HW);
+        for (int r = 0; r < N; ++r) v[r] = __ldcs(src + (size_t)r * HW);
         if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
 #pragma unroll
-        for (int r = 0; r < RH; ++r) {
+        for (int r = 0; r < N; ++r) {
           const float h = tf32_hi(v[r]);
-          const int o = swz128(half * RH + r, i, N);
+          const int o = swz128(r, i, N);
           bh[o] = h;
           bl[o] = tf32_hi(v[r] - h);
         }
@@ -308,8 +314,9 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
     }
   } else {
     // =========================== epilogue: row j of D = all streams / points of neuron j ===========================
-    const int j = warp * 32 + lane;
-    const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16) + 256;
+    const int q = warp & 3, h = warp >> 2;     // TMEM quadrant; (adjoint) which 8 points of the tile
+    const int j = q * 32 + lane;
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + 256;
     if (MODE == FWD) {
       const float bias = __ldg(a.packed + lay.b(l) + j);
       int it = 0;
@@ -353,63 +360,57 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
         float part_db = 0.0f, part_w0[MAXD];
 #pragma unroll
         for (int c = 0; c < MAXD; ++c) part_w0[c] = 0.0f;
-        const float* cks = a.ck + (size_t)tile * N * HW + j;
-        float* dst = a.out + (size_t)tile * N * HW + j;
+        const float* cks = a.ck + ((size_t)tile * N + h * 8) * HW + j;
+        float* dst = a.out + ((size_t)tile * N + h * 8) * HW + j;
+        // this tile's checkpoints: in flight while the warp waits for the product
+        float ck[8][S], xr[8][MAXD];
+        if (l == 1) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float ck[8][S], xr[8][MAXD];
+          for (int pp = 0; pp < 8; ++pp) {
+            const int64_t gp = tile * P + h * 8 + pp;
+            float z = l0.b;
+#pragma unroll
+            for (int c = 0; c < MAXD; ++c) {
+              xr[pp][c] = (gp < a.n && c < l0.d_in) ? __ldg(a.x + gp * l0.d_in + c) : 0.0f;
+              z = fmaf(l0.w[c], xr[pp][c], z);
+            }
+            ck[pp][0] = tanh_w(z);
+#pragma unroll
+            for (int k = 0; k < ND; ++k) ck[pp][1 + k] = dz0[k];
+            if (LAP) ck[pp][S - 1] = 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+            for (int s = 0; s < S; ++s) ck[pp][s] = __ldcs(cks + (size_t)(s * P + pp) * HW);
+        }
+        mbar_wait(&bar_dfull[st], (it >> 1) & 1);
+        fence_after();
+        float ab[S][8];
+#pragma unroll
+        for (int s = 0; s < S; ++s) tmem_ld8(tq + st * 128 + s * P + h * 8, ab[s]);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_dempty[st]);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          float hb[S];
+#pragma unroll
+          for (int s = 0; s < S; ++s) hb[s] = ab[s][pp];
+          adjoint_jets<ND, LAP>(hb, ck[pp], lapw);
+          part_db += hb[0];
           if (l == 1) {
 #pragma unroll
-            for (int pp = 0; pp < 8; ++pp) {
-              const int64_t gp = tile * P + h * 8 + pp;
-              float z = l0.b;
+            for (int c = 0; c < MAXD; ++c) {
+              float g = hb[0] * xr[pp][c];
 #pragma unroll
-              for (int c = 0; c < MAXD; ++c) {
-                xr[pp][c] = (gp < a.n && c < l0.d_in) ? __ldg(a.x + gp * l0.d_in + c) : 0.0f;
-                z = fmaf(l0.w[c], xr[pp][c], z);
-              }
-              ck[pp][0] = tanh_w(z);
-#pragma unroll
-              for (int k = 0; k < ND; ++k) ck[pp][1 + k] = dz0[k];
-              if (LAP) ck[pp][S - 1] = 0.0f;
+              for (int k = 0; k < ND; ++k) g += (dcol[k] == c) ? hb[1 + k] : 0.0f;
+              part_w0[c] += g;
             }
           } else {
 #pragma unroll
-            for (int pp = 0; pp < 8; ++pp)
-#pragma unroll
-              for (int s = 0; s < S; ++s) ck[pp][s] = __ldcs(cks + (size_t)(s * P + h * 8 + pp) * HW);
-          }
-          if (h == 0) {
-            mbar_wait(&bar_dfull[st], (it >> 1) & 1);
-            fence_after();
-          }
-          float ab[S][8];
-#pragma unroll
-          for (int s = 0; s < S; ++s) tmem_ld8(tq + st * 128 + s * P + h * 8, ab[s]);
-          if (h == 1) {
-            fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_dempty[st]);
-          }
-#pragma unroll
-          for (int pp = 0; pp < 8; ++pp) {
-            float hb[S];
-#pragma unroll
-            for (int s = 0; s < S; ++s) hb[s] = ab[s][pp];
-            adjoint_jets<ND, LAP>(hb, ck[pp], lapw);
-            part_db += hb[0];
-            if (l == 1) {
-#pragma unroll
-              for (int c = 0; c < MAXD; ++c) {
-                float g = hb[0] * xr[pp][c];
-#pragma unroll
-                for (int k = 0; k < ND; ++k) g += (dcol[k] == c) ? hb[1 + k] : 0.0f;
-                part_w0[c] += g;
-              }
-            } else {
-#pragma unroll
-              for (int s = 0; s < S; ++s) __stcs(dst + (size_t)(s * P + h * 8 + pp) * HW, hb[s]);
-            }
+            for (int s = 0; s < S; ++s) __stcs(dst + (size_t)(s * P + pp) * HW, hb[s]);
           }
         }
         acc_db += (double)part_db;
@@ -662,17 +663,17 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_fwd_kernel(WArgs a, float* 
 }
 
 // output adjoints -> Zbar_{L-1} (written for every row of every tile, zeros for the padding points), dWL, dbL, db_{L-1}
-template <int ND, int LAP>
-__global__ void __launch_bounds__(OUT_THREADS) w_out_bwd_kernel(WArgs a, const float* __restrict__ gu, const float* __restrict__ gdu,
+template <int ND, int LAP, int DO>
+__global__ void __launch_bounds__(OUT_THREADS, (DO <= 2) ? 3 : 2) w_out_bwd_kernel(WArgs a, const float* __restrict__ gu, const float* __restrict__ gdu,
                                                                 const float* __restrict__ glap) {
   constexpr int S = 1 + ND + LAP, N = S * P;
   constexpr int NDX = ND > 0 ? ND : 1;
-  __shared__ float WL[MAXO * HW];
-  __shared__ float red[(MAXO + 1) * HW + MAXO];
+  __shared__ float WL[DO * HW];
+  __shared__ float red[(DO + 1) * HW + DO];
   const Layout lay = a.lay;
   const int d_out = lay.d_out;
   for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + v);
-  for (int v = threadIdx.x; v < (MAXO + 1) * HW + MAXO; v += OUT_THREADS) red[v] = 0.0f;
+  for (int v = threadIdx.x; v < (DO + 1) * HW + DO; v += OUT_THREADS) red[v] = 0.0f;
   __syncthreads();
   float lapw[NDX];
 #pragma unroll
@@ -680,12 +681,12 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_bwd_kernel(WArgs a, const f
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = (int64_t)gridDim.x * (OUT_THREADS / 32);
   const int64_t npad = (a.n + P - 1) / P * P;
-  float acc_wl[MAXO][4], acc_db[4], acc_bl = 0.0f;
+  float acc_wl[DO][4], acc_db[4], acc_bl = 0.0f;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     acc_db[c] = 0.0f;
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o) acc_wl[o][c] = 0.0f;
+    for (int o = 0; o < DO; ++o) acc_wl[o][c] = 0.0f;
   }
   for (int64_t pt = (int64_t)blockIdx.x * (OUT_THREADS / 32) + (threadIdx.x >> 5); pt < npad; pt += nwarps) {
     const int64_t tile = pt / P;
@@ -698,19 +699,19 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_bwd_kernel(WArgs a, const f
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int s = 0; s < S; ++s) ck[c][s] = __ldcs(src + (size_t)s * P * HW + c * 32);
-    float g[MAXO][S];
+    float g[DO][S];
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o) {
+    for (int o = 0; o < DO; ++o) {
       const bool on = valid && o < d_out;
       g[o][0] = (on && gu) ? __ldg(gu + pt * d_out + o) : 0.0f;
 #pragma unroll
       for (int k = 0; k < ND; ++k) g[o][1 + k] = (on && gdu) ? __ldg(gdu + (pt * d_out + o) * ND + k) : 0.0f;
       if (LAP) g[o][S - 1] = (on && glap) ? __ldg(glap + pt * d_out + o) : 0.0f;
     }
-    if (lane < MAXO) {
+    if (lane < DO) {
       float t = 0.0f;
 #pragma unroll
-      for (int o = 0; o < MAXO; ++o) t = (lane == o) ? g[o][0] : t;
+      for (int o = 0; o < DO; ++o) t = (lane == o) ? g[o][0] : t;
       acc_bl += t;
     }
 #pragma unroll
@@ -720,7 +721,7 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_bwd_kernel(WArgs a, const f
       for (int s = 0; s < S; ++s) { act[s] = ck[c][s]; hb[s] = 0.0f; }
       jets_from_ckpt<ND, LAP>(act, lapw);
 #pragma unroll
-      for (int o = 0; o < MAXO; ++o) {
+      for (int o = 0; o < DO; ++o) {
         if (o < d_out) {
           const float w = WL[o * HW + c * 32 + lane];
           float dw = 0.0f;
@@ -741,16 +742,16 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_bwd_kernel(WArgs a, const f
   // CTA-level reduction in shared memory, then one float64 atomic per element and CTA
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    atomicAdd(&red[MAXO * HW + c * 32 + lane], acc_db[c]);
+    atomicAdd(&red[DO * HW + c * 32 + lane], acc_db[c]);
 #pragma unroll
-    for (int o = 0; o < MAXO; ++o)
+    for (int o = 0; o < DO; ++o)
       if (o < d_out) atomicAdd(&red[o * HW + c * 32 + lane], acc_wl[o][c]);
   }
-  if (lane < MAXO) atomicAdd(&red[(MAXO + 1) * HW + lane], acc_bl);
+  if (lane < DO) atomicAdd(&red[(DO + 1) * HW + lane], acc_bl);
   __syncthreads();
   for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.wl() + v, (double)red[v]);
-  for (int v = threadIdx.x; v < HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.b(lay.L - 1) + v, (double)red[MAXO * HW + v]);
-  if (threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(MAXO + 1) * HW + threadIdx.x]);
+  for (int v = threadIdx.x; v < HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.b(lay.L - 1) + v, (double)red[DO * HW + v]);
+  if (threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(DO + 1) * HW + threadIdx.x]);
 }
 
 static int env_flag(const char* name) {
@@ -814,8 +815,12 @@ struct Launch {
     {
       const int64_t npad = (a.n + P - 1) / P * P;
       int64_t blocks = (npad + OUT_THREADS / 32 - 1) / (OUT_THREADS / 32);
-      if (blocks > (int64_t)sm_count * 4) blocks = (int64_t)sm_count * 4;
-      w_out_bwd_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+      if (blocks > (int64_t)sm_count * 6) blocks = (int64_t)sm_count * 6;
+      const int d_out = a.lay.d_out;
+      if (d_out <= 1) w_out_bwd_kernel<ND, LAP, 1><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+      else if (d_out <= 2) w_out_bwd_kernel<ND, LAP, 2><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+      else if (d_out <= 4) w_out_bwd_kernel<ND, LAP, 4><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+      else w_out_bwd_kernel<ND, LAP, 8><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
       if ((rc = check("w_out_bwd_kernel"))) return rc;
     }
     int cur = 0;
