@@ -108,6 +108,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+
 // round-to-nearest (ties away) tf32 "high" part; x - hi is exact in fp32 and fits tf32 up to 2^-24 |x|.
 // Two integer instructions; equals cvt.rna.tf32.f32 for finite values (which ptxas expands to ~4 instructions).
 __device__ __forceinline__ float tf32_hi(float x) {

@@ -58,6 +58,11 @@ __device__ __forceinline__ float tanh_w(float x) { return tanhf(x); }
 __device__ __forceinline__ float tanh_w(float x) { return tanh_fast(x); }
 #endif
 
+static int env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
 struct WArgs {
   Layout lay;            // FP32 parameter image (HP = 128)
   JetArgs jet;
@@ -248,6 +253,15 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
       for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
     }
     int it = 0;
+    constexpr bool PREFETCH = S <= 4;          // S = 5: no registers for it (128 per thread)
+    float vn[8][S];                            // forward, l > 1: the next tile's rows, in flight during this tile
+    if (PREFETCH && MODE == FWD && l > 1) {
+      const float* src = a.in + ((size_t)blockIdx.x * N + half * 8) * HW + i;
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+        for (int s = 0; s < S; ++s) vn[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
@@ -272,11 +286,25 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
             if (LAP) v[pp][S - 1] = 0.0f;
           }
         } else {
-          const float* src = a.in + ((size_t)tile * N + half * 8) * HW + i;
+          if (PREFETCH) {
 #pragma unroll
-          for (int pp = 0; pp < 8; ++pp)
+            for (int pp = 0; pp < 8; ++pp)
 #pragma unroll
-            for (int s = 0; s < S; ++s) v[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
+              for (int s = 0; s < S; ++s) v[pp][s] = vn[pp][s];
+          } else {
+            const float* src = a.in + ((size_t)tile * N + half * 8) * HW + i;
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+              for (int s = 0; s < S; ++s) v[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
+          }
+          if (PREFETCH && tile + gridDim.x < ntiles) {
+            const float* src = a.in + ((size_t)(tile + gridDim.x) * N + half * 8) * HW + i;
+#pragma unroll
+            for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+              for (int s = 0; s < S; ++s) vn[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
+          }
         }
         if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
 #pragma unroll
@@ -609,6 +637,351 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
 }
 
 // =============================================================================================================
+// fused reverse kernel of one hidden matrix: dW_l += Zbar_l^T a_{l-1}  AND  Zbar_{l-1} = adjoint jets(W_l^T Zbar_l)
+// =============================================================================================================
+// One read of Zbar_l and of ckpt_{l-1} serves both products (3 activation rows of HBM traffic per point instead of
+// 5).  TMEM: W^T hi | lo (256 columns) + dW accumulator (128) leave 128 columns, so a step is a SUB-tile of 8
+// points (rows r = 8 s + pp of the 16-point tile, half h):  D (NP = 8 S rounded up to 16 columns) and Zbar^T hi | lo
+// (2 x 8 S columns), both single-buffered; the shared-memory operands are double-buffered:
+//   Zn  [NP rows][128]   Zbar_l rows, K = j     B operand of the adjoint product (rows >= 8 S stay zero)
+//   At  [128 rows][8 S]  a_{l-1}^T,   K = r     B operand of the gradient product
+// Warps 0-3: Zbar loaders (lane = neuron j: Zn rows to shared memory, Zbar^T to TMEM).  Warps 4-11: two sets of four
+// (lane = neuron i), set = stage = parity of the step: checkpoint loads -> a_{l-1} -> At, then the adjoint jets of the
+// SAME checkpoints once the adjoint product has landed -> Zbar_{l-1} (l = 1: dW0, db0).  Warp 12 issues the MMAs:
+// adjoint(it), gradient(it), adjoint(it+1), ...; Zbar^T of step it+1 is written while adjoint(it+1) runs.
+// Every mbarrier is waited on by roles that can be at most one phase behind (per-stage barriers for the two sets).
+template <int ND, int LAP, bool FIRST>      // FIRST: l = 1 (layer 0 is recomputed from x; dW0, db0 instead of Zbar_0)
+__global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
+  constexpr int S = 1 + ND + LAP, N16 = S * P;
+  constexpr int NS = 8 * S;                    // rows of a sub-tile
+  constexpr int NP = (NS + 15) / 16 * 16;      // ... padded to a legal UMMA N
+  constexpr int NDX = ND > 0 ? ND : 1;
+  constexpr int KA = (NS + 31) / 32;
+  constexpr int ZN = NP * HW;                  // floats of Zn hi (or lo)
+  constexpr int AT = KA * HW * 32;             // floats of At hi (or lo)
+  constexpr int STAGE = 2 * ZN + 2 * AT;
+  constexpr uint32_t T_DW = 256, T_D = 384, T_ZH = 384 + NP, T_ZL = T_ZH + NS;
+  static_assert(T_ZL + NS <= 512, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_fzn[2], bar_fzt, bar_fa[2], bar_dfull[2], bar_dempty, bar_zfree, bar_afree[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const Layout lay = a.lay;
+  const int l = a.l;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t nsub = (a.n + P - 1) / P * 2;
+
+  if (warp == MMA_WARP) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_fzn[s], 4);
+      mbar_init(&bar_fa[s], 4);
+      mbar_init(&bar_dfull[s], 1);
+      mbar_init(&bar_afree[s], 1);
+    }
+    mbar_init(&bar_fzt, 4);
+    mbar_init(&bar_dempty, 4);
+    mbar_init(&bar_zfree, 1);
+    mbar_init(&bar_done, 1);
+    mbar_init_fence();
+  }
+  // padding rows of Zn (both stages, hi and lo) are zero for the whole launch
+  if (NP > NS) {
+    for (int v = tid; v < 4 * (NP - NS) * HW; v += THREADS) {
+      const int part = v / ((NP - NS) * HW), e = v % ((NP - NS) * HW);
+      sm[(part >> 1) * STAGE + (part & 1) * ZN + swz128(NS + e / HW, e % HW, NP)] = 0.0f;
+    }
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (warp < 4) {                              // W^T into TMEM: lane = input neuron i, K = output neuron j
+    const float* Wrow = a.packed + lay.wt(l) + (size_t)(warp * 32 + lane) * HW;
+    const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < HW / 16; ++c) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(Wrow + c * 16) + v);
+        hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float h = tf32_hi(hi[e]);
+        lo[e] = tf32_hi(hi[e] - h);
+        hi[e] = h;
+      }
+      tmem_st16(tw + c * 16, hi);
+      tmem_st16(tw + HW + c * 16, lo);
+    }
+    tmem_wait_st();
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+
+  float lapw[NDX];
+  int dcol[NDX];
+#pragma unroll
+  for (int k = 0; k < NDX; ++k) {
+    lapw[k] = (k < ND) ? a.jet.lap_w[k] : 0.0f;
+    dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
+  }
+
+  if (warp == MMA_WARP) {
+    // =========================== MMA issuer ===========================
+    constexpr uint32_t idesc_adj = idesc_tf32(128, NP), idesc_dw = idesc_tf32(128, HW);
+    const uint32_t sbase = smem_u32(sm);
+    int it = 0;
+    for (int64_t sub = blockIdx.x; sub < nsub; sub += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph2 = (it >> 1) & 1;
+      const uint32_t zn_h = sbase + (uint32_t)st * (STAGE * 4), zn_l = zn_h + ZN * 4;
+      const uint32_t at_h = zn_h + 2 * ZN * 4, at_l = at_h + AT * 4;
+      mbar_wait(&bar_fzn[st], ph2);
+      if (it >= 1) mbar_wait(&bar_dempty, (it - 1) & 1);
+      fence_after();
+      if (elect_one()) {
+        // correction products first (the accumulator rounds toward zero on every add)
+#pragma unroll
+        for (int ks = 0; ks < HW / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (NP * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tmem + T_D, tmem + HW + ks * 8, desc_k_sw128(zn_h + off), idesc_adj, ks > 0);
+          mma_tf32_ts(tmem + T_D, tmem + ks * 8, desc_k_sw128(zn_l + off), idesc_adj, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < HW / 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (NP * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tmem + T_D, tmem + ks * 8, desc_k_sw128(zn_h + off), idesc_adj, 1);
+        }
+        mma_commit(&bar_dfull[st]);
+      }
+      __syncwarp();
+      mbar_wait(&bar_fzt, it & 1);
+      mbar_wait(&bar_fa[st], ph2);
+      fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < S; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (HW * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tmem + T_DW, tmem + T_ZL + ks * 8, desc_k_sw128(at_h + off), idesc_dw, (it > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32_ts(tmem + T_DW, tmem + T_ZH + ks * 8, desc_k_sw128(at_l + off), idesc_dw, 1);
+        }
+#pragma unroll
+        for (int ks = 0; ks < S; ++ks) {
+          const uint32_t off = (uint32_t)(ks >> 2) * (HW * 128) + (ks & 3) * 32;
+          mma_tf32_ts(tmem + T_DW, tmem + T_ZH + ks * 8, desc_k_sw128(at_h + off), idesc_dw, 1);
+        }
+        mma_commit(&bar_zfree);
+        mma_commit(&bar_afree[st]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&bar_done);
+    __syncwarp();
+  } else if (warp < 4) {
+    // =========================== Zbar_l loaders: lane = output neuron j ===========================
+    const int j = warp * 32 + lane;
+    const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16);
+    int it = 0;
+    // this step's rows; the next step's rows, in flight during this step
+    constexpr bool PREFETCH = true;
+    float v[S][8], vn[S][8];
+    if (PREFETCH) {
+      const float* src = a.in + ((size_t)(blockIdx.x >> 1) * N16 + (blockIdx.x & 1) * 8) * HW + j;
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) vn[s][pp] = __ldcs(src + (size_t)(s * P + pp) * HW);
+    }
+    for (int64_t sub = blockIdx.x; sub < nsub; sub += gridDim.x, ++it) {
+      const int st = it & 1;
+      float* zn_h = sm + st * STAGE;
+      float* zn_l = zn_h + ZN;
+      if (PREFETCH) {
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) v[s][pp] = vn[s][pp];
+      } else {
+        const float* src = a.in + ((size_t)(sub >> 1) * N16 + (sub & 1) * 8) * HW + j;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) v[s][pp] = __ldcs(src + (size_t)(s * P + pp) * HW);
+      }
+      if (PREFETCH && sub + gridDim.x < nsub) {
+        const int64_t nx = sub + gridDim.x;
+        const float* src = a.in + ((size_t)(nx >> 1) * N16 + (nx & 1) * 8) * HW + j;
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int pp = 0; pp < 8; ++pp) vn[s][pp] = __ldcs(src + (size_t)(s * P + pp) * HW);
+      }
+      // Zn[st] is free once the adjoint product of step it-2 has completed
+      if (it >= 2) mbar_wait(&bar_dfull[st], ((it >> 1) - 1) & 1);
+#pragma unroll
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const float h = tf32_hi(v[s][pp]);
+          const int o = swz128(s * 8 + pp, j, NP);
+          zn_h[o] = h;
+          zn_l[o] = tf32_hi(v[s][pp] - h);
+        }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_fzn[st]);
+      // Zbar^T in TMEM is free once the gradient product of step it-1 has completed
+      if (it >= 1) mbar_wait(&bar_zfree, (it - 1) & 1);
+      fence_after();
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          hi[pp] = tf32_hi(v[s][pp]);
+          lo[pp] = tf32_hi(v[s][pp] - hi[pp]);
+        }
+        tmem_st8(tq + T_ZH + s * 8, hi);
+        tmem_st8(tq + T_ZL + s * 8, lo);
+      }
+      tmem_wait_st();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_fzt);
+    }
+    mbar_wait(&bar_done, 0);
+    fence_after();
+    double* g = a.gacc + lay.w(l) + (size_t)j * HW;
+#pragma unroll 1
+    for (int c = 0; c < HW / 16; ++c) {
+      float d[16];
+      tmem_ld16(tq + T_DW + c * 16, d);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) atomicAdd(g + c * 16 + e, (double)d[e]);
+    }
+  } else {
+    // =========================== a_{l-1}^T producers + adjoint-jet epilogue: lane = input neuron i ===========================
+    const int q = warp & 3, set = (warp - 4) >> 2;
+    const int i = q * 32 + lane;
+    const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+    Layer0 l0;
+    float dz0[NDX];
+    if (FIRST) {
+      l0.load(lay, a.packed, i);
+#pragma unroll
+      for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
+    }
+    double acc_db = 0.0, acc_w0[MAXD];
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) acc_w0[c] = 0.0;
+    float* at_h = sm + set * STAGE + 2 * ZN;
+    float* at_l = at_h + AT;
+    int it = set;
+    for (int64_t sub = blockIdx.x + (int64_t)set * gridDim.x; sub < nsub; sub += 2 * (int64_t)gridDim.x, it += 2) {
+      const uint32_t ph2 = (it >> 1) & 1;
+      const size_t row0 = ((size_t)(sub >> 1) * N16 + (sub & 1) * 8) * HW + i;
+      float ck[8][S], xr[8][FIRST ? MAXD : 1];
+      if (FIRST) {
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const int64_t gp = (sub >> 1) * P + (sub & 1) * 8 + pp;
+          float z = l0.b;
+#pragma unroll
+          for (int c = 0; c < MAXD; ++c) {
+            xr[pp][c] = (gp < a.n && c < l0.d_in) ? __ldg(a.x + gp * l0.d_in + c) : 0.0f;
+            z = fmaf(l0.w[c], xr[pp][c], z);
+          }
+          ck[pp][0] = tanh_w(z);
+#pragma unroll
+          for (int k = 0; k < ND; ++k) ck[pp][1 + k] = dz0[k];
+          if (LAP) ck[pp][S - 1] = 0.0f;
+        }
+      } else {
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+          for (int s = 0; s < S; ++s) ck[pp][s] = __ldcs(a.ck + row0 + (size_t)(s * P + pp) * HW);
+      }
+      // At[set] is free once the gradient product of step it-2 has completed
+      if (it >= 2) mbar_wait(&bar_afree[set], ph2 ^ 1);
+      {
+        float av[8][S];
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) av[pp][s] = ck[pp][s];
+          jets_from_ckpt<ND, LAP>(av[pp], lapw);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float4 h4, l4;
+            h4.x = tf32_hi(av[c * 4 + 0][s]); h4.y = tf32_hi(av[c * 4 + 1][s]); h4.z = tf32_hi(av[c * 4 + 2][s]); h4.w = tf32_hi(av[c * 4 + 3][s]);
+            l4.x = tf32_hi(av[c * 4 + 0][s] - h4.x); l4.y = tf32_hi(av[c * 4 + 1][s] - h4.y);
+            l4.z = tf32_hi(av[c * 4 + 2][s] - h4.z); l4.w = tf32_hi(av[c * 4 + 3][s] - h4.w);
+            const int o = swz128(i, s * 8 + c * 4, HW);
+            *reinterpret_cast<float4*>(at_h + o) = h4;
+            *reinterpret_cast<float4*>(at_l + o) = l4;
+          }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_fa[set]);
+      // the adjoint product of this step
+      mbar_wait(&bar_dfull[set], ph2);
+      fence_after();
+      float ab[S][8];
+#pragma unroll
+      for (int s = 0; s < S; ++s) tmem_ld8(tq + T_D + s * 8, ab[s]);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_dempty);
+      float part_db = 0.0f, part_w0[MAXD];
+#pragma unroll
+      for (int c = 0; c < MAXD; ++c) part_w0[c] = 0.0f;
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        float hb[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) hb[s] = ab[s][pp];
+        adjoint_jets<ND, LAP>(hb, ck[pp], lapw);
+        part_db += hb[0];
+        if (FIRST) {
+#pragma unroll
+          for (int c = 0; c < MAXD; ++c) {
+            float g = hb[0] * xr[pp][c];
+#pragma unroll
+            for (int k = 0; k < ND; ++k) g += (dcol[k] == c) ? hb[1 + k] : 0.0f;
+            part_w0[c] += g;
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < S; ++s) __stcs(a.out + row0 + (size_t)(s * P + pp) * HW, hb[s]);
+        }
+      }
+      acc_db += (double)part_db;
+#pragma unroll
+      for (int c = 0; c < MAXD; ++c) acc_w0[c] += (double)part_w0[c];
+    }
+    atomicAdd(a.gacc + (FIRST ? lay.b0() : lay.b(l - 1)) + i, acc_db);
+    if (FIRST) {
+#pragma unroll
+      for (int c = 0; c < MAXD; ++c)
+        if (c < lay.d_in) atomicAdd(a.gacc + lay.w0() + (size_t)c * HW + i, acc_w0[c]);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================================
 // output layer (CUDA cores): one warp per point, lane owns neurons lane + 32 c
 // =============================================================================================================
 constexpr int OUT_THREADS = 256;
@@ -754,15 +1127,14 @@ __global__ void __launch_bounds__(OUT_THREADS, (DO <= 2) ? 3 : 2) w_out_bwd_kern
   if (threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(DO + 1) * HW + threadIdx.x]);
 }
 
-static int env_flag(const char* name) {
-  const char* v = getenv(name);
-  return v && v[0] && v[0] != '0';
-}
-
 template <int ND, int LAP>
 struct Launch {
   static constexpr int S = 1 + ND + LAP, N = S * P;
   static size_t layer_smem() { return (size_t)2 * 2 * N * HW * sizeof(float) + 1024; }
+  static size_t rev_smem() {
+    constexpr int NS = 8 * S, NP = (NS + 15) / 16 * 16, KA = (NS + 31) / 32;
+    return (size_t)2 * (2 * NP * HW + 2 * KA * HW * 32) * sizeof(float) + 1024;
+  }
   static size_t dw_smem() { return (size_t)2 * 2 * ((N + 31) / 32) * HW * 32 * sizeof(float) + 1024; }
 
   template <class K>
@@ -823,16 +1195,27 @@ struct Launch {
       else w_out_bwd_kernel<ND, LAP, 8><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
       if ((rc = check("w_out_bwd_kernel"))) return rc;
     }
+    static const int split = env_flag("TPX_TCW_SPLIT");      // development: separate dW / adjoint launches
+    if (!split && (rc = set_smem(w_rev_kernel<ND, LAP, false>, rev_smem(), "w_rev_kernel"))) return rc;
+    if (!split && (rc = set_smem(w_rev_kernel<ND, LAP, true>, rev_smem(), "w_rev_kernel"))) return rc;
     int cur = 0;
     for (int l = L - 1; l >= 1; --l) {
       a.l = l;
       a.in = zb[cur];
       a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * per;
       a.out = zb[cur ^ 1];
-      w_dw_kernel<ND, LAP><<<grid(a, sm_count), THREADS, dw_smem(), stream>>>(a);
-      if ((rc = check("w_dw_kernel"))) return rc;
-      w_layer_kernel<ND, LAP, ADJ><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
-      if ((rc = check("w_layer_kernel<ADJ>"))) return rc;
+      if (split) {
+        w_dw_kernel<ND, LAP><<<grid(a, sm_count), THREADS, dw_smem(), stream>>>(a);
+        if ((rc = check("w_dw_kernel"))) return rc;
+        w_layer_kernel<ND, LAP, ADJ><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
+        if ((rc = check("w_layer_kernel<ADJ>"))) return rc;
+      } else {
+        const int64_t nsub = (a.n + P - 1) / P * 2;
+        const unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
+        if (l == 1) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
+        else w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
+        if ((rc = check("w_rev_kernel"))) return rc;
+      }
       cur ^= 1;
     }
     return 0;
