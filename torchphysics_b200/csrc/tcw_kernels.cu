@@ -63,6 +63,15 @@ static int env_flag(const char* name) {
   return v && v[0] && v[0] != '0';
 }
 
+// low part of the tf32 split of an activation: x - hi is exact; the MMA truncates it to tf32 (2^-23 |x|, toward zero).
+// Rounding it here instead costs two more integer instructions per element in kernels that are bound by instruction
+// issue (13 warps per SM) and changed the measured parity margins by < 10 % (-DTPX_TCW_ROUND_LO selects it).
+#ifdef TPX_TCW_ROUND_LO
+__device__ __forceinline__ float lo_part(float x, float hi) { return tf32_hi(x - hi); }
+#else
+__device__ __forceinline__ float lo_part(float x, float hi) { return x - hi; }
+#endif
+
 struct WArgs {
   Layout lay;            // FP32 parameter image (HP = 128)
   JetArgs jet;
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
             const float h = tf32_hi(val);
             const int o = swz128(s * P + p, i, N);
             bh[o] = h;
-            bl[o] = tf32_hi(val - h);
+            bl[o] = lo_part(val, h);
           }
         }
       } else {
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
           const float h = tf32_hi(v[r]);
           const int o = swz128(r, i, N);
           bh[o] = h;
-          bl[o] = tf32_hi(v[r] - h);
+          bl[o] = lo_part(v[r], h);
         }
       }
       fence_async_smem();
@@ -580,7 +589,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) vv[e] = v[c * 4 + e][s];
           h4.x = tf32_hi(vv[0]); h4.y = tf32_hi(vv[1]); h4.z = tf32_hi(vv[2]); h4.w = tf32_hi(vv[3]);
-          l4.x = tf32_hi(vv[0] - h4.x); l4.y = tf32_hi(vv[1] - h4.y); l4.z = tf32_hi(vv[2] - h4.z); l4.w = tf32_hi(vv[3] - h4.w);
+          l4.x = lo_part(vv[0], h4.x); l4.y = lo_part(vv[1], h4.y); l4.z = lo_part(vv[2], h4.z); l4.w = lo_part(vv[3], h4.w);
           const int o = swz128(i, n0 + c * 4, HW);
           *reinterpret_cast<float4*>(ah + o) = h4;
           *reinterpret_cast<float4*>(al + o) = l4;
@@ -609,7 +618,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           const float h = tf32_hi(hi[p]);
-          lo[p] = tf32_hi(hi[p] - h);
+          lo[p] = lo_part(hi[p], h);
           hi[p] = h;
         }
         tmem_st16(zh + s * P, hi);
@@ -830,7 +839,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
           const float h = tf32_hi(v[s][pp]);
           const int o = swz128(s * 8 + pp, j, NP);
           zn_h[o] = h;
-          zn_l[o] = tf32_hi(v[s][pp] - h);
+          zn_l[o] = lo_part(v[s][pp], h);
         }
       fence_async_smem();
       __syncwarp();
@@ -844,7 +853,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) {
           hi[pp] = tf32_hi(v[s][pp]);
-          lo[pp] = tf32_hi(v[s][pp] - hi[pp]);
+          lo[pp] = lo_part(v[s][pp], hi[pp]);
         }
         tmem_st8(tq + T_ZH + s * 8, hi);
         tmem_st8(tq + T_ZL + s * 8, lo);
@@ -923,8 +932,8 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
           for (int c = 0; c < 2; ++c) {
             float4 h4, l4;
             h4.x = tf32_hi(av[c * 4 + 0][s]); h4.y = tf32_hi(av[c * 4 + 1][s]); h4.z = tf32_hi(av[c * 4 + 2][s]); h4.w = tf32_hi(av[c * 4 + 3][s]);
-            l4.x = tf32_hi(av[c * 4 + 0][s] - h4.x); l4.y = tf32_hi(av[c * 4 + 1][s] - h4.y);
-            l4.z = tf32_hi(av[c * 4 + 2][s] - h4.z); l4.w = tf32_hi(av[c * 4 + 3][s] - h4.w);
+            l4.x = lo_part(av[c * 4 + 0][s], h4.x); l4.y = lo_part(av[c * 4 + 1][s], h4.y);
+            l4.z = lo_part(av[c * 4 + 2][s], h4.z); l4.w = lo_part(av[c * 4 + 3][s], h4.w);
             const int o = swz128(i, s * 8 + c * 4, HW);
             *reinterpret_cast<float4*>(at_h + o) = h4;
             *reinterpret_cast<float4*>(at_l + o) = l4;
