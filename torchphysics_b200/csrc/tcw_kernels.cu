@@ -83,6 +83,7 @@ struct WArgs {
   const float* ck;       // ADJ / DW: ckpt_{l-1} (unused for l = 1)
   float* out;            // FWD: ckpt_l; ADJ: Zbar_{l-1} (unused for l = 1)
   double* gacc;
+  long long* dbg;        // development (-DTPX_TIMELINE): clock64 stamps of steps 40..43 of CTA 0 of the reverse kernel
 };
 
 // layer-0 pre-activation of neuron i at one point: z = b0 + W0 x
@@ -668,37 +669,46 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
   constexpr int KA = (NS + 31) / 32;
   constexpr int ZN = NP * HW;                  // floats of Zn hi (or lo)
   constexpr int AT = KA * HW * 32;             // floats of At hi (or lo)
-  constexpr int STAGE = 2 * ZN + 2 * AT;
+  // Zn is double-buffered where shared memory allows (S <= 4); with one buffer (S = 5) it is rewritten while the
+  // gradient product of the step runs, which leaves its ~1000-cycle write on the critical path
+  constexpr int ZSTAGES = (S <= 4) ? 2 : 1;
+  constexpr int AT_OFF = ZSTAGES * 2 * ZN, AT_STAGE = 2 * AT, RAW_OFF = AT_OFF + 2 * AT_STAGE, RAW_SLOT = NS * HW;
   constexpr uint32_t T_DW = 256, T_D = 384, T_ZH = 384 + NP, T_ZL = T_ZH + NS;
   static_assert(T_ZL + NS <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_fzn[2], bar_fzt, bar_fa[2], bar_dfull[2], bar_dempty, bar_zfree, bar_afree[2], bar_done;
+  __shared__ uint64_t bar_fzn, bar_fzt, bar_fa[2], bar_dfull[2], bar_dempty, bar_zfree, bar_afree[2], bar_done;
   __shared__ uint32_t tmem_slot;
   float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const Layout lay = a.lay;
   const int l = a.l;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t nsub = (a.n + P - 1) / P * 2;
+#ifdef TPX_TIMELINE
+  long long* dbg = (a.dbg && !FIRST && blockIdx.x == 0 && lane == 0 && (warp == MMA_WARP || warp == 0 || warp == 4 || warp == 8)) ? a.dbg : nullptr;
+#define TPX_WSTAMP(role, e) do { if (dbg && it >= 40 && it < 44) dbg[(role) * 64 + (it - 40) * 8 + (e)] = clock64(); } while (0)
+#else
+#define TPX_WSTAMP(role, e) do { } while (0)
+#endif
 
   if (warp == MMA_WARP) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_fzn[s], 4);
       mbar_init(&bar_fa[s], 4);
       mbar_init(&bar_dfull[s], 1);
       mbar_init(&bar_afree[s], 1);
     }
+    mbar_init(&bar_fzn, 4);
     mbar_init(&bar_fzt, 4);
     mbar_init(&bar_dempty, 4);
     mbar_init(&bar_zfree, 1);
     mbar_init(&bar_done, 1);
     mbar_init_fence();
   }
-  // padding rows of Zn (both stages, hi and lo) are zero for the whole launch
+  // padding rows of Zn (hi and lo) are zero for the whole launch
   if (NP > NS) {
-    for (int v = tid; v < 4 * (NP - NS) * HW; v += THREADS) {
+    for (int v = tid; v < ZSTAGES * 2 * (NP - NS) * HW; v += THREADS) {
       const int part = v / ((NP - NS) * HW), e = v % ((NP - NS) * HW);
-      sm[(part >> 1) * STAGE + (part & 1) * ZN + swz128(NS + e / HW, e % HW, NP)] = 0.0f;
+      sm[part * ZN + swz128(NS + e / HW, e % HW, NP)] = 0.0f;
     }
   }
   fence_async_smem();
@@ -748,13 +758,17 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     for (int64_t sub = blockIdx.x; sub < nsub; sub += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph2 = (it >> 1) & 1;
-      const uint32_t zn_h = sbase + (uint32_t)st * (STAGE * 4), zn_l = zn_h + ZN * 4;
-      const uint32_t at_h = zn_h + 2 * ZN * 4, at_l = at_h + AT * 4;
-      mbar_wait(&bar_fzn[st], ph2);
+      const uint32_t zn_h = sbase + (uint32_t)(it & (ZSTAGES - 1)) * (2 * ZN * 4), zn_l = zn_h + ZN * 4;
+      const uint32_t at_h = sbase + (uint32_t)(AT_OFF + st * AT_STAGE) * 4, at_l = at_h + AT * 4;
+      TPX_WSTAMP(0, 0);
+      mbar_wait(&bar_fzn, it & 1);
+      TPX_WSTAMP(0, 1);
       if (it >= 1) mbar_wait(&bar_dempty, (it - 1) & 1);
       fence_after();
+      TPX_WSTAMP(0, 2);
       if (elect_one()) {
-        // correction products first (the accumulator rounds toward zero on every add)
+        // correction products first (the accumulator rounds toward zero on every add).  N = 48 costs as much as
+        // N = 64 (measured); issuing it as N = 32 + N = 16 is slower still (small-N MMAs have a minimum cost)
 #pragma unroll
         for (int ks = 0; ks < HW / 8; ++ks) {
           const uint32_t off = (uint32_t)(ks >> 2) * (NP * 128) + (ks & 3) * 32;
@@ -769,9 +783,12 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
         mma_commit(&bar_dfull[st]);
       }
       __syncwarp();
+      TPX_WSTAMP(0, 3);
       mbar_wait(&bar_fzt, it & 1);
+      TPX_WSTAMP(0, 4);
       mbar_wait(&bar_fa[st], ph2);
       fence_after();
+      TPX_WSTAMP(0, 5);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < S; ++ks) {
@@ -788,6 +805,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
         mma_commit(&bar_afree[st]);
       }
       __syncwarp();
+      TPX_WSTAMP(0, 6);
     }
     if (elect_one()) mma_commit(&bar_done);
     __syncwarp();
@@ -796,42 +814,41 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     const int j = warp * 32 + lane;
     const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16);
     int it = 0;
-    // this step's rows; the next step's rows, in flight during this step
-    constexpr bool PREFETCH = true;
-    float v[S][8], vn[S][8];
-    if (PREFETCH) {
-      const float* src = a.in + ((size_t)(blockIdx.x >> 1) * N16 + (blockIdx.x & 1) * 8) * HW + j;
-#pragma unroll
-      for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int pp = 0; pp < 8; ++pp) vn[s][pp] = __ldcs(src + (size_t)(s * P + pp) * HW);
-    }
-    for (int64_t sub = blockIdx.x; sub < nsub; sub += gridDim.x, ++it) {
-      const int st = it & 1;
-      float* zn_h = sm + st * STAGE;
-      float* zn_l = zn_h + ZN;
-      if (PREFETCH) {
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-#pragma unroll
-          for (int pp = 0; pp < 8; ++pp) v[s][pp] = vn[s][pp];
-      } else {
+    // The rows of the next two steps are in flight (cp.async of a thread's OWN 8 S elements into a two-slot ring of raw
+    // rows: nothing but the issuing thread reads them, so no barrier is involved): measured HBM latency under load is
+    // ~3600 cycles, longer than a step, and a register prefetch of one step left the loader as the critical chain.
+    auto issue = [&](int64_t sub, int slot) {
+      if (sub < nsub) {
         const float* src = a.in + ((size_t)(sub >> 1) * N16 + (sub & 1) * 8) * HW + j;
+        const uint32_t dst = smem_u32(sm + RAW_OFF + slot * RAW_SLOT + j);
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll
-          for (int pp = 0; pp < 8; ++pp) v[s][pp] = __ldcs(src + (size_t)(s * P + pp) * HW);
+          for (int pp = 0; pp < 8; ++pp)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)((s * 8 + pp) * HW * 4)),
+                         "l"(src + (size_t)(s * P + pp) * HW) : "memory");
       }
-      if (PREFETCH && sub + gridDim.x < nsub) {
-        const int64_t nx = sub + gridDim.x;
-        const float* src = a.in + ((size_t)(nx >> 1) * N16 + (nx & 1) * 8) * HW + j;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(blockIdx.x, 0);
+    issue((int64_t)blockIdx.x + gridDim.x, 1);
+    for (int64_t sub = blockIdx.x; sub < nsub; sub += gridDim.x, ++it) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      float v[S][8];
+      {
+        const float* raw = sm + RAW_OFF + (it & 1) * RAW_SLOT + j;
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll
-          for (int pp = 0; pp < 8; ++pp) vn[s][pp] = __ldcs(src + (size_t)(s * P + pp) * HW);
+          for (int pp = 0; pp < 8; ++pp) v[s][pp] = raw[(s * 8 + pp) * HW];
       }
-      // Zn[st] is free once the adjoint product of step it-2 has completed
-      if (it >= 2) mbar_wait(&bar_dfull[st], ((it >> 1) - 1) & 1);
+      issue(sub + 2 * (int64_t)gridDim.x, it & 1);
+      TPX_WSTAMP(1, 0);
+      // this step's Zn buffer is free once the adjoint product of step it - ZSTAGES has completed
+      float* zn_h = sm + (it & (ZSTAGES - 1)) * (2 * ZN);
+      float* zn_l = zn_h + ZN;
+      if (it >= ZSTAGES) mbar_wait(&bar_dfull[(it - ZSTAGES) & 1], ((it - ZSTAGES) >> 1) & 1);
+      TPX_WSTAMP(1, 1);
 #pragma unroll
       for (int s = 0; s < S; ++s)
 #pragma unroll
@@ -843,10 +860,12 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
         }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_fzn[st]);
+      if (lane == 0) mbar_arrive(&bar_fzn);
+      TPX_WSTAMP(1, 2);
       // Zbar^T in TMEM is free once the gradient product of step it-1 has completed
       if (it >= 1) mbar_wait(&bar_zfree, (it - 1) & 1);
       fence_after();
+      TPX_WSTAMP(1, 3);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         float hi[8], lo[8];
@@ -862,6 +881,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_fzt);
+      TPX_WSTAMP(1, 4);
     }
     mbar_wait(&bar_done, 0);
     fence_after();
@@ -888,7 +908,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     double acc_db = 0.0, acc_w0[MAXD];
 #pragma unroll
     for (int c = 0; c < MAXD; ++c) acc_w0[c] = 0.0;
-    float* at_h = sm + set * STAGE + 2 * ZN;
+    float* at_h = sm + AT_OFF + set * AT_STAGE;
     float* at_l = at_h + AT;
     int it = set;
     for (int64_t sub = blockIdx.x + (int64_t)set * gridDim.x; sub < nsub; sub += 2 * (int64_t)gridDim.x, it += 2) {
@@ -916,8 +936,10 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
 #pragma unroll
           for (int s = 0; s < S; ++s) ck[pp][s] = __ldcs(a.ck + row0 + (size_t)(s * P + pp) * HW);
       }
+      TPX_WSTAMP(2 + set, 0);
       // At[set] is free once the gradient product of step it-2 has completed
       if (it >= 2) mbar_wait(&bar_afree[set], ph2 ^ 1);
+      TPX_WSTAMP(2 + set, 1);
       {
         float av[8][S];
 #pragma unroll
@@ -942,15 +964,18 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_fa[set]);
+      TPX_WSTAMP(2 + set, 2);
       // the adjoint product of this step
       mbar_wait(&bar_dfull[set], ph2);
       fence_after();
+      TPX_WSTAMP(2 + set, 3);
       float ab[S][8];
 #pragma unroll
       for (int s = 0; s < S; ++s) tmem_ld8(tq + T_D + s * 8, ab[s]);
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_dempty);
+      TPX_WSTAMP(2 + set, 4);
       float part_db = 0.0f, part_w0[MAXD];
 #pragma unroll
       for (int c = 0; c < MAXD; ++c) part_w0[c] = 0.0f;
@@ -977,6 +1002,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       acc_db += (double)part_db;
 #pragma unroll
       for (int c = 0; c < MAXD; ++c) acc_w0[c] += (double)part_w0[c];
+      TPX_WSTAMP(2 + set, 5);
     }
     atomicAdd(a.gacc + (FIRST ? lay.b0() : lay.b(l - 1)) + i, acc_db);
     if (FIRST) {
@@ -1142,7 +1168,7 @@ struct Launch {
   static size_t layer_smem() { return (size_t)2 * 2 * N * HW * sizeof(float) + 1024; }
   static size_t rev_smem() {
     constexpr int NS = 8 * S, NP = (NS + 15) / 16 * 16, KA = (NS + 31) / 32;
-    return (size_t)2 * (2 * NP * HW + 2 * KA * HW * 32) * sizeof(float) + 1024;
+    return (size_t)((S <= 4 ? 2 : 1) * 2 * NP * HW + 4 * KA * HW * 32 + 2 * NS * HW) * sizeof(float) + 1024;   // Zn, 2 x At, raw ring
   }
   static size_t dw_smem() { return (size_t)2 * 2 * ((N + 31) / 32) * HW * 32 * sizeof(float) + 1024; }
 
@@ -1281,6 +1307,7 @@ int tcw_backward(const Layout& lay, const JetArgs& jet, int lap, const float* pa
   WArgs a;
   memset(&a, 0, sizeof(a));
   a.lay = lay; a.jet = jet; a.packed = packed; a.x = x; a.n = n; a.gacc = gacc;
+  a.dbg = g_tc_debug;
   TCW_DISPATCH(backward(a, saved, gu, gdu, glap, sm_count, stream))
 }
 
