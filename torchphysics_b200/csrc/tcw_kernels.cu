@@ -20,11 +20,14 @@
 //   w_layer_kernel<FWD>  ckpt_{l-1} (or x for l = 1) -> a_{l-1} -> z_l = W_l a_{l-1} + b_l -> ckpt_l = (tanh z, d_k z, L z)
 //   w_out_fwd_kernel     ckpt_{L-1} -> u, du, lap      (linear output layer, CUDA cores: d_out x 128 per stream)
 //   w_out_bwd_kernel     output adjoints -> dWL, dbL, Zbar_{L-1} (adjoint of the pre-activation streams), db_{L-1}
-//   w_dw_kernel          dW_l[j][i] += sum_n Zbar_l[n][j] a_{l-1}[n][i]   (A = Zbar^T in TMEM, written by its lane-bound
-//                        loader warps; B = a^T in shared memory, 16-byte stores of a thread's own row; K = n)
-//   w_layer_kernel<ADJ>  Abar_{l-1} = W_l^T Zbar_l -> adjoint jets with ckpt_{l-1} -> Zbar_{l-1}, db_{l-1} (l = 1: dW0, db0)
-// HBM traffic per point and hidden matrix: forward 2, adjoint 3, dW 2 activation rows of S * 512 bytes: these
-// kernels are HBM-bound, the tensor pipe is roughly half busy.
+//   w_rev_kernel         one read of Zbar_l and ckpt_{l-1} for BOTH reverse products of matrix l:
+//                        dW_l[j][i] += sum_n Zbar_l[n][j] a_{l-1}[n][i]   (A = Zbar^T in TMEM, written by its lane-bound
+//                        loader warps; B = a^T in shared memory, 16-byte stores of a thread's own row; K = n) and
+//                        Abar_{l-1} = W_l^T Zbar_l -> adjoint jets with ckpt_{l-1} -> Zbar_{l-1}, db_{l-1} (l = 1: dW0, db0)
+//   w_dw_kernel, w_layer_kernel<ADJ>   the same two products as separate launches (TPX_TCW_SPLIT=1, development)
+// HBM traffic per point and hidden matrix: forward 2, reverse 3 activation rows of S * 512 bytes.  The forward launches
+// are HBM-bound (~75 % of the copy peak), the fused reverse launch is bound by the tensor pipe and load latency
+// (DESIGN.md section 3.2b).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,6 +60,21 @@ __device__ __forceinline__ float tanh_w(float x) { return tanhf(x); }
 #else
 __device__ __forceinline__ float tanh_w(float x) { return tanh_fast(x); }
 #endif
+
+// mbarrier wait with a watchdog: a protocol error (or a fault in another role) traps after ~10 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_w(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  if (done) return;
+  const long long t0 = clock64();
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (!done && clock64() - t0 > 20000000000ll) __trap();
+  } while (!done);
+}
 
 static int env_flag(const char* name) {
   const char* v = getenv(name);
@@ -227,8 +245,8 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&bar_full[st], ph);
-      if (it >= 2) mbar_wait(&bar_dempty[st], ph ^ 1);
+      mbar_wait_w(&bar_full[st], ph);
+      if (it >= 2) mbar_wait_w(&bar_dempty[st], ph ^ 1);
       fence_after();
       if (elect_one()) {
         const uint32_t tD = tmem + 256 + st * 128;
@@ -316,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
               for (int s = 0; s < S; ++s) vn[pp][s] = __ldcs(src + (size_t)(s * P + pp) * HW);
           }
         }
-        if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+        if (it >= 2) mbar_wait_w(&bar_empty[st], ph ^ 1);
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) {
           const int p = half * 8 + pp;
@@ -337,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
         const float* src = a.in + (size_t)tile * N * HW + i;
 #pragma unroll
         for (int r = 0; r < N; ++r) v[r] = __ldcs(src + (size_t)r * HW);
-        if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+        if (it >= 2) mbar_wait_w(&bar_empty[st], ph ^ 1);
 #pragma unroll
         for (int r = 0; r < N; ++r) {
           const float h = tf32_hi(v[r]);
@@ -360,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int st = it & 1;
-        mbar_wait(&bar_dfull[st], (it >> 1) & 1);
+        mbar_wait_w(&bar_dfull[st], (it >> 1) & 1);
         fence_after();
         float* dst = a.out + (size_t)tile * N * HW + j;
 #pragma unroll
@@ -423,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
 #pragma unroll
             for (int s = 0; s < S; ++s) ck[pp][s] = __ldcs(cks + (size_t)(s * P + pp) * HW);
         }
-        mbar_wait(&bar_dfull[st], (it >> 1) & 1);
+        mbar_wait_w(&bar_dfull[st], (it >> 1) & 1);
         fence_after();
         float ab[S][8];
 #pragma unroll
@@ -518,8 +536,8 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&bar_fa[st], ph);
-      mbar_wait(&bar_fz[st], ph);
+      mbar_wait_w(&bar_fa[st], ph);
+      mbar_wait_w(&bar_fz[st], ph);
       fence_after();
       if (elect_one()) {
         const uint32_t zh = tmem + HW + st * ZCOLS, zl = zh + N;
@@ -579,7 +597,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
       }
 #pragma unroll
       for (int pp = 0; pp < 8; ++pp) jets_from_ckpt<ND, LAP>(v[pp], lapw);
-      if (it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+      if (it >= 2) mbar_wait_w(&bar_empty[st], ph ^ 1);
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         const int n0 = s * P + half * 8;                 // 8 consecutive K positions = two 16-byte chunks
@@ -615,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
         float hi[16], lo[16];
 #pragma unroll
         for (int p = 0; p < P; ++p) hi[p] = __ldcs(src + (size_t)(s * P + p) * HW);
-        if (s == 0 && it >= 2) mbar_wait(&bar_empty[st], ph ^ 1);
+        if (s == 0 && it >= 2) mbar_wait_w(&bar_empty[st], ph ^ 1);
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           const float h = tf32_hi(hi[p]);
@@ -630,7 +648,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_fz[st]);
     }
-    mbar_wait(&bar_done, 0);
+    mbar_wait_w(&bar_done, 0);
     fence_after();
     double* g = a.gacc + lay.w(l) + (size_t)j * HW;
 #pragma unroll 1
@@ -676,7 +694,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
   constexpr uint32_t T_DW = 256, T_D = 384, T_ZH = 384 + NP, T_ZL = T_ZH + NS;
   static_assert(T_ZL + NS <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_fzn, bar_fzt, bar_fa[2], bar_dfull[2], bar_dempty, bar_zfree, bar_afree[2], bar_done;
+  __shared__ uint64_t bar_fzn[2], bar_fzt, bar_fa[2], bar_dfull[2], bar_dempty, bar_zfree, bar_afree[2], bar_done;
   __shared__ uint32_t tmem_slot;
   float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const Layout lay = a.lay;
@@ -697,7 +715,8 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       mbar_init(&bar_dfull[s], 1);
       mbar_init(&bar_afree[s], 1);
     }
-    mbar_init(&bar_fzn, 4);
+    mbar_init(&bar_fzn[0], 4);
+    mbar_init(&bar_fzn[1], 4);
     mbar_init(&bar_fzt, 4);
     mbar_init(&bar_dempty, 4);
     mbar_init(&bar_zfree, 1);
@@ -761,9 +780,11 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       const uint32_t zn_h = sbase + (uint32_t)(it & (ZSTAGES - 1)) * (2 * ZN * 4), zn_l = zn_h + ZN * 4;
       const uint32_t at_h = sbase + (uint32_t)(AT_OFF + st * AT_STAGE) * 4, at_l = at_h + AT * 4;
       TPX_WSTAMP(0, 0);
-      mbar_wait(&bar_fzn, it & 1);
+      // one barrier per Zn buffer: with two buffers the loader may be a whole step ahead, and a single barrier two
+      // phases ahead of its waiter passes the parity test the wrong way round (dead-lock)
+      mbar_wait_w(&bar_fzn[it & (ZSTAGES - 1)], (ZSTAGES == 2 ? (it >> 1) : it) & 1);
       TPX_WSTAMP(0, 1);
-      if (it >= 1) mbar_wait(&bar_dempty, (it - 1) & 1);
+      if (it >= 1) mbar_wait_w(&bar_dempty, (it - 1) & 1);
       fence_after();
       TPX_WSTAMP(0, 2);
       if (elect_one()) {
@@ -784,9 +805,9 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       }
       __syncwarp();
       TPX_WSTAMP(0, 3);
-      mbar_wait(&bar_fzt, it & 1);
+      mbar_wait_w(&bar_fzt, it & 1);
       TPX_WSTAMP(0, 4);
-      mbar_wait(&bar_fa[st], ph2);
+      mbar_wait_w(&bar_fa[st], ph2);
       fence_after();
       TPX_WSTAMP(0, 5);
       if (elect_one()) {
@@ -847,7 +868,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       // this step's Zn buffer is free once the adjoint product of step it - ZSTAGES has completed
       float* zn_h = sm + (it & (ZSTAGES - 1)) * (2 * ZN);
       float* zn_l = zn_h + ZN;
-      if (it >= ZSTAGES) mbar_wait(&bar_dfull[(it - ZSTAGES) & 1], ((it - ZSTAGES) >> 1) & 1);
+      if (it >= ZSTAGES) mbar_wait_w(&bar_dfull[(it - ZSTAGES) & 1], ((it - ZSTAGES) >> 1) & 1);
       TPX_WSTAMP(1, 1);
 #pragma unroll
       for (int s = 0; s < S; ++s)
@@ -860,10 +881,10 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
         }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_fzn);
+      if (lane == 0) mbar_arrive(&bar_fzn[it & (ZSTAGES - 1)]);
       TPX_WSTAMP(1, 2);
       // Zbar^T in TMEM is free once the gradient product of step it-1 has completed
-      if (it >= 1) mbar_wait(&bar_zfree, (it - 1) & 1);
+      if (it >= 1) mbar_wait_w(&bar_zfree, (it - 1) & 1);
       fence_after();
       TPX_WSTAMP(1, 3);
 #pragma unroll
@@ -883,7 +904,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       if (lane == 0) mbar_arrive(&bar_fzt);
       TPX_WSTAMP(1, 4);
     }
-    mbar_wait(&bar_done, 0);
+    mbar_wait_w(&bar_done, 0);
     fence_after();
     double* g = a.gacc + lay.w(l) + (size_t)j * HW;
 #pragma unroll 1
@@ -938,7 +959,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       }
       TPX_WSTAMP(2 + set, 0);
       // At[set] is free once the gradient product of step it-2 has completed
-      if (it >= 2) mbar_wait(&bar_afree[set], ph2 ^ 1);
+      if (it >= 2) mbar_wait_w(&bar_afree[set], ph2 ^ 1);
       TPX_WSTAMP(2 + set, 1);
       {
         float av[8][S];
@@ -966,7 +987,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       if (lane == 0) mbar_arrive(&bar_fa[set]);
       TPX_WSTAMP(2 + set, 2);
       // the adjoint product of this step
-      mbar_wait(&bar_dfull[set], ph2);
+      mbar_wait_w(&bar_dfull[set], ph2);
       fence_after();
       TPX_WSTAMP(2 + set, 3);
       float ab[S][8];
