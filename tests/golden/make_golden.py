@@ -421,16 +421,23 @@ def domains():
 
 
 if __name__ == "__main__":
-    poisson((64, 64, 64, 64), 257, "poisson_4x64")
-    poisson((20, 20, 20), 100, "poisson_3x20_sin", act=tp.models.Sinus())
-    heat((48, 48, 48), 193, "heat_3x48")
-    navier_stokes((32, 32, 32), 130, "ns_3x32")
-    deep_ritz((40, 40, 40, 40), 150, "ritz_4x40")
-    heat_normalized((48, 48, 48), 161, "heat_norm_3x48")
-    poisson_hard_constraint((32, 32, 32), 143, "poisson_hard_3x32")
-    deeponet(6, 40, 16, "deeponet_2x32")
-    deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50)
-    domains()
-    boundaries()
-    cut_boundary()
-    union_boundary()
+    JOBS = {
+        "poisson_4x64": lambda: poisson((64, 64, 64, 64), 257, "poisson_4x64"),
+        "poisson_3x20_sin": lambda: poisson((20, 20, 20), 100, "poisson_3x20_sin", act=tp.models.Sinus()),
+        "heat_3x48": lambda: heat((48, 48, 48), 193, "heat_3x48"),
+        "ns_3x32": lambda: navier_stokes((32, 32, 32), 130, "ns_3x32"),
+        "ritz_4x40": lambda: deep_ritz((40, 40, 40, 40), 150, "ritz_4x40"),
+        "heat_norm_3x48": lambda: heat_normalized((48, 48, 48), 161, "heat_norm_3x48"),
+        "poisson_hard_3x32": lambda: poisson_hard_constraint((32, 32, 32), 143, "poisson_hard_3x32"),
+        "deeponet_2x32": lambda: deeponet(6, 40, 16, "deeponet_2x32"),
+        "deeponet_4x64": lambda: deeponet(5, 33, 64, "deeponet_4x64", trunk_hidden=(64,) * 4, branch_hidden=(64,) * 4, n_sensors=50),
+        "domains": domains,
+        "boundaries": boundaries,
+        "cut_boundary": cut_boundary,
+        "union_boundary": union_boundary,
+        # hidden width 128 (configs 2 and 3 of BASELINE.json at reduced depth): the wide tensor-core path
+        "heat_3x128": lambda: heat((128, 128, 128), 211, "heat_3x128"),
+        "ns_3x128": lambda: navier_stokes((128, 128, 128), 147, "ns_3x128"),
+    }
+    for job in (sys.argv[1:] or list(JOBS)):      # `make_golden.py NAME ...` regenerates only those fixtures
+        JOBS[job]()

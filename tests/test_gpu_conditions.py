@@ -46,11 +46,12 @@ def test_pinn_condition_poisson_matches_reference():
             assert relerr(a, w) < TOL
 
 
-def test_operators_on_model_output_match_reference():
+@pytest.mark.parametrize("name,width", [("ns_3x32", 32), ("ns_3x128", 128)])     # 128: wide tensor-core path
+def test_operators_on_model_output_match_reference(name, width):
     import torchphysics_b200 as tp
-    G = load("ns_3x32")
+    G = load(name)
     X, Y = tp.spaces.R2("x"), tp.spaces.R2("u") * tp.spaces.R1("p")
-    model = tp.models.FCN(X, Y, hidden=(32,) * 3).cuda()
+    model = tp.models.FCN(X, Y, hidden=(width,) * 3).cuda()
     _load_params(model, G["params"])
     pts = tp.spaces.Points(torch.from_numpy(G["x"]).cuda(), X)
     coords, pts = pts.track_coord_gradients()
@@ -77,11 +78,12 @@ def test_operators_on_model_output_match_reference():
             assert relerr(a, w) < TOL
 
 
-def test_heat_condition_with_product_space():
+@pytest.mark.parametrize("name,width", [("heat_3x48", 48), ("heat_3x128", 128)])   # 128: wide tensor-core path
+def test_heat_condition_with_product_space(name, width):
     import torchphysics_b200 as tp
-    G = load("heat_3x48")
+    G = load(name)
     X, T, U = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
-    model = tp.models.FCN(X * T, U, hidden=(48,) * 3).cuda()
+    model = tp.models.FCN(X * T, U, hidden=(width,) * 3).cuda()
     _load_params(model, G["params"])
     sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["xt"]), X * T))
     cond = tp.conditions.PINNCondition(model, sampler, lambda u, x, t: tp.utils.grad(u, t) - tp.utils.laplacian(u, x))

@@ -66,8 +66,9 @@ def test_poisson_golden(name, act):
         assert relerr(g, w) < TOL
 
 
-def test_heat_golden():
-    G = load("heat_3x48")
+@pytest.mark.parametrize("name", ["heat_3x48", "heat_3x128"])           # 128: wide tensor-core path (reverse sweep)
+def test_heat_golden(name):
+    G = load(name)
     xt = G["xt"]
     N = xt.shape[0]
     u, du, lap, _ = _run(G["params"], "tanh", xt, (0, 1, 2), (1.0, 1.0, 0.0))
@@ -82,8 +83,9 @@ def test_heat_golden():
         assert relerr(g, w) < TOL
 
 
-def test_navier_stokes_golden():
-    G = load("ns_3x32")
+@pytest.mark.parametrize("name", ["ns_3x32", "ns_3x128"])
+def test_navier_stokes_golden(name):
+    G = load(name)
     u, du, lap, _ = _run(G["params"], "tanh", G["x"], (0, 1), (1.0, 1.0))
     assert relerr(u, G["y"]) < TOL
     assert relerr(du, G["jac"]) < TOL
