@@ -14,6 +14,10 @@ CASES = {
     "d": (2, 3, (100, 128, 96), (0, 1), (1.0, 1.0), 200),
     "e": (4, 8, (128,) * 3, (), None, 777),
     "f": (1, 2, (96,) * 4, (0,), None, 5000),
+    "g": (2, 1, (256,) * 3, (0, 1), None, 300),
+    "h": (2, 1, (256,) * 8, (0, 1), None, 150),
+    "i": (3, 2, (200, 256, 130), (0, 1, 2), (1.0, 1.0, 0.0), 1000),
+    "j": (2, 1, (256, 256), (0, 1), (1.0, 1.0), 5000),
 }
 for name in (sys.argv[1:] or list(CASES)):
     d_in, d_out, hidden, dcols, lap_w, N = CASES[name]

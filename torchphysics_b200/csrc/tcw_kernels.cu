@@ -101,6 +101,11 @@ struct WArgs {
   const float* ck;       // ADJ / DW: ckpt_{l-1} (unused for l = 1)
   float* out;            // FWD: ckpt_l; ADJ: Zbar_{l-1} (unused for l = 1)
   double* gacc;
+  // hidden width 129..256: the matrices are processed as 128 x 128 blocks, activations are stored as two half-arrays
+  int jb, kb;            // FWD: output-neuron block jb, input-neuron block kb.  REV: Zbar (output-neuron) block jb, input-neuron block kb
+  int part_out, part_in; // the product is one K block of a sum: write it raw to `part` / add `part` to it before the epilogue
+  float* part;           // half-array of partial products
+  int64_t half_stride;   // output kernels: floats between the half-arrays of one layer
   long long* dbg;        // development (-DTPX_TIMELINE): clock64 stamps of steps 40..43 of CTA 0 of the reverse kernel
 };
 
@@ -111,7 +116,7 @@ struct Layer0 {
   __device__ __forceinline__ void load(const Layout& lay, const float* __restrict__ packed, int i) {
     d_in = lay.d_in;
 #pragma unroll
-    for (int c = 0; c < MAXD; ++c) w[c] = (c < d_in) ? __ldg(packed + lay.w0() + (size_t)c * HW + i) : 0.0f;
+    for (int c = 0; c < MAXD; ++c) w[c] = (c < d_in) ? __ldg(packed + lay.w0() + (size_t)c * lay.HP + i) : 0.0f;
     b = __ldg(packed + lay.b0() + i);
   }
   __device__ __forceinline__ float col(int c) const {
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
   const uint32_t tmem = tmem_slot;
   // ---- the matrix (A operand) into TMEM: lane = row, columns [0,128) hi, [128,256) lo
   if (warp < EPI_WARPS) {
-    const float* Wrow = a.packed + (MODE == FWD ? lay.w(l) : lay.wt(l)) + (size_t)(warp * 32 + lane) * HW;
+    const float* Wrow = a.packed + (MODE == FWD ? lay.w(l) : lay.wt(l)) + (size_t)(a.jb * HW + warp * 32 + lane) * lay.HP + a.kb * HW;
     const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < HW / 16; ++c) {
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
     Layer0 l0;
     float dz0[NDX];
     if (MODE == FWD && l == 1) {
-      l0.load(lay, a.packed, i);
+      l0.load(lay, a.packed, a.kb * HW + i);
 #pragma unroll
       for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
     }
@@ -374,13 +379,15 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
     const int j = q * 32 + lane;
     const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + 256;
     if (MODE == FWD) {
-      const float bias = __ldg(a.packed + lay.b(l) + j);
+      const float bias = __ldg(a.packed + lay.b(l) + a.jb * HW + j);
+      const bool part_in = a.part_in != 0, part_out = a.part_out != 0;
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int st = it & 1;
         mbar_wait_w(&bar_dfull[st], (it >> 1) & 1);
         fence_after();
-        float* dst = a.out + (size_t)tile * N * HW + j;
+        float* dst = (part_out ? a.part : a.out) + (size_t)tile * N * HW + j;
+        const float* pin = a.part + (size_t)tile * N * HW + j;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           float d[16];
@@ -390,7 +397,11 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dempty[st]);
           }
-          if (s == 0) {
+          if (part_in) {                       // the other K block of a 256-wide layer
+#pragma unroll
+            for (int p = 0; p < P; ++p) d[p] += __ldcs(pin + (size_t)(s * P + p) * HW);
+          }
+          if (s == 0 && !part_out) {
 #pragma unroll
             for (int p = 0; p < P; ++p) d[p] = tanh_w(d[p] + bias);
           }
@@ -736,7 +747,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
   fence_after();
   const uint32_t tmem = tmem_slot;
   if (warp < 4) {                              // W^T into TMEM: lane = input neuron i, K = output neuron j
-    const float* Wrow = a.packed + lay.wt(l) + (size_t)(warp * 32 + lane) * HW;
+    const float* Wrow = a.packed + lay.wt(l) + (size_t)(a.kb * HW + warp * 32 + lane) * lay.HP + a.jb * HW;
     const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < HW / 16; ++c) {
@@ -906,7 +917,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     }
     mbar_wait_w(&bar_done, 0);
     fence_after();
-    double* g = a.gacc + lay.w(l) + (size_t)j * HW;
+    double* g = a.gacc + lay.w(l) + (size_t)(a.jb * HW + j) * lay.HP + a.kb * HW;
 #pragma unroll 1
     for (int c = 0; c < HW / 16; ++c) {
       float d[16];
@@ -922,7 +933,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     Layer0 l0;
     float dz0[NDX];
     if (FIRST) {
-      l0.load(lay, a.packed, i);
+      l0.load(lay, a.packed, a.kb * HW + i);
 #pragma unroll
       for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
     }
@@ -997,6 +1008,19 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_dempty);
       TPX_WSTAMP(2 + set, 4);
+      if (a.part_in) {                         // 256-wide layers: the other block of output neurons
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+          for (int s = 0; s < S; ++s) ab[s][pp] += __ldcs(a.part + row0 + (size_t)(s * P + pp) * HW);
+      }
+      if (a.part_out) {                        // ... not complete yet: park the raw product, no adjoint jets
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+          for (int s = 0; s < S; ++s) __stcs(a.part + row0 + (size_t)(s * P + pp) * HW, ab[s][pp]);
+        continue;
+      }
       float part_db = 0.0f, part_w0[MAXD];
 #pragma unroll
       for (int c = 0; c < MAXD; ++c) part_w0[c] = 0.0f;
@@ -1025,11 +1049,13 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       for (int c = 0; c < MAXD; ++c) acc_w0[c] += (double)part_w0[c];
       TPX_WSTAMP(2 + set, 5);
     }
-    atomicAdd(a.gacc + (FIRST ? lay.b0() : lay.b(l - 1)) + i, acc_db);
-    if (FIRST) {
+    if (!a.part_out) {
+      atomicAdd(a.gacc + (FIRST ? lay.b0() : lay.b(l - 1)) + a.kb * HW + i, acc_db);
+      if (FIRST) {
 #pragma unroll
-      for (int c = 0; c < MAXD; ++c)
-        if (c < lay.d_in) atomicAdd(a.gacc + lay.w0() + (size_t)c * HW + i, acc_w0[c]);
+        for (int c = 0; c < MAXD; ++c)
+          if (c < lay.d_in) atomicAdd(a.gacc + lay.w0() + (size_t)c * lay.HP + a.kb * HW + i, acc_w0[c]);
+      }
     }
   }
   fence_before();
@@ -1047,10 +1073,10 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_fwd_kernel(WArgs a, float* 
                                                                 float* __restrict__ lapo) {
   constexpr int S = 1 + ND + LAP, N = S * P;
   constexpr int NDX = ND > 0 ? ND : 1;
-  __shared__ float WL[MAXO * HW];
+  __shared__ float WL[MAXO * 2 * HW];
   const Layout lay = a.lay;
-  const int d_out = lay.d_out;
-  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + v);
+  const int d_out = lay.d_out, hp = lay.HP, nblk = hp / HW;
+  for (int v = threadIdx.x; v < d_out * hp; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + v);
   __syncthreads();
   float lapw[NDX];
 #pragma unroll
@@ -1060,22 +1086,37 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_fwd_kernel(WArgs a, float* 
   for (int64_t pt = (int64_t)blockIdx.x * (OUT_THREADS / 32) + (threadIdx.x >> 5); pt < a.n; pt += nwarps) {
     const int64_t tile = pt / P;
     const int p = (int)(pt % P);
-    const float* src = a.in + ((size_t)tile * N + p) * HW + lane;
-    float v[4][S];
+    float acc[MAXO][S];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int o = 0; o < MAXO; ++o)
 #pragma unroll
-      for (int s = 0; s < S; ++s) v[c][s] = __ldcs(src + (size_t)s * P * HW + c * 32);
+      for (int s = 0; s < S; ++s) acc[o][s] = 0.0f;
+    for (int hb = 0; hb < nblk; ++hb) {        // half-arrays of a 256-wide layer
+      const float* src = a.in + (size_t)hb * a.half_stride + ((size_t)tile * N + p) * HW + lane;
+      float v[4][S];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) jets_from_ckpt<ND, LAP>(v[c], lapw);
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int s = 0; s < S; ++s) v[c][s] = __ldcs(src + (size_t)s * P * HW + c * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) jets_from_ckpt<ND, LAP>(v[c], lapw);
+#pragma unroll
+      for (int o = 0; o < MAXO; ++o)
+        if (o < d_out) {
+#pragma unroll
+          for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[o][s] = fmaf(WL[o * hp + hb * HW + c * 32 + lane], v[c][s], acc[o][s]);
+        }
+    }
     for (int o = 0; o < d_out; ++o) {
       float r[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        float acc = 0.0f;
+        float t = acc[0][s];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc = fmaf(WL[o * HW + c * 32 + lane], v[c][s], acc);
-        r[s] = acc;
+        for (int oo = 1; oo < MAXO; ++oo) t = (o == oo) ? acc[oo][s] : t;
+        r[s] = t;
       }
 #pragma unroll
       for (int m = 16; m > 0; m >>= 1)
@@ -1101,7 +1142,8 @@ __global__ void __launch_bounds__(OUT_THREADS, (DO <= 2) ? 3 : 2) w_out_bwd_kern
   __shared__ float red[(DO + 1) * HW + DO];
   const Layout lay = a.lay;
   const int d_out = lay.d_out;
-  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + v);
+  const int hp = lay.HP, hb = a.kb;              // this launch: neurons [128 hb, 128 hb + 128) of the last hidden layer
+  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) WL[v] = __ldg(a.packed + lay.wl() + (size_t)(v / HW) * hp + hb * HW + v % HW);
   for (int v = threadIdx.x; v < (DO + 1) * HW + DO; v += OUT_THREADS) red[v] = 0.0f;
   __syncthreads();
   float lapw[NDX];
@@ -1178,9 +1220,10 @@ __global__ void __launch_bounds__(OUT_THREADS, (DO <= 2) ? 3 : 2) w_out_bwd_kern
   }
   if (lane < DO) atomicAdd(&red[(DO + 1) * HW + lane], acc_bl);
   __syncthreads();
-  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.wl() + v, (double)red[v]);
-  for (int v = threadIdx.x; v < HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.b(lay.L - 1) + v, (double)red[DO * HW + v]);
-  if (threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(DO + 1) * HW + threadIdx.x]);
+  for (int v = threadIdx.x; v < d_out * HW; v += OUT_THREADS)
+    atomicAdd(a.gacc + lay.wl() + (size_t)(v / HW) * hp + hb * HW + v % HW, (double)red[v]);
+  for (int v = threadIdx.x; v < HW; v += OUT_THREADS) atomicAdd(a.gacc + lay.b(lay.L - 1) + hb * HW + v, (double)red[DO * HW + v]);
+  if (hb == 0 && threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(DO + 1) * HW + threadIdx.x]);
 }
 
 template <int ND, int LAP>
@@ -1209,20 +1252,29 @@ struct Launch {
     return (unsigned)(sm_count < ntiles ? sm_count : ntiles);
   }
 
+  // Storage (floats): per = one half-array = ntiles x N x 128; a layer is nblk = HP / 128 consecutive half-arrays.
+  //   [checkpoints of hidden layers 1..L-1][Zbar A][Zbar B][partial products (nblk = 2 only)]
+  static size_t per_floats(int64_t n) { return (size_t)((n + P - 1) / P) * N * HW; }
+
   static int forward(WArgs a, float* saved, float* u, float* du, float* lapo, int sm_count, cudaStream_t stream) {
-    const int L = a.lay.L;
-    const size_t per = (size_t)((a.n + P - 1) / P) * N * HW;     // floats of one activation array
+    const int L = a.lay.L, nblk = a.lay.HP / HW;
+    const size_t per = per_floats(a.n), layer = (size_t)nblk * per;
+    float* part = saved + (size_t)(L + 1) * layer;
     int rc = set_smem(w_layer_kernel<ND, LAP, FWD>, layer_smem(), "w_layer_kernel<FWD>");
     if (rc) return rc;
-    for (int l = 1; l < L; ++l) {
-      a.l = l;
-      a.in = (l == 1) ? nullptr : saved + (size_t)(l - 2) * per;
-      a.out = saved + (size_t)(l - 1) * per;
-      w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
-      if ((rc = check("w_layer_kernel<FWD>"))) return rc;
-    }
+    for (int l = 1; l < L; ++l)
+      for (int jb = 0; jb < nblk; ++jb)
+        for (int kb = 0; kb < nblk; ++kb) {      // z_l[jb] = sum_kb W_l[jb][kb] a_{l-1}[kb]: the K blocks meet in `part`
+          a.l = l; a.jb = jb; a.kb = kb;
+          a.in = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer + (size_t)kb * per;
+          a.out = saved + (size_t)(l - 1) * layer + (size_t)jb * per;
+          a.part = part; a.part_out = kb < nblk - 1; a.part_in = kb > 0;
+          w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
+          if ((rc = check("w_layer_kernel<FWD>"))) return rc;
+        }
     if (u) {
-      a.in = saved + (size_t)(L - 2) * per;
+      a.in = saved + (size_t)(L - 2) * layer;
+      a.half_stride = (int64_t)per;
       int64_t blocks = (a.n + OUT_THREADS / 32 - 1) / (OUT_THREADS / 32);
       if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
       w_out_fwd_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, u, du, lapo);
@@ -1232,15 +1284,16 @@ struct Launch {
   }
 
   static int backward(WArgs a, float* saved, const float* gu, const float* gdu, const float* glap, int sm_count, cudaStream_t stream) {
-    const int L = a.lay.L;
-    const size_t per = (size_t)((a.n + P - 1) / P) * N * HW;
-    float* zb[2] = {saved + (size_t)(L - 1) * per, saved + (size_t)L * per};
-    int rc = set_smem(w_layer_kernel<ND, LAP, ADJ>, layer_smem(), "w_layer_kernel<ADJ>");
-    if (rc) return rc;
-    if ((rc = set_smem(w_dw_kernel<ND, LAP>, dw_smem(), "w_dw_kernel"))) return rc;
-    a.in = saved + (size_t)(L - 2) * per;
-    a.out = zb[0];
-    {
+    const int L = a.lay.L, nblk = a.lay.HP / HW;
+    const size_t per = per_floats(a.n), layer = (size_t)nblk * per;
+    float* zb[2] = {saved + (size_t)(L - 1) * layer, saved + (size_t)L * layer};
+    float* part = saved + (size_t)(L + 1) * layer;
+    static const int split = env_flag("TPX_TCW_SPLIT");      // development: separate dW / adjoint launches (width <= 128)
+    int rc;
+    for (int hb = 0; hb < nblk; ++hb) {
+      a.kb = hb;
+      a.in = saved + (size_t)(L - 2) * layer + (size_t)hb * per;
+      a.out = zb[0] + (size_t)hb * per;
       const int64_t npad = (a.n + P - 1) / P * P;
       int64_t blocks = (npad + OUT_THREADS / 32 - 1) / (OUT_THREADS / 32);
       if (blocks > (int64_t)sm_count * 6) blocks = (int64_t)sm_count * 6;
@@ -1251,26 +1304,40 @@ struct Launch {
       else w_out_bwd_kernel<ND, LAP, 8><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
       if ((rc = check("w_out_bwd_kernel"))) return rc;
     }
-    static const int split = env_flag("TPX_TCW_SPLIT");      // development: separate dW / adjoint launches
-    if (!split && (rc = set_smem(w_rev_kernel<ND, LAP, false>, rev_smem(), "w_rev_kernel"))) return rc;
-    if (!split && (rc = set_smem(w_rev_kernel<ND, LAP, true>, rev_smem(), "w_rev_kernel"))) return rc;
+    if (split && nblk == 1) {
+      if ((rc = set_smem(w_layer_kernel<ND, LAP, ADJ>, layer_smem(), "w_layer_kernel<ADJ>"))) return rc;
+      if ((rc = set_smem(w_dw_kernel<ND, LAP>, dw_smem(), "w_dw_kernel"))) return rc;
+    } else {
+      if ((rc = set_smem(w_rev_kernel<ND, LAP, false>, rev_smem(), "w_rev_kernel"))) return rc;
+      if ((rc = set_smem(w_rev_kernel<ND, LAP, true>, rev_smem(), "w_rev_kernel"))) return rc;
+    }
     int cur = 0;
     for (int l = L - 1; l >= 1; --l) {
       a.l = l;
-      a.in = zb[cur];
-      a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * per;
-      a.out = zb[cur ^ 1];
-      if (split) {
+      if (split && nblk == 1) {
+        a.jb = a.kb = 0; a.part_out = a.part_in = 0;
+        a.in = zb[cur];
+        a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer;
+        a.out = zb[cur ^ 1];
         w_dw_kernel<ND, LAP><<<grid(a, sm_count), THREADS, dw_smem(), stream>>>(a);
         if ((rc = check("w_dw_kernel"))) return rc;
         w_layer_kernel<ND, LAP, ADJ><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
         if ((rc = check("w_layer_kernel<ADJ>"))) return rc;
       } else {
-        const int64_t nsub = (a.n + P - 1) / P * 2;
-        const unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
-        if (l == 1) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
-        else w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
-        if ((rc = check("w_rev_kernel"))) return rc;
+        // dW_l[jb][ib] is complete per launch; Abar_{l-1}[ib] = sum_jb W_l[jb][ib]^T Zbar_l[jb] meets in `part`
+        for (int ib = 0; ib < nblk; ++ib)
+          for (int jb = 0; jb < nblk; ++jb) {
+            a.jb = jb; a.kb = ib;
+            a.in = zb[cur] + (size_t)jb * per;
+            a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer + (size_t)ib * per;
+            a.out = zb[cur ^ 1] + (size_t)ib * per;
+            a.part = part; a.part_out = jb < nblk - 1; a.part_in = jb > 0;
+            const int64_t nsub = (a.n + P - 1) / P * 2;
+            const unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
+            if (l == 1) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
+            else w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
+            if ((rc = check("w_rev_kernel"))) return rc;
+          }
       }
       cur ^= 1;
     }
@@ -1289,17 +1356,21 @@ bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   if (net->n_hidden < 2) return false;
   int wmax = 0;
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
-  if (wmax <= 64 || wmax > HW) return false;
+  if (wmax <= 64 || wmax > 2 * HW) return false;     // 129..256: two 128-neuron blocks per layer
   if (net->d_in > MAXD || net->d_out > MAXO) return false;
   if (lap && nd == 0) return false;
   if (nd < 0 || nd > 3) return false;
   return true;
 }
 
-// checkpoints of hidden layers 1..L-1 plus the two Zbar buffers of the reverse sweep
+// checkpoints of hidden layers 1..L-1 plus the two Zbar buffers of the reverse sweep (+ one half-array of partial
+// products for 256-wide layers); a layer of width <= 128 is one half-array, a wider one two
 size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n) {
+  int wmax = 0;
+  for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
+  const size_t nblk = wmax > HW ? 2 : 1;
   const size_t per = (size_t)((n + P - 1) / P) * (size_t)((1 + nd + lap) * P) * HW * sizeof(float);
-  return (size_t)(net->n_hidden + 1) * per;
+  return ((size_t)(net->n_hidden + 1) * nblk + (nblk > 1 ? 1 : 0)) * per;
 }
 
 #define TCW_DISPATCH(CALL)                                     \
