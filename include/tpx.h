@@ -101,11 +101,13 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
  * (the normal training step: condition.py:293-304 then solver.py:100-109), the forward kernel can save the
  * per-layer jets (8 KB per point for a 4x64 net; HBM is 180 GB) and the reverse kernel reads them instead of
  * re-running the forward sweep.  *bytes = 0 when this network / jet has no saving kernel.
- * Hidden widths 65..128 (tanh, d_in <= 4, d_out <= 8) run on the layer-major tensor-core kernels
+ * Hidden widths 65..256 (tanh, d_in <= 4, d_out <= 8) run on the layer-major tensor-core kernels
  * (csrc/tcw_kernels.cu) ONLY through this pair of calls: their `saved` buffer holds the checkpoints of the
- * hidden layers 1..L-1 ([tile of 16 points][stream * 16 + point][128 neurons] fp32 per layer) followed by two
- * scratch arrays of the same size for the reverse sweep, (L + 1) * S * 512 bytes per point in total; the
- * checkpoints are not consumed (the reverse may be repeated), the scratch part is overwritten.
+ * hidden layers 1..L-1 ([tile of 16 points][stream * 16 + point][128 neurons] fp32 per layer and 128-neuron
+ * block: one block up to width 128, two above) followed by two scratch arrays of the same size for the reverse
+ * sweep (+ one block of partial products for two blocks): (L + 1) * S * 512 bytes per point up to width 128,
+ * (2 L + 3) * S * 512 above; the checkpoints are not consumed (the reverse may be repeated), the scratch part
+ * is overwritten.
  * Without a saved buffer (tpx_fcn_jet_forward / tpx_fcn_jet_backward) those networks use the FP32 kernels. */
 int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_t n, size_t* bytes);
 int tpx_fcn_jet_forward_save(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,

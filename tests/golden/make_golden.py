@@ -438,6 +438,8 @@ if __name__ == "__main__":
         # hidden width 128 (configs 2 and 3 of BASELINE.json at reduced depth): the wide tensor-core path
         "heat_3x128": lambda: heat((128, 128, 128), 211, "heat_3x128"),
         "ns_3x128": lambda: navier_stokes((128, 128, 128), 147, "ns_3x128"),
+        # hidden width 256 (config 5 at reduced depth): two 128-neuron blocks per layer on the wide path
+        "ritz_2x256": lambda: deep_ritz((256, 256), 139, "ritz_2x256"),
     }
     for job in (sys.argv[1:] or list(JOBS)):      # `make_golden.py NAME ...` regenerates only those fixtures
         JOBS[job]()

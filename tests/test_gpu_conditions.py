@@ -96,11 +96,12 @@ def test_heat_condition_with_product_space(name, width):
         assert relerr(a, w) < TOL
 
 
-def test_deep_ritz_condition():
+@pytest.mark.parametrize("name,hidden", [("ritz_4x40", (40,) * 4), ("ritz_2x256", (256, 256))])   # 256: wide path, two blocks
+def test_deep_ritz_condition(name, hidden):
     import torchphysics_b200 as tp
-    G = load("ritz_4x40")
+    G = load(name)
     X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
-    model = tp.models.FCN(X, U, hidden=(40,) * 4).cuda()
+    model = tp.models.FCN(X, U, hidden=hidden).cuda()
     _load_params(model, G["params"])
     sampler = tp.samplers.DataSampler(tp.spaces.Points(torch.from_numpy(G["x"]), X))
     cond = tp.conditions.DeepRitzCondition(

@@ -92,8 +92,9 @@ def test_navier_stokes_golden(name):
     assert relerr(lap[:, :2], G["lap"]) < TOL
 
 
-def test_deep_ritz_golden():
-    G = load("ritz_4x40")
+@pytest.mark.parametrize("name", ["ritz_4x40", "ritz_2x256"])
+def test_deep_ritz_golden(name):
+    G = load(name)
     x = G["x"]
     N = x.shape[0]
     u, du, lap, _ = _run(G["params"], "tanh", x, (0, 1), None)
@@ -137,6 +138,10 @@ CASES = [
     (4, 1, (128, 72, 128, 90), "tanh", (3, 0, 1), None, 2371),
     (2, 4, (112,) * 3, "tanh", (1,), (0.75,), 2500),
     (5, 1, (128,) * 3, "tanh", (0, 4), (1.0, 1.0), 150),       # d_in > 4: FP32 kernels
+    # widths 129..256: two 128-neuron blocks per layer on the wide path
+    (3, 2, (200, 256, 130), "tanh", (0, 1, 2), (1.0, 1.0, 0.0), 1000),
+    (2, 1, (256, 256), "tanh", (0, 1), (1.0, 1.0), 5000),
+    (2, 3, (129,) * 4, "tanh", (1,), None, 333),
 ]
 
 
@@ -258,7 +263,8 @@ def test_saved_checkpoints_equal_recompute(hidden, dcols, lap_w, d_out):
 
 
 @pytest.mark.parametrize("hidden,dcols,lap_w,d_out,d_in", [((128,) * 4, (0, 1, 2), (1.0, 1.0, 0.0), 1, 3),
-                                                            ((96, 128, 80), (0, 1), (1.0, 1.0), 3, 2)])
+                                                            ((96, 128, 80), (0, 1), (1.0, 1.0), 3, 2),
+                                                            ((256, 192, 256), (0, 1), None, 1, 2)])
 def test_wide_path_equals_fp32_kernels(hidden, dcols, lap_w, d_out, d_in):
     """wide tensor-core path (checkpoint-saving forward + layer-major reverse, used when the engine hands the
     kernels a saved buffer) against the FP32 CUDA-core kernels (plain forward / workspace reverse) on the same
@@ -276,7 +282,8 @@ def test_wide_path_equals_fp32_kernels(hidden, dcols, lap_w, d_out, d_in):
     gdu = torch.randn(N, d_out, len(dcols), device="cuda")
     glap = torch.randn(N, d_out, device="cuda") if lap_w else None
     nbytes = eng.saved_bytes(spec, N)
-    assert nbytes == ((N + 15) // 16) * (len(hidden) + 1) * S * 16 * 128 * 4
+    nblk = 2 if max(hidden) > 128 else 1       # 128-neuron blocks per layer; one more half-array of partial products for two
+    assert nbytes == ((N + 15) // 16) * ((len(hidden) + 1) * nblk + (nblk > 1)) * S * 16 * 128 * 4
     saved = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     u1, du1, lap1 = eng.forward_raw(packed, x, spec, saved)
     u0, du0, lap0 = eng.forward_raw(packed, x, spec)          # FP32 kernels

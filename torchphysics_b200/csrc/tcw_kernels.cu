@@ -1,4 +1,5 @@
-// Tensor-core (tcgen05 / TMEM) jet kernels for hidden widths 65..128 ("wide" path), tanh, <= 5 streams.
+// Tensor-core (tcgen05 / TMEM) jet kernels for hidden widths 65..256 ("wide" path), tanh, <= 5 streams.
+// (Written for one 128-neuron block per layer; widths 129..256 run the same kernels on 128 x 128 blocks, see Launch.)
 //
 // Formulation: NEURONS ARE THE UMMA ROWS.  For a hidden matrix W (128 x 128, zero padded) and a tile of
 // P = 16 collocation points with S streams (value, d_k, weighted Laplacian), N = S * P columns:
