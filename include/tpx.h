@@ -83,6 +83,14 @@ int tpx_fcn_pack(const tpx_fcn_desc* net, const void* const* params_host, float*
 int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
                         const float* x, int64_t n, float* u, float* du, float* lap, void* stream);
 
+/* The same forward jet with a caller workspace of at least tpx_fcn_backward_workspace_bytes() bytes: networks of
+ * hidden width 65..256 (tanh, d_in <= 4, d_out <= 8) then run on the layer-major tensor-core kernels
+ * (csrc/tcw_kernels.cu), whose per-layer activation arrays live in the workspace (chunks of points); every other
+ * network ignores the workspace.  tpx_fcn_jet_backward uses its workspace for those networks in the same way. */
+int tpx_fcn_jet_forward_ws(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                           const float* x, int64_t n, float* u, float* du, float* lap, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* Bytes of scratch tpx_fcn_jet_backward needs (per-CTA activation checkpoints that are
  * written and re-read within one kernel, sized to stay in the 126 MB L2). */
 int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, size_t* bytes);
@@ -102,13 +110,14 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
  * per-layer jets (8 KB per point for a 4x64 net; HBM is 180 GB) and the reverse kernel reads them instead of
  * re-running the forward sweep.  *bytes = 0 when this network / jet has no saving kernel.
  * Hidden widths 65..256 (tanh, d_in <= 4, d_out <= 8) run on the layer-major tensor-core kernels
- * (csrc/tcw_kernels.cu) ONLY through this pair of calls: their `saved` buffer holds the checkpoints of the
+ * (csrc/tcw_kernels.cu); through this pair of calls their `saved` buffer holds the checkpoints of the
  * hidden layers 1..L-1 ([tile of 16 points][stream * 16 + point][128 neurons] fp32 per layer and 128-neuron
  * block: one block up to width 128, two above) followed by two scratch arrays of the same size for the reverse
  * sweep (+ one block of partial products for two blocks): (L + 1) * S * 512 bytes per point up to width 128,
  * (2 L + 3) * S * 512 above; the checkpoints are not consumed (the reverse may be repeated), the scratch part
  * is overwritten.
- * Without a saved buffer (tpx_fcn_jet_forward / tpx_fcn_jet_backward) those networks use the FP32 kernels. */
+ * Without a saved buffer those networks run the same kernels in chunks through a caller workspace
+ * (tpx_fcn_jet_forward_ws, tpx_fcn_jet_backward); plain tpx_fcn_jet_forward uses the FP32 kernels. */
 int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_t n, size_t* bytes);
 int tpx_fcn_jet_forward_save(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
                              const float* x, int64_t n, float* u, float* du, float* lap, void* saved,

@@ -265,16 +265,20 @@ def test_saved_checkpoints_equal_recompute(hidden, dcols, lap_w, d_out):
 @pytest.mark.parametrize("hidden,dcols,lap_w,d_out,d_in", [((128,) * 4, (0, 1, 2), (1.0, 1.0, 0.0), 1, 3),
                                                             ((96, 128, 80), (0, 1), (1.0, 1.0), 3, 2),
                                                             ((256, 192, 256), (0, 1), None, 1, 2)])
-def test_wide_path_equals_fp32_kernels(hidden, dcols, lap_w, d_out, d_in):
-    """wide tensor-core path (checkpoint-saving forward + layer-major reverse, used when the engine hands the
-    kernels a saved buffer) against the FP32 CUDA-core kernels (plain forward / workspace reverse) on the same
-    inputs; the saved buffer holds the checkpoints of hidden layers 1..L-1 and the two Zbar buffers of the reverse."""
+def test_wide_path_saved_workspace_and_fp32(hidden, dcols, lap_w, d_out, d_in):
+    """wide tensor-core path: (a) checkpoint-saving forward + reverse over the saved buffer (the training step), (b) the
+    same kernels in chunks of 65536 points through the caller workspace (no saved buffer), (c) the FP32 CUDA-core kernels
+    (TPX_DISABLE_TCW=1, separate process) agree on the same inputs.  The saved buffer holds the checkpoints of hidden
+    layers 1..L-1 and the scratch arrays of the reverse sweep."""
+    import os
+    import subprocess
+    import sys
     from torchphysics_b200.engine import FcnEngine, JetSpec
     torch.manual_seed(7)
     seq = ref_autograd.build_fcn(d_in, d_out, hidden).cuda()
     eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
     spec = JetSpec(dcols, lap_w)
-    N = 40001                                  # not a multiple of the 16-point tile, more tiles than SMs
+    N = 70001                                  # not a multiple of the 16-point tile, more tiles than SMs, two workspace chunks
     S = 1 + len(dcols) + (lap_w is not None)
     x = torch.rand(N, d_in, device="cuda")
     packed = eng.packed(eng.params())
@@ -286,19 +290,41 @@ def test_wide_path_equals_fp32_kernels(hidden, dcols, lap_w, d_out, d_in):
     assert nbytes == ((N + 15) // 16) * ((len(hidden) + 1) * nblk + (nblk > 1)) * S * 16 * 128 * 4
     saved = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     u1, du1, lap1 = eng.forward_raw(packed, x, spec, saved)
-    u0, du0, lap0 = eng.forward_raw(packed, x, spec)          # FP32 kernels
-    assert float((u1 - u0).abs().max() / u0.abs().max()) < 6e-6      # two fp32 evaluations, each ~2e-6 from the truth
-    assert float((du1 - du0).abs().max() / du0.abs().max()) < 6e-6
-    if lap_w:
-        assert float((lap1 - lap0).abs().max() / lap0.abs().max()) < 6e-6
-    g_wide = eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
-    g_fp32 = eng.backward_raw(packed, x, spec, gu, gdu, glap)
-    den = g_fp32.abs().max()
-    assert float((g_wide - g_fp32).abs().max() / den) < 6e-6
+    u0, du0, lap0 = eng.forward_raw(packed, x, spec)          # chunks through the workspace: the same arithmetic per point
+    assert torch.equal(u1, u0) and torch.equal(du1, du0) and (not lap_w or torch.equal(lap1, lap0))
+    g_saved = eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
+    g_ws = eng.backward_raw(packed, x, spec, gu, gdu, glap)
+    den = g_saved.abs().max()
+    assert float((g_saved - g_ws).abs().max() / den) < 2e-6    # dW sums are split differently over CTAs / chunks
     # a second reverse sweep over the same saved buffer (the checkpoints are not consumed) gives the same result up to
     # the order of the atomics (fp32 in shared memory for the output layer, float64 across CTAs)
     g_again = eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
-    assert float((g_again - g_wide).abs().max() / den) < 1e-6
+    assert float((g_again - g_saved).abs().max() / den) < 1e-6
+    # FP32 CUDA-core kernels in a separate process (the switch is read once per process)
+    code = (
+        "import sys, torch, torch.nn as nn; sys.path.insert(0, '.');"
+        "from oracle import ref_autograd; from torchphysics_b200.engine import FcnEngine, JetSpec;"
+        f"torch.manual_seed(7); seq = ref_autograd.build_fcn({d_in}, {d_out}, {hidden!r}).cuda();"
+        "eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], 'tanh');"
+        f"spec = JetSpec({dcols!r}, {lap_w!r}); x = torch.rand({N}, {d_in}, device='cuda');"
+        f"gu = torch.randn({N}, {d_out}, device='cuda'); gdu = torch.randn({N}, {d_out}, {len(dcols)}, device='cuda');"
+        + (f"glap = torch.randn({N}, {d_out}, device='cuda');" if lap_w else "glap = None;") +
+        "packed = eng.packed(eng.params()); u, du, lap = eng.forward_raw(packed, x, spec);"
+        "g = eng.backward_raw(packed, x, spec, gu, gdu, glap);"
+        "torch.save({'g': g.cpu(), 'u': u.cpu(), 'du': du.cpu(), 'lap': None if lap is None else lap.cpu()}, sys.argv[1])"
+    )
+    out = os.path.join(os.environ.get("TMPDIR", "/tmp"), f"tpx_fp32w_{os.getpid()}.pt")
+    env = dict(os.environ, TPX_DISABLE_TCW="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root, timeout=300)
+    ref = torch.load(out)
+    os.remove(out)
+    # two fp32 evaluations, each ~2e-6 from the truth
+    assert float((u1.cpu() - ref["u"]).abs().max() / ref["u"].abs().max()) < 6e-6
+    assert float((du1.cpu() - ref["du"]).abs().max() / ref["du"].abs().max()) < 6e-6
+    if lap_w:
+        assert float((lap1.cpu() - ref["lap"]).abs().max() / ref["lap"].abs().max()) < 6e-6
+    assert float((g_saved.cpu() - ref["g"]).abs().max() / den) < 6e-6
 
 
 def test_wide_path_reverse_is_linear_at_scale():

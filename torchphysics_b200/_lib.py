@@ -28,6 +28,7 @@ EXPORTS = (
     "tpx_fcn_packed_floats",
     "tpx_fcn_pack",
     "tpx_fcn_jet_forward",
+    "tpx_fcn_jet_forward_ws",
     "tpx_fcn_backward_workspace_bytes",
     "tpx_fcn_jet_backward",
     "tpx_fcn_unpack_grads",

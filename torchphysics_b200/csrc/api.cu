@@ -269,6 +269,42 @@ int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   return jet_forward(net, jet, packed, x, n, u, du, lap, nullptr, stream);
 }
 
+// points per chunk of the wide tensor-core path when its activation arrays live in a caller workspace
+static const int64_t kWideChunkPoints = 65536;
+static int64_t wide_chunk_points(const tpx_fcn_desc* net, int nd, int lap, size_t workspace_bytes) {
+  const size_t per16 = tcw_saved_bytes(net, nd, lap, 16);        // bytes of one 16-point tile
+  return (int64_t)(workspace_bytes / per16) * 16;
+}
+
+int tpx_fcn_jet_forward_ws(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const float* packed,
+                           const float* x, int64_t n, float* u, float* du, float* lap, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  Layout lay;
+  int rc = make_layout(net, &lay);
+  if (rc) return rc;
+  JetArgs ja;
+  rc = check_jet(net, jet, &ja);
+  if (rc) return rc;
+  const int lp = jet->lap ? 1 : 0;
+  if (tc_supported(net, jet->nd, lp) || !tcw_supported(net, jet->nd, lp) || n <= 0)
+    return jet_forward(net, jet, packed, x, n, u, du, lap, nullptr, stream);
+  if (!packed || !x || !u || !workspace) return fail(TPX_E_ARG, "NULL pointer");
+  if (jet->nd > 0 && !du) return fail(TPX_E_ARG, "du is NULL but nd > 0");
+  if (jet->lap && !lap) return fail(TPX_E_ARG, "lap is NULL but lap requested");
+  const int64_t cpts = wide_chunk_points(net, jet->nd, lp, workspace_bytes);
+  if (cpts < 16) return fail(TPX_E_WORKSPACE, "workspace of %zu bytes holds no 16-point tile of the wide path", workspace_bytes);
+  const int sms = sm_count();
+  if (sms <= 0) return fail(TPX_E_CUDA, "no CUDA device");
+  const int d_in = net->d_in, d_out = net->d_out, nd = jet->nd;
+  for (int64_t p0 = 0; p0 < n; p0 += cpts) {
+    const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
+    rc = tcw_forward(lay, ja, lp, packed, x + p0 * d_in, m, u + p0 * d_out, du ? du + p0 * d_out * nd : nullptr,
+                     lap ? lap + p0 * d_out : nullptr, (float*)workspace, sms, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_t n, size_t* bytes) {
   Layout lay;
   int rc = make_layout(net, &lay);
@@ -312,6 +348,9 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
   if (tc_bwd_supported(net, jet->nd, a.lap)) {
     const size_t tcb = tc_bwd_workspace_bytes(net, a.sm_count);
     if (tcb > *bytes) *bytes = tcb;
+  } else if (tcw_supported(net, jet->nd, a.lap)) {
+    const size_t wb = tcw_saved_bytes(net, jet->nd, a.lap, kWideChunkPoints);
+    if (wb > *bytes) *bytes = wb;
   }
   return 0;
 }
@@ -341,6 +380,24 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
     rc = tc_backward(net, a.lay, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
                      (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);
     return rc;                       // the launcher recorded the message
+  }
+  if (tcw_supported(net, jet->nd, a.lap)) {
+    // no saved activations: chunks of (forward sweep writing checkpoints only) + reverse sweep through the workspace;
+    // a workspace too small for one tile (a caller that sized it for the FP32 kernels) falls through to those
+    const int64_t cpts = wide_chunk_points(net, jet->nd, a.lap, workspace_bytes);
+    if (cpts >= 16) {
+      const int d_in = net->d_in, d_out = net->d_out, nd = jet->nd;
+      for (int64_t p0 = 0; p0 < n; p0 += cpts) {
+        const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
+        rc = tcw_forward(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, nullptr, nullptr, nullptr, (float*)workspace, a.sm_count, a.stream);
+        if (rc) return rc;
+        rc = tcw_backward(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, a.gu ? a.gu + p0 * d_out : nullptr,
+                          a.gdu ? a.gdu + p0 * d_out * nd : nullptr, a.glap ? a.glap + p0 * d_out : nullptr, grad_acc,
+                          (float*)workspace, a.sm_count, a.stream);
+        if (rc) return rc;
+      }
+      return 0;
+    }
   }
   switch (a.lay.HP) {
     case 32: rc = launch_bwd<32>(a); break;

@@ -150,9 +150,18 @@ class FcnEngine:
         lap = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device) if spec.lap else None
         j = spec.c_struct()
         if saved is None:
-            _lib.check(_lib.lib().tpx_fcn_jet_forward(
-                ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
-                _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.stream_ptr()))
+            try:                                    # widths 65..256: activation arrays of the tensor-core kernels
+                ws = self.workspace(spec, x.device)
+            except _lib.TpxError:                   # a jet without a reverse kernel: plain forward
+                ws = None
+            if ws is None:
+                _lib.check(_lib.lib().tpx_fcn_jet_forward(
+                    ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+                    _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.stream_ptr()))
+            else:
+                _lib.check(_lib.lib().tpx_fcn_jet_forward_ws(
+                    ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
+                    _lib.ptr(u), _lib.ptr(du), _lib.ptr(lap), _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr()))
         else:
             _lib.check(_lib.lib().tpx_fcn_jet_forward_save(
                 ctypes.byref(self.desc), ctypes.byref(j), _lib.ptr(packed), _lib.ptr(x), ctypes.c_int64(n),
