@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--points", type=int, default=1 << 21, help="collocation points per GPU per step")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -321,9 +322,51 @@ def run_native(args):
             line["cpu_baseline"] = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
                                     "sample": f"8 steps of {n_cpu} points, torch CPU autograd restatement of the "
                                               "reference call sites (oracle/ref_autograd.poisson_step)"}
+        if world == 1 and not args.no_other_configs:
+            # informational: kernel-only forward + reverse rate of the parity configurations 2 / 3 / 5 of BASELINE.json
+            # (hidden width 128 / 256: wide tensor-core kernels, csrc/tcw_kernels.cu), 2^18 points, inputs resident
+            try:
+                line["other_configs"] = other_configs_rate(dev)
+            except Exception as e:                       # never lose the headline line over the extras
+                line["other_configs"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs_rate(dev, n=1 << 18, reps=3):
+    import torch
+    import torchphysics_b200 as tp
+    from torchphysics_b200.engine import JetSpec
+    X, T, U, V, Pr = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u"), tp.spaces.R2("v"), tp.spaces.R1("p")
+    out = []
+    for name, inp, outp, hidden, spec in (
+            ("config 2: heat, FCN 6x128, S=5", X * T, U, (128,) * 6, JetSpec((0, 1, 2), (1.0, 1.0, 0.0))),
+            ("config 3: Navier-Stokes, FCN 6x128, 3 outputs, S=4", X, V * Pr, (128,) * 6, JetSpec((0, 1), (1.0, 1.0))),
+            ("config 5: Deep Ritz, FCN 8x256, S=3", X, U, (256,) * 8, JetSpec((0, 1), None))):
+        torch.manual_seed(0)
+        model = tp.models.FCN(inp, outp, hidden=hidden).to(dev)
+        eng = model._native_engine()
+        d_in, d_out = eng.d_in, eng.d_out
+        x = torch.rand(n, d_in, device=dev)
+        gu = torch.randn(n, d_out, device=dev)
+        gdu = torch.randn(n, d_out, spec.nd, device=dev)
+        glap = torch.randn(n, d_out, device=dev) if spec.lap else None
+        packed = eng.packed(eng.params())
+        saved = torch.empty(eng.saved_bytes(spec, n), dtype=torch.uint8, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for r in range(reps + 2):
+            if r == 2:
+                ev[0].record()
+            eng.forward_raw(packed, x, spec, saved)
+            eng.backward_raw(packed, x, spec, gu, gdu, glap, saved)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        out.append({"config": name, "value": n / ms * 1e3, "unit": "points/s", "ms_per_step": ms, "points": n,
+                    "what": "forward (saving checkpoints) + reverse sweep, kernels only"})
+        del saved, x, gu, gdu, glap
+    return out
 
 
 def main():
