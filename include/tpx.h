@@ -127,6 +127,14 @@ int tpx_fcn_jet_backward_saved(const tpx_fcn_desc* net, const tpx_jet_desc* jet,
                                const float* glap, double* grad_acc, const void* saved, size_t saved_bytes,
                                void* stream);
 
+/* Residual-loss reduction of PINNCondition (problem/conditions/condition.py:11-27 SquaredError, :488-489 mean):
+ *   *loss_acc += (1 / rows) * sum of r^2 over all `total` elements  (float64 device scalar, caller zeroes it;
+ *   warp-shuffle reduction, one atomic per CTA), and its adjoint  grad_r = grad_loss * 2 r / rows
+ *   (grad_loss: device scalar, NULL = 1).  r is the (rows, ...) residual batch, contiguous fp32. */
+int tpx_squared_error_mean(const float* r, int64_t total, int64_t rows, double* loss_acc, void* stream);
+int tpx_squared_error_mean_backward(const float* r, int64_t total, int64_t rows, const float* grad_loss, float* grad_r,
+                                    void* stream);
+
 /* float64 packed accumulator -> per-parameter float32 gradients (layout of nn.Linear).
  * grads_host: HOST array of 2*(n_hidden+1) device pointers (entries may be NULL).
  * accumulate != 0 adds to the existing gradient (PyTorch .grad semantics). */

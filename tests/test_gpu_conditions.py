@@ -391,3 +391,26 @@ def test_reference_poisson_examples_run_unchanged(kind):
         warnings.simplefilter("ignore")
         losses, err = mod.main(kind, 150)
     assert losses[-1] < 0.3 * losses[0] and err < 1.0
+
+
+@pytest.mark.parametrize("shape", [(1000, 1), (4097, 3), (7, 333, 2), (1, 1), (100003, 1)])
+def test_native_squared_error_mean(shape):
+    """tpx_squared_error_mean / _backward (the PINN loss reduction, reference condition.py:11-27 + 488-489) against the torch
+    expression the reference uses, values and gradients, incl. a residual that is not 16-byte aligned."""
+    from torchphysics_b200.conditions import SquaredError, _SquaredErrorMean
+    torch.manual_seed(0)
+    base = torch.randn(int(np.prod(shape)) + 1, device="cuda")
+    for off in (0, 1):
+        r = base[off:off + int(np.prod(shape))].reshape(shape).clone() if off == 0 else base[1:].reshape(shape)
+        a = r.detach().clone().requires_grad_(True)
+        b = r.detach().requires_grad_(True) if off == 0 else None
+        ref = torch.mean(SquaredError()(a))
+        (3.0 * ref).backward()
+        src = b if b is not None else base.detach().clone().requires_grad_(True)
+        rr = src if b is not None else src[1:].reshape(shape)
+        out = _SquaredErrorMean.apply(rr)
+        (3.0 * out).backward()
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        assert abs(float(out) - float(ref)) <= 2e-6 * abs(float(ref))
+        g = src.grad if b is not None else src.grad[1:].reshape(shape)
+        assert torch.allclose(g, a.grad, rtol=1e-6, atol=0)

@@ -45,6 +45,8 @@ EXPORTS = (
     "tpx_sample_lhs",
     "tpx_union_pick",
     "tpx_adam_step",
+    "tpx_squared_error_mean",
+    "tpx_squared_error_mean_backward",
 )
 
 TPX_SHAPE_INTERVAL = 1

@@ -24,6 +24,39 @@ class SquaredError(torch.nn.Module):
         return torch.sum(torch.square(x), dim=list(range(1, len(x.shape))))
 
 
+class _SquaredErrorMean(torch.autograd.Function):
+    """mean over rows of the summed squares as ONE reduction kernel (``tpx_squared_error_mean``: warp-shuffle reduction, float64
+    accumulation) with a one-kernel adjoint, instead of torch's square / sum / mean launches and their autograd nodes."""
+
+    @staticmethod
+    def forward(ctx, r):
+        import ctypes
+        from . import _lib
+        r = r.contiguous()
+        acc = torch.zeros(1, dtype=torch.float64, device=r.device)
+        _lib.check(_lib.lib().tpx_squared_error_mean(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
+                                                     _lib.ptr(acc), _lib.stream_ptr()))
+        ctx.save_for_backward(r)
+        return acc.to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        from . import _lib
+        (r,) = ctx.saved_tensors
+        g = g.to(device=r.device, dtype=torch.float32).contiguous()
+        gr = torch.empty_like(r)
+        _lib.check(_lib.lib().tpx_squared_error_mean_backward(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
+                                                              _lib.ptr(g), _lib.ptr(gr), _lib.stream_ptr()))
+        return gr
+
+
+def _fusable_residual(r):
+    # (a 1-D residual is not a batch of rows for SquaredError: torch.sum(., dim=[]) reduces everything)
+    return (isinstance(r, torch.Tensor) and r.is_cuda and r.dtype == torch.float32 and r.dim() >= 2 and r.numel() > 0
+            and r.requires_grad)
+
+
 class Condition(torch.nn.Module):
     def __init__(self, name=None, weight=1.0, track_gradients=True):
         super().__init__()
@@ -82,8 +115,13 @@ class SingleModuleCondition(Condition):
             data[name] = self.data_functions[name](x_coordinates)
         with jets.scope(id(self)):
             y = self.module(x)
-            unreduced_loss = self.error_fn(self.residual_fn(
-                {**y.coordinates, **x_coordinates, **self.parameter.coordinates, **data}))
+            residual = self.residual_fn({**y.coordinates, **x_coordinates, **self.parameter.coordinates, **data})
+            # the PINN loss (SquaredError + mean, reference condition.py:11-27, 488-489) as one native reduction kernel;
+            # adaptive samplers need the per-point loss and keep the generic path
+            if (type(self.error_fn) is SquaredError and self.reduce_fn is torch.mean and not self.sampler.is_adaptive
+                    and _fusable_residual(residual)):
+                return _SquaredErrorMean.apply(residual)
+            unreduced_loss = self.error_fn(residual)
         if self.sampler.is_adaptive:
             self.last_unreduced_loss = unreduced_loss
         return self.reduce_fn(unreduced_loss)
@@ -182,7 +220,11 @@ class DeepONetSingleModuleCondition(Condition):
             input_dict = {**model_out.coordinates, **trunk_coordinates, **self.parameter.coordinates, **data_fn}
             if data is not None:
                 input_dict = {**input_dict, **data.coordinates}
-            unreduced_loss = self.error_fn(self.residual_fn(input_dict))
+            residual = self.residual_fn(input_dict)
+            if (type(self.error_fn) is SquaredError and self.reduce_fn is torch.mean
+                    and not self.trunk_points_sampler.is_adaptive and _fusable_residual(residual)):
+                return _SquaredErrorMean.apply(residual)      # mean over functions of the summed squares
+            unreduced_loss = self.error_fn(residual)
         if self.trunk_points_sampler.is_adaptive:
             self.last_unreduced_loss = unreduced_loss
         return self.reduce_fn(unreduced_loss)
