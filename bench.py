@@ -181,14 +181,24 @@ def run_native(args):
     saved_bytes = eng.saved_bytes(spec, N)
     saved = torch.empty(saved_bytes, dtype=torch.uint8, device=dev) if saved_bytes else None
 
+    import ctypes
+    from torchphysics_b200 import _lib
+    loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    glap_buf = torch.empty(N, 1, dtype=torch.float32, device=dev)
+
     def step_resident(i):
         """forward jet + residual + loss + reverse + flat gradient (+ all-reduce)."""
         x, f = xs[i % n_batches], fs[i % n_batches]
         packed = eng.packed(params)
         u, du, lap = eng.forward_raw(packed, x, spec, saved)
         r = lap + f
-        loss = torch.mean(r * r)
-        glap = r * (2.0 / N)
+        # loss = mean(r^2) and dLoss/dr = 2 r / N: the native reduction kernels of csrc/loss.cu (warp shuffles, float64 atomics)
+        loss_acc.zero_()
+        _lib.check(_lib.lib().tpx_squared_error_mean(_lib.ptr(r), ctypes.c_int64(N), ctypes.c_int64(N), _lib.ptr(loss_acc),
+                                                     _lib.stream_ptr()))
+        _lib.check(_lib.lib().tpx_squared_error_mean_backward(_lib.ptr(r), ctypes.c_int64(N), ctypes.c_int64(N), None,
+                                                              _lib.ptr(glap_buf), _lib.stream_ptr()))
+        loss, glap = loss_acc[0], glap_buf
         gacc = eng.backward_raw(packed, x, spec, None, None, glap, saved)
         grads = eng.unpack(gacc, params, skip_last_bias=True)
         off = 0
@@ -199,7 +209,7 @@ def run_native(args):
         flat[-1] = loss
         if world > 1:
             dist.all_reduce(flat)
-        launches["n"] += 3                                # fwd kernel, bwd kernel, unpack kernel
+        launches["n"] += 5                                # fwd kernel, loss + loss-adjoint kernels, bwd kernel, unpack kernel
         return loss
 
     def timed(fn, steps, warmup):
