@@ -1,5 +1,5 @@
 """Development aid: clock64 timeline of four consecutive steps of CTA 0 of the fused reverse kernel of the wide path
-(build with `make EXTRA=-DTPX_TIMELINE`).  usage: tcw_probe.py [N]"""
+(build with `make EXTRA=-DTPX_TIMELINE`).  usage: tcw_probe.py [N [S]]"""
 import ctypes
 import os
 import sys
@@ -13,14 +13,15 @@ from torchphysics_b200 import _lib  # noqa: E402
 from torchphysics_b200.engine import FcnEngine, JetSpec  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 5                # 5: config-2 streams (3 directions + Laplacian), 4: config 3
 torch.manual_seed(0)
-seq = ref_autograd.build_fcn(3, 1, (128, 128)).cuda()          # one hidden matrix: the stamps of l = 1 ... use 3 layers
-seq = ref_autograd.build_fcn(3, 1, (128,) * 3).cuda()
+d_in = 3 if S == 5 else 2
+seq = ref_autograd.build_fcn(d_in, 1, (128,) * 3).cuda()
 eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
-spec = JetSpec((0, 1, 2), (1.0, 1.0, 0.0))
-x = torch.rand(N, 3, device="cuda")
+spec = JetSpec((0, 1, 2), (1.0, 1.0, 0.0)) if S == 5 else JetSpec((0, 1), (1.0, 1.0))
+x = torch.rand(N, d_in, device="cuda")
 packed = eng.packed(eng.params())
-gdu = torch.randn(N, 1, 3, device="cuda")
+gdu = torch.randn(N, 1, spec.nd, device="cuda")
 glap = torch.randn(N, 1, device="cuda")
 saved = torch.empty(eng.saved_bytes(spec, N), dtype=torch.uint8, device="cuda")
 eng.forward_raw(packed, x, spec, saved)
