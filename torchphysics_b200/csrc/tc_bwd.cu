@@ -44,6 +44,11 @@ constexpr int B_EPI_WARPS = 4 * B_GROUPS;
 constexpr int B_THREADS = 32 * (B_EPI_WARPS + 1);
 constexpr uint32_t B_TMEM_COLS = 512;
 constexpr uint32_t T_D = 0, T_AH = 64, T_AL = 128, T_DW = 192;   // TMEM columns
+// The TMEM accumulators of dW round toward zero on every add (one ulp of the running sum): over the ~450 tiles of a CTA
+// at 2^21 points the sums came out ~1e-4 short (scripts/dw_scale_check.py).  Every FLUSH_TILES tiles the activation warps
+// move them into per-CTA fp32 partial sums in global memory (RED.ADD.F32, round to nearest) and the products restart from 0.
+constexpr int FLUSH_TILES = 16;
+constexpr int MAX_BWD_CTAS = 160;        // the partial sums are sized for this many CTAs (B200: 148 SMs)
 constexpr int MAXL = 6;                  // hidden layers supported (dW accumulators: 64 columns each, L - 1 <= 5)
 constexpr int MAXIO = 4;                 // d_in, d_out supported
 // dW accumulators: the hidden matrices processed first get N = 128 accumulators ([a_hi | a_lo] as ONE B operand, so the
@@ -86,6 +91,7 @@ struct BwdArgs {
   const float *gu, *gdu, *glap;
   double* gacc;
   const float* ckpt;   // per tile: L x 4 arrays x 64 x 32 floats
+  float* dwpart;       // per CTA: (MAXL - 1) x 64 x 64 fp32 partial sums of the hidden dW, [matrix][input neuron i][output neuron j]
   long long* dbg;      // development: timestamps of one tile
 };
 
@@ -126,6 +132,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   for (int v = tid; v < (int)lay.small(); v += B_THREADS) sm[so.small + v] = __ldg(a.img + v);
   for (int v = tid; v < ACC_TOTAL; v += B_THREADS) sm[so.acc + v] = 0.0f;
   for (int v = tid; v < 2 * 16384; v += B_THREADS) sm[so.zt + v] = 0.0f;     // K atoms of unused streams stay zero
+  float* dwp = a.dwpart + (size_t)blockIdx.x * ((MAXL - 1) * HP * HP);
+  for (int v = tid; v < (L - 1) * HP * HP; v += B_THREADS) dwp[v] = 0.0f;
   if (warp == B_EPI_WARPS) tmem_alloc(&tmem_slot, B_TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_a, B_EPI_WARPS);
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     __syncwarp();
     for (int64_t g = 0; g < total_phases; ++g) {
       const int l = (L - 1) - (int)(g % nphase);
-      const bool first_tile = g < nphase;
+      const bool first_tile = ((g / nphase) % FLUSH_TILES) == 0;   // the accumulators were flushed before this tile
       mbar_wait(&bar_a, ph_a);
       ph_a ^= 1;
 #ifdef TPX_TIMELINE
@@ -252,6 +260,26 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     }
     uint32_t ph_d = 0, ph_f = 0;
     bool dw_pending = false;             // a gradient product may still be reading Zt / At
+    bool flush_now = false;              // first step of a tile that follows FLUSH_TILES tiles of accumulation
+    int tcount = 0;
+    // this thread's slice of the hidden dW accumulators -> the CTA's fp32 partial sums (hi rows j and lo rows 64 + j of a
+    // matrix, and the a_lo columns 64 + i of a wide accumulator, all add into element (j, i))
+    auto flush_dw = [&]() {
+      const int j = (quad & 1) * 32 + lane;
+      for (int l = 1; l < L; ++l) {
+        const uint32_t tW = tmem + T_DW + dw_col(L, l) + lane_base;
+        float w[B_CH];
+        tmem_ld16(tW + jc, w);
+        if (dw_is_wide(L, l)) {
+          float w2[B_CH];
+          tmem_ld16(tW + HP + jc, w2);
+#pragma unroll
+          for (int i = 0; i < B_CH; ++i) w[i] += w2[i];
+        }
+#pragma unroll
+        for (int i = 0; i < B_CH; ++i) atomicAdd(dwp + ((size_t)(l - 1) * HP + jc + i) * HP + j, w[i]);
+      }
+    };
     // transposed operands: element (row = neuron, K = 32 s + lane); 128-byte swizzle:
     //   offset = s * atom + row * 32 + ((lane / 4) ^ (row % 8)) * 4 + lane % 4
     float* Zt = sm + so.zt + jn * 32 + (lane & 3);
@@ -388,6 +416,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         mbar_wait(&bar_f, ph_f);
         ph_f ^= 1;
       }
+      if (flush_now) {                   // every gradient product so far has completed; the next ones start from zero
+        fence_after();
+        flush_dw();
+        fence_before();
+        flush_now = false;
+      }
       TPX_STAMP(5);
 #pragma unroll
       for (int s = 0; s < S; ++s)
@@ -416,6 +450,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     };
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      flush_now = tcount > 0 && tcount % FLUSH_TILES == 0;
+      ++tcount;
       const int64_t gp = tile * TILE + lane;
       const bool valid = gp < a.n;
 #ifdef TPX_TIMELINE
@@ -539,6 +575,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     }
     // hidden matrices: rows j (hi, quadrants 0-1) and 64 + j (lo, quadrants 2-3) both add into dW[j][i]; a wide
     // accumulator also holds the a_lo products in columns 64 + i
+    __threadfence();                        // the reductions into the partial sums of every activation warp ...
+    named_bar_sync(15, 32 * B_EPI_WARPS);   // ... have been performed before anyone reads them back
     if (my_tiles > 0) {
       const int j = (quad & 1) * 32 + lane;
       for (int l = 1; l < L; ++l) {
@@ -554,7 +592,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 #pragma unroll
         for (int i = 0; i < B_CH; ++i) {
           const int col = jc + i;
-          if (j < HP32 && col < HP32) atomicAdd(a.gacc + lay32.w(l) + (size_t)j * HP32 + col, (double)w[i]);
+          const double part = (quad < 2) ? (double)__ldcg(dwp + ((size_t)(l - 1) * HP + col) * HP + j) : 0.0;   // added once
+          if (j < HP32 && col < HP32) atomicAdd(a.gacc + lay32.w(l) + (size_t)j * HP32 + col, (double)w[i] + part);
         }
       }
     }
@@ -580,12 +619,15 @@ static size_t ckpt_floats_per_tile(int L) { return (size_t)L * 4 * HP * TILE; }
 // workspace, then the reverse kernel; a chunk is 16 tiles per SM
 static int64_t chunk_tiles(int sm_count) { return (int64_t)sm_count * 16; }
 
+// behind the checkpoints: the per-CTA fp32 partial sums of the hidden dW
+static size_t dwpart_bytes() { return (size_t)MAX_BWD_CTAS * (MAXL - 1) * HP * HP * sizeof(float); }
+
 size_t tc_bwd_workspace_bytes(const tpx_fcn_desc* net, int sm_count) {
-  return (size_t)chunk_tiles(sm_count) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
+  return (size_t)chunk_tiles(sm_count) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float) + dwpart_bytes();
 }
 
 size_t tc_saved_bytes(const tpx_fcn_desc* net, int64_t n) {
-  return (size_t)((n + TILE - 1) / TILE) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
+  return (size_t)((n + TILE - 1) / TILE) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float) + dwpart_bytes();
 }
 
 template <int ND, int LAP>
@@ -593,7 +635,8 @@ static int launch_tc_bwd(const BwdArgs& a, int sm_count, cudaStream_t stream) {
   const size_t smem = (size_t)bwd_smem(a.lay).total * sizeof(float) + 1024;
   if (smem > 227 * 1024) return fail(TPX_E_UNSUPPORTED, "tc_bwd_kernel needs %zu bytes of shared memory", smem);
   const int64_t ntiles = (a.n + TILE - 1) / TILE;
-  const int64_t grid = sm_count < ntiles ? sm_count : ntiles;
+  int64_t grid = sm_count < ntiles ? sm_count : ntiles;
+  if (grid > MAX_BWD_CTAS) grid = MAX_BWD_CTAS;
   if (grid < 1) return 0;
   cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel: shared memory attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
@@ -626,13 +669,15 @@ int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet
   a.dbg = g_tc_debug;
   const size_t per_tile = ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
   if (saved) {
-    const size_t need = (size_t)((n + TILE - 1) / TILE) * per_tile;
+    const size_t need = (size_t)((n + TILE - 1) / TILE) * per_tile + dwpart_bytes();
     if (ckpt_bytes < need) return fail(TPX_E_WORKSPACE, "checkpoint buffer of %zu bytes is too small (%zu needed)", ckpt_bytes, need);
+    a.dwpart = (float*)((char*)ckpt + (need - dwpart_bytes()));
     a.x = x; a.n = n; a.gu = gu; a.gdu = gdu; a.glap = glap;
     return launch_tc_bwd_any(a, jet.nd, lap, sm_count, stream);
   }
   // no saved checkpoints: chunks of (forward kernel writing checkpoints only) + reverse kernel
-  const int64_t ctiles = (int64_t)(ckpt_bytes / per_tile);
+  const int64_t ctiles = ckpt_bytes > dwpart_bytes() ? (int64_t)((ckpt_bytes - dwpart_bytes()) / per_tile) : 0;
+  a.dwpart = (float*)((char*)ckpt + (size_t)ctiles * per_tile);
   if (ctiles < 1) return fail(TPX_E_WORKSPACE, "workspace of %zu bytes holds no tile (%zu bytes each)", ckpt_bytes, per_tile);
   const int64_t cpts = ctiles * TILE;
   const int d_in = net->d_in, d_out = net->d_out, nd = jet.nd;

@@ -52,6 +52,12 @@ constexpr int THREADS = 32 * (MMA_WARP + 1);
 constexpr int MAXD = 4;            // d_in supported by the layer-0 code
 constexpr int MAXO = 8;            // d_out supported by the output-layer kernels
 constexpr int FWD = 0, ADJ = 1;
+// The TMEM accumulator of dW rounds toward zero on every add (one ulp of the running sum): after thousands of steps of a
+// CTA the sum would be ~1e-4 short.  Every FLUSH steps the loader warps move it into a per-CTA fp32 array in global
+// memory (round-to-nearest fp32 reductions at L2, fire and forget; every element belongs to one thread) and the next
+// product starts from zero.
+constexpr int FLUSH = 64;
+constexpr int MAX_REV_CTAS = 160;   // per-CTA partial arrays are sized for this many CTAs (B200: 148 SMs)
 
 // tc::tanh_fast (ex2 + rcp + one Newton step, absolute error <= 3e-7).  The library tanhf gives the same parity
 // margins (measured: the error of these kernels comes from the accumulator's round-toward-zero adds, not from tanh)
@@ -107,6 +113,7 @@ struct WArgs {
   int part_out, part_in; // the product is one K block of a sum: write it raw to `part` / add `part` to it before the epilogue
   float* part;           // half-array of partial products
   int64_t half_stride;   // output kernels: floats between the half-arrays of one layer
+  float* dwpart;         // reverse kernel: per-CTA fp32 partial sums of dW, [CTA][input neuron i][output neuron j]
   long long* dbg;        // development (-DTPX_TIMELINE): clock64 stamps of steps 40..43 of CTA 0 of the reverse kernel
 };
 
@@ -826,7 +833,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
 #pragma unroll
         for (int ks = 0; ks < S; ++ks) {
           const uint32_t off = (uint32_t)(ks >> 2) * (HW * 128) + (ks & 3) * 32;
-          mma_tf32_ts(tmem + T_DW, tmem + T_ZL + ks * 8, desc_k_sw128(at_h + off), idesc_dw, (it > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32_ts(tmem + T_DW, tmem + T_ZL + ks * 8, desc_k_sw128(at_h + off), idesc_dw, (it % FLUSH != 0 || ks > 0) ? 1u : 0u);
           mma_tf32_ts(tmem + T_DW, tmem + T_ZH + ks * 8, desc_k_sw128(at_l + off), idesc_dw, 1);
         }
 #pragma unroll
@@ -847,6 +854,9 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     const int j = warp * 32 + lane;
     const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16);
     int it = 0;
+    float* dwp = a.dwpart + (size_t)blockIdx.x * (HW * HW) + j;     // element (i, j) at dwp[i * HW]: owned by this thread
+#pragma unroll 8
+    for (int c = 0; c < HW; ++c) dwp[c * HW] = 0.0f;
     // The rows of the next two steps are in flight (cp.async of a thread's OWN 8 S elements into a two-slot ring of raw
     // rows: nothing but the issuing thread reads them, so no barrier is involved): measured HBM latency under load is
     // ~3600 cycles, longer than a step, and a register prefetch of one step left the loader as the critical chain.
@@ -899,6 +909,16 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       if (it >= 1) mbar_wait_w(&bar_zfree, (it - 1) & 1);
       fence_after();
       TPX_WSTAMP(1, 3);
+      if (it > 0 && it % FLUSH == 0) {           // all gradient products so far have completed; the next one starts from zero
+#pragma unroll 1
+        for (int c = 0; c < HW / 16; ++c) {
+          float d[16];
+          tmem_ld16(tq + T_DW + c * 16, d);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) atomicAdd(dwp + (c * 16 + e) * HW, d[e]);   // RED.ADD.F32: no round trip
+        }
+        fence_before();
+      }
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         float hi[8], lo[8];
@@ -918,13 +938,14 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     }
     mbar_wait_w(&bar_done, 0);
     fence_after();
+    __threadfence();                             // this thread's own reductions into dwp have been performed at L2
     double* g = a.gacc + lay.w(l) + (size_t)(a.jb * HW + j) * lay.HP + a.kb * HW;
 #pragma unroll 1
     for (int c = 0; c < HW / 16; ++c) {
       float d[16];
       tmem_ld16(tq + T_DW + c * 16, d);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) atomicAdd(g + c * 16 + e, (double)d[e]);
+      for (int e = 0; e < 16; ++e) atomicAdd(g + c * 16 + e, (double)d[e] + (double)__ldcg(dwp + (c * 16 + e) * HW));
     }
   } else {
     // =========================== a_{l-1}^T producers + adjoint-jet epilogue: lane = input neuron i ===========================
@@ -1289,6 +1310,7 @@ struct Launch {
     const size_t per = per_floats(a.n), layer = (size_t)nblk * per;
     float* zb[2] = {saved + (size_t)(L - 1) * layer, saved + (size_t)L * layer};
     float* part = saved + (size_t)(L + 1) * layer;
+    a.dwpart = part + (nblk > 1 ? per : 0);
     static const int split = env_flag("TPX_TCW_SPLIT");      // development: separate dW / adjoint launches (width <= 128)
     int rc;
     for (int hb = 0; hb < nblk; ++hb) {
@@ -1334,7 +1356,8 @@ struct Launch {
             a.out = zb[cur ^ 1] + (size_t)ib * per;
             a.part = part; a.part_out = jb < nblk - 1; a.part_in = jb > 0;
             const int64_t nsub = (a.n + P - 1) / P * 2;
-            const unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
+            unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
+            if (g > MAX_REV_CTAS) g = MAX_REV_CTAS;
             if (l == 1) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
             else w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
             if ((rc = check("w_rev_kernel"))) return rc;
@@ -1371,7 +1394,7 @@ size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n) {
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
   const size_t nblk = wmax > HW ? 2 : 1;
   const size_t per = (size_t)((n + P - 1) / P) * (size_t)((1 + nd + lap) * P) * HW * sizeof(float);
-  return ((size_t)(net->n_hidden + 1) * nblk + (nblk > 1 ? 1 : 0)) * per;
+  return ((size_t)(net->n_hidden + 1) * nblk + (nblk > 1 ? 1 : 0)) * per + (size_t)MAX_REV_CTAS * HW * HW * sizeof(float);
 }
 
 #define TCW_DISPATCH(CALL)                                     \
