@@ -108,7 +108,8 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
 /* Activation-jet checkpoints.  When a forward evaluation is followed by loss.backward() on the same points
  * (the normal training step: condition.py:293-304 then solver.py:100-109), the forward kernel can save the
  * per-layer jets (8 KB per point for a 4x64 net; HBM is 180 GB) and the reverse kernel reads them instead of
- * re-running the forward sweep.  *bytes = 0 when this network / jet has no saving kernel.
+ * re-running the forward sweep.  *bytes = 0 when this network / jet has no saving kernel.  The size includes a
+ * fixed tail (<= 13 MB) of per-CTA fp32 partial sums the reverse kernels flush their TMEM dW accumulators into.
  * Hidden widths 65..256 (tanh, d_in <= 4, d_out <= 8) run on the layer-major tensor-core kernels
  * (csrc/tcw_kernels.cu); through this pair of calls their `saved` buffer holds the checkpoints of the
  * hidden layers 1..L-1 ([tile of 16 points][stream * 16 + point][128 neurons] fp32 per layer and 128-neuron
