@@ -47,7 +47,7 @@ constexpr uint32_t T_D = 0, T_AH = 64, T_AL = 128, T_DW = 192;   // TMEM columns
 // The TMEM accumulators of dW round toward zero on every add (one ulp of the running sum): over the ~450 tiles of a CTA
 // at 2^21 points the sums came out ~1e-4 short (scripts/dw_scale_check.py).  Every FLUSH_TILES tiles the activation warps
 // move them into per-CTA fp32 partial sums in global memory (RED.ADD.F32, round to nearest) and the products restart from 0.
-constexpr int FLUSH_TILES = 16;
+constexpr int FLUSH_TILES = 8;
 constexpr int MAX_BWD_CTAS = 160;        // the partial sums are sized for this many CTAs (B200: 148 SMs)
 constexpr int MAXL = 6;                  // hidden layers supported (dW accumulators: 64 columns each, L - 1 <= 5)
 constexpr int MAXIO = 4;                 // d_in, d_out supported
