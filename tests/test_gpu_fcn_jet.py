@@ -203,7 +203,7 @@ def test_linearity_of_reverse_at_scale():
     b = eng.backward_raw(packed, x[N // 3:].contiguous(), spec, None, None, g[N // 3:].contiguous())
     twice = eng.backward_raw(packed, x, spec, None, None, 2 * g)
     # random-sign adjoints are the worst case for a float32 sum over 2^20 points (the result is ~sqrt(N) while the summed
-    # magnitudes are ~N).  The TMEM accumulators of dW (round toward zero) are flushed every 16 tiles into round-to-nearest
+    # magnitudes are ~N).  The TMEM accumulators of dW (round toward zero) are flushed every 8 tiles into round-to-nearest
     # fp32 partial sums per CTA, float64 across CTAs: before that flush this deviation was ~1e-4
     den = full.abs().max()
     assert ((a + b - full).abs().max() / den) < 2e-5
