@@ -743,9 +743,10 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     mbar_init_fence();
   }
   // padding rows of Zn (hi and lo) are zero for the whole launch
-  if (NP > NS) {
-    for (int v = tid; v < ZSTAGES * 2 * (NP - NS) * HW; v += THREADS) {
-      const int part = v / ((NP - NS) * HW), e = v % ((NP - NS) * HW);
+  if constexpr (NP > NS) {
+    constexpr int PADF = (NP - NS) * HW;       // floats of the padding rows of one hi (or lo) part
+    for (int v = tid; v < ZSTAGES * 2 * PADF; v += THREADS) {
+      const int part = v / PADF, e = v % PADF;
       sm[part * ZN + swz128(NS + e / HW, e % HW, NP)] = 0.0f;
     }
   }
