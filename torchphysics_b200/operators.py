@@ -132,7 +132,10 @@ def normal_derivative(model_out, normals, *derivative_variable):
 
 def convective(deriv_out, convective_field, *derivative_variable):
     j = jac(deriv_out, *derivative_variable)
-    return torch.bmm(j, convective_field.unsqueeze(dim=2)).squeeze(dim=2)
+    # (v . grad) u = J v per point (reference differentialoperators.py:320-342 uses torch.bmm: a batch of N tiny products that
+    # cuBLAS runs as ~16 launches per 2^20 points, forward and twice in backward: 4.8 ms of an 18.6 ms Navier-Stokes step);
+    # the same contraction as one broadcast multiply + sum over the last axis
+    return (j * convective_field.unsqueeze(dim=-2)).sum(dim=-1)
 
 
 def rot(model_out, *derivative_variable):
