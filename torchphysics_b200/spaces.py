@@ -284,7 +284,13 @@ class Points:
                     all_cols = list(range(self.dim))
                     for name in space:
                         cols += all_cols[sl[name]]
-                    idx[-1] = cols
+                    # a contiguous range of columns is a slice (a view whose backward is a slice too); a list is advanced
+                    # indexing, and its backward an index_put with accumulation: 1 ms of a 2.4 ms PI-DeepONet step for the
+                    # (256, 16384, 1) trunk points that FunctionSet._transform_locations selects by variable name
+                    if cols and cols == list(range(cols[0], cols[0] + len(cols))):
+                        idx[-1] = slice(cols[0], cols[0] + len(cols))
+                    else:
+                        idx[-1] = cols
             idx = tuple(idx)
         return idx, space
 
