@@ -115,13 +115,14 @@ def test_deep_ritz_condition(name, hidden):
         assert relerr(a, w) < TOL
 
 
-def test_solver_trains_poisson():
+@pytest.mark.parametrize("hidden", [(32,) * 3, (128,) * 3, (160, 256)])     # width-64, wide (1 block), wide (2 blocks) kernels
+def test_solver_trains_poisson(hidden):
     """a few Adam steps through Solver/Trainer reduce the PINN loss; steady state uses one
-    forward and one reverse launch per condition."""
+    forward and one reverse launch per condition (width <= 64) or one launch per hidden matrix block and direction."""
     import torchphysics_b200 as tp
     torch.manual_seed(0)
     X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
-    model = tp.models.FCN(X, U, hidden=(32,) * 3)
+    model = tp.models.FCN(X, U, hidden=hidden)
     sq = tp.domains.Parallelogram(X, [0, 0], [1, 0], [0, 1])
     f = lambda x: 2 * math.pi ** 2 * torch.sin(math.pi * x[:, :1]) * torch.sin(math.pi * x[:, 1:])
     pde = tp.conditions.PINNCondition(model, tp.samplers.RandomUniformSampler(sq, n_points=4096),
