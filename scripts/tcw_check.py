@@ -18,11 +18,15 @@ CASES = {
     "h": (2, 1, (256,) * 8, (0, 1), None, 150),
     "i": (3, 2, (200, 256, 130), (0, 1, 2), (1.0, 1.0, 0.0), 1000),
     "j": (2, 1, (256, 256), (0, 1), (1.0, 1.0), 5000),
+    "k": (2, 1, (128,) * 3, (0, 1), (1.0, 1.0), 1000, "sin"),
+    "l": (3, 2, (200, 256, 130), (0, 1, 2), (1.0, 1.0, 0.0), 1000, "sin"),
+    "m": (2, 1, (256,) * 3, (0, 1), (1.0, 0.5), 100, "sin"),
 }
 for name in (sys.argv[1:] or list(CASES)):
-    d_in, d_out, hidden, dcols, lap_w, N = CASES[name]
+    d_in, d_out, hidden, dcols, lap_w, N = CASES[name][:6]
+    act = CASES[name][6] if len(CASES[name]) > 6 else "tanh"
     torch.manual_seed(1234)
-    seq = ref_autograd.build_fcn(d_in, d_out, hidden, "tanh")
+    seq = ref_autograd.build_fcn(d_in, d_out, hidden, act)
     params = [p.detach().numpy() for p in ref_autograd.linear_params(seq)]
     rng = np.random.default_rng(5)
     x = rng.uniform(-1, 1, size=(N, d_in)).astype(np.float32)
@@ -30,12 +34,12 @@ for name in (sys.argv[1:] or list(CASES)):
     gu = rng.standard_normal((N, d_out)).astype(np.float32)
     gdu = rng.standard_normal((N, d_out, nd)).astype(np.float32) if nd else None
     glap = rng.standard_normal((N, d_out)).astype(np.float32) if lap_w is not None else None
-    u, du, lap, grads = _run(params, "tanh", x, dcols, lap_w, gu=gu, gdu=gdu, glap=glap)
+    u, du, lap, grads = _run(params, act, x, dcols, lap_w, gu=gu, gdu=gdu, glap=glap)
     c = np.zeros(d_in)
     if lap_w is not None:
         for col, w in zip(dcols, lap_w):
             c[col] = w
-    ou, odu, olap = jet_numpy.jet_forward(params, x, c if lap_w is not None else None, "tanh")
+    ou, odu, olap = jet_numpy.jet_forward(params, x, c if lap_w is not None else None, act)
     msg = [f"u {relerr(u, ou):.2e}"]
     if nd:
         msg.append(f"du {relerr(du, odu[:, :, list(dcols)]):.2e}")
@@ -44,6 +48,6 @@ for name in (sys.argv[1:] or list(CASES)):
     full_gdu = np.zeros((N, d_out, d_in))
     if nd:
         full_gdu[:, :, list(dcols)] = gdu
-    og = jet_numpy.jet_backward(params, x, gu, full_gdu, glap, c if lap_w is not None else None, "tanh")
+    og = jet_numpy.jet_backward(params, x, gu, full_gdu, glap, c if lap_w is not None else None, act)
     msg.append("grads " + " ".join(f"{relerr(g, w):.1e}" for g, w in zip(grads, og)))
-    print(name, hidden, "S", 1 + nd + (lap_w is not None), "|", " ".join(msg), flush=True)
+    print(name, act, hidden, "S", 1 + nd + (lap_w is not None), "|", " ".join(msg), flush=True)

@@ -251,7 +251,7 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
     return 0;
   }
   if (saved && tcw_supported(net, jet->nd, a.lap))     // the launcher recorded the message
-    return tcw_forward(a.lay, a.jet, a.lap, packed, x, n, u, du, lap, saved, a.sm_count, a.stream);
+    return (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(a.lay, a.jet, a.lap, packed, x, n, u, du, lap, saved, a.sm_count, a.stream);
   switch (a.lay.HP) {
     case 32: rc = launch_fwd<32>(a); break;
     case 64: rc = launch_fwd<64>(a); break;
@@ -300,7 +300,7 @@ int tpx_fcn_jet_forward_ws(const tpx_fcn_desc* net, const tpx_jet_desc* jet, con
   const int d_in = net->d_in, d_out = net->d_out, nd = jet->nd;
   for (int64_t p0 = 0; p0 < n; p0 += cpts) {
     const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
-    rc = tcw_forward(lay, ja, lp, packed, x + p0 * d_in, m, u + p0 * d_out, du ? du + p0 * d_out * nd : nullptr,
+    rc = (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(lay, ja, lp, packed, x + p0 * d_in, m, u + p0 * d_out, du ? du + p0 * d_out * nd : nullptr,
                      lap ? lap + p0 * d_out : nullptr, (float*)workspace, sms, (cudaStream_t)stream);
     if (rc) return rc;
   }
@@ -376,7 +376,7 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
     if (!tcw_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel that reads saved checkpoints");
     const size_t need = tcw_saved_bytes(net, jet->nd, a.lap, n);
     if (workspace_bytes < need) return fail(TPX_E_WORKSPACE, "saved buffer of %zu bytes < %zu", workspace_bytes, need);
-    return tcw_backward(a.lay, a.jet, a.lap, packed, x, n, a.gu, a.gdu, a.glap, grad_acc, (float*)workspace, a.sm_count, a.stream);
+    return (net->activation == TPX_ACT_SIN ? tcws_backward : tcw_backward)(a.lay, a.jet, a.lap, packed, x, n, a.gu, a.gdu, a.glap, grad_acc, (float*)workspace, a.sm_count, a.stream);
   }
   if (tc_bwd_supported(net, jet->nd, a.lap)) {
     rc = tc_backward(net, a.lay, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
@@ -391,9 +391,9 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
       const int d_in = net->d_in, d_out = net->d_out, nd = jet->nd;
       for (int64_t p0 = 0; p0 < n; p0 += cpts) {
         const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
-        rc = tcw_forward(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, nullptr, nullptr, nullptr, (float*)workspace, a.sm_count, a.stream);
+        rc = (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, nullptr, nullptr, nullptr, (float*)workspace, a.sm_count, a.stream);
         if (rc) return rc;
-        rc = tcw_backward(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, a.gu ? a.gu + p0 * d_out : nullptr,
+        rc = (net->activation == TPX_ACT_SIN ? tcws_backward : tcw_backward)(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, a.gu ? a.gu + p0 * d_out : nullptr,
                           a.gdu ? a.gdu + p0 * d_out * nd : nullptr, a.glap ? a.glap + p0 * d_out : nullptr, grad_acc,
                           (float*)workspace, a.sm_count, a.stream);
         if (rc) return rc;

@@ -28,5 +28,11 @@ int tcw_forward(const Layout& lay, const JetArgs& jet, int lap, const float* pac
 int tcw_backward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
                  const float* gu, const float* gdu, const float* glap, double* gacc, float* saved, int sm_count,
                  cudaStream_t stream);
+// the same for the sin activation (tcw_sin.cu)
+int tcws_forward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
+                 float* u, float* du, float* lapo, float* saved, int sm_count, cudaStream_t stream);
+int tcws_backward(const Layout& lay, const JetArgs& jet, int lap, const float* packed, const float* x, int64_t n,
+                  const float* gu, const float* gdu, const float* glap, double* gacc, float* saved, int sm_count,
+                  cudaStream_t stream);
 extern long long* g_tc_debug;   // development: device buffer of >= 512 int64 timestamps, or NULL
 }  // namespace tpx

@@ -38,8 +38,16 @@
 #include "tc_kernels.h"
 #include "tpx_internal.h"
 
+// This file is compiled twice: as it is for tanh (namespace tcw, entry points tcw_*) and from tcw_sin.cu with
+// TCW_ACT_SIN defined for tp.models.Sinus (namespace tcws, entry points tcws_*).
+#ifdef TCW_ACT_SIN
+#define TCW_NS tcws
+#else
+#define TCW_NS tcw
+#endif
+
 namespace tpx {
-namespace tcw {
+namespace TCW_NS {
 
 using namespace tc;
 
@@ -66,6 +74,25 @@ constexpr int MAX_REV_CTAS = 160;   // per-CTA partial arrays are sized for this
 __device__ __forceinline__ float tanh_w(float x) { return tanhf(x); }
 #else
 __device__ __forceinline__ float tanh_w(float x) { return tanh_fast(x); }
+#endif
+
+// What the value stream of a checkpoint keeps, and the activation with its first two (three) derivatives from it: tanh keeps
+// t = tanh z (every derivative is a polynomial in t), sin keeps z (reference models/activation_fn.py:76-85).
+#ifdef TCW_ACT_SIN
+__device__ __forceinline__ float keep_of(float z) { return z; }
+__device__ __forceinline__ void act_derivs(float keep, float& s0, float& s1, float& s2) {
+  sincosf(keep, &s0, &s1);
+  s2 = -s0;
+}
+__device__ __forceinline__ float act_s3(float, float s1) { return -s1; }
+#else
+__device__ __forceinline__ float keep_of(float z) { return tanh_w(z); }
+__device__ __forceinline__ void act_derivs(float keep, float& s0, float& s1, float& s2) {
+  s0 = keep;
+  s1 = fmaf(-keep, keep, 1.0f);
+  s2 = -2.0f * keep * s1;
+}
+__device__ __forceinline__ float act_s3(float keep, float s1) { return -2.0f * s1 * fmaf(-3.0f * keep, keep, 1.0f); }
 #endif
 
 // mbarrier wait with a watchdog: a protocol error (or a fault in another role) traps after ~10 s instead of hanging the GPU
@@ -138,8 +165,9 @@ struct Layer0 {
 // checkpoint streams (t = tanh z, d_k z, L z) -> activation streams, in place
 template <int ND, int LAP>
 __device__ __forceinline__ void jets_from_ckpt(float (&v)[1 + ND + LAP], const float (&lapw)[ND > 0 ? ND : 1]) {
-  const float t = v[0];
-  const float s1 = fmaf(-t, t, 1.0f);
+  float s0, s1, s2;
+  act_derivs(v[0], s0, s1, s2);
+  v[0] = s0;
   float q = 0.0f;
 #pragma unroll
   for (int k = 0; k < ND; ++k) {
@@ -147,7 +175,7 @@ __device__ __forceinline__ void jets_from_ckpt(float (&v)[1 + ND + LAP], const f
     if (LAP) q = fmaf(lapw[k] * dz, dz, q);
     v[1 + k] = s1 * dz;
   }
-  if (LAP) v[ND + 1] = fmaf(-2.0f * t * s1, q, s1 * v[ND + 1]);
+  if (LAP) v[ND + 1] = fmaf(s2, q, s1 * v[ND + 1]);
 }
 
 // adjoint of the activation jets: hb = adjoints of the activation streams (in), ck = checkpoint streams;
@@ -155,9 +183,8 @@ __device__ __forceinline__ void jets_from_ckpt(float (&v)[1 + ND + LAP], const f
 template <int ND, int LAP>
 __device__ __forceinline__ void adjoint_jets(float (&hb)[1 + ND + LAP], const float (&ck)[1 + ND + LAP],
                                              const float (&lapw)[ND > 0 ? ND : 1]) {
-  const float t = ck[0];
-  const float s1 = fmaf(-t, t, 1.0f);
-  const float s2 = -2.0f * t * s1;
+  float s0, s1, s2;
+  act_derivs(ck[0], s0, s1, s2);
   float dot = 0.0f, q = 0.0f;
 #pragma unroll
   for (int k = 0; k < ND; ++k) {
@@ -167,7 +194,7 @@ __device__ __forceinline__ void adjoint_jets(float (&hb)[1 + ND + LAP], const fl
   float zb = fmaf(hb[0], s1, dot * s2);
   if (LAP) {
     const float lhb = hb[ND + 1];
-    const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
+    const float s3 = act_s3(ck[0], s1);
     zb = fmaf(lhb, fmaf(s3, q, s2 * ck[ND + 1]), zb);
 #pragma unroll
     for (int k = 0; k < ND; ++k) hb[1 + k] = fmaf(hb[1 + k], s1, 2.0f * lhb * s2 * lapw[k] * ck[1 + k]);
@@ -321,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
               for (int c = 0; c < MAXD; ++c)
                 if (c < l0.d_in) z = fmaf(l0.w[c], __ldg(a.x + gp * l0.d_in + c), z);
             }
-            v[pp][0] = tanh_w(z);
+            v[pp][0] = keep_of(z);
 #pragma unroll
             for (int k = 0; k < ND; ++k) v[pp][1 + k] = dz0[k];
             if (LAP) v[pp][S - 1] = 0.0f;
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
           }
           if (s == 0 && !part_out) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) d[p] = tanh_w(d[p] + bias);
+            for (int p = 0; p < P; ++p) d[p] = keep_of(d[p] + bias);
           }
 #pragma unroll
           for (int p = 0; p < P; ++p) __stcs(dst + (size_t)(s * P + p) * HW, d[p]);
@@ -449,7 +476,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
               xr[pp][c] = (gp < a.n && c < l0.d_in) ? __ldg(a.x + gp * l0.d_in + c) : 0.0f;
               z = fmaf(l0.w[c], xr[pp][c], z);
             }
-            ck[pp][0] = tanh_w(z);
+            ck[pp][0] = keep_of(z);
 #pragma unroll
             for (int k = 0; k < ND; ++k) ck[pp][1 + k] = dz0[k];
             if (LAP) ck[pp][S - 1] = 0.0f;
@@ -602,7 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_dw_kernel(WArgs a) {
             for (int c = 0; c < MAXD; ++c)
               if (c < l0.d_in) z = fmaf(l0.w[c], __ldg(a.x + gp * l0.d_in + c), z);
           }
-          v[pp][0] = tanh_w(z);
+          v[pp][0] = keep_of(z);
 #pragma unroll
           for (int k = 0; k < ND; ++k) v[pp][1 + k] = dz0[k];
           if (LAP) v[pp][S - 1] = 0.0f;
@@ -980,7 +1007,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
             xr[pp][c] = (gp < a.n && c < l0.d_in) ? __ldg(a.x + gp * l0.d_in + c) : 0.0f;
             z = fmaf(l0.w[c], xr[pp][c], z);
           }
-          ck[pp][0] = tanh_w(z);
+          ck[pp][0] = keep_of(z);
 #pragma unroll
           for (int k = 0; k < ND; ++k) ck[pp][1 + k] = dz0[k];
           if (LAP) ck[pp][S - 1] = 0.0f;
@@ -1370,14 +1397,18 @@ struct Launch {
   }
 };
 
-}  // namespace tcw
+}  // namespace TCW_NS
 
-using namespace tcw;
+using namespace TCW_NS;
 
+#ifdef TCW_ACT_SIN
+#define tcw_forward tcws_forward
+#define tcw_backward tcws_backward
+#else
 bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   static const int disabled = tcw::env_flag("TPX_DISABLE_TCW");
   if (disabled) return false;
-  if (net->activation != TPX_ACT_TANH) return false;
+  if (net->activation != TPX_ACT_TANH && net->activation != TPX_ACT_SIN) return false;
   if (net->n_hidden < 2) return false;
   int wmax = 0;
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
@@ -1397,6 +1428,8 @@ size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n) {
   const size_t per = (size_t)((n + P - 1) / P) * (size_t)((1 + nd + lap) * P) * HW * sizeof(float);
   return ((size_t)(net->n_hidden + 1) * nblk + (nblk > 1 ? 1 : 0)) * per + (size_t)MAX_REV_CTAS * HW * HW * sizeof(float);
 }
+
+#endif  // !TCW_ACT_SIN
 
 #define TCW_DISPATCH(CALL)                                     \
   switch (jet.nd * 2 + lap) {                                  \
