@@ -142,7 +142,10 @@ CASES = [
     (3, 2, (200, 256, 130), "tanh", (0, 1, 2), (1.0, 1.0, 0.0), 1000),
     (2, 1, (256, 256), "tanh", (0, 1), (1.0, 1.0), 5000),
     (2, 3, (129,) * 4, "tanh", (1,), None, 333),
-    # tp.models.Sinus on the wide path (csrc/tcw_sin.cu)
+    # tp.models.Sinus on the width-64 tensor-core kernels (ACT = 1 instantiations) ...
+    (2, 2, (64,) * 3, "sin", (0, 1), (1.0, 1.0), 999),
+    (3, 1, (20, 50, 30), "sin", (2,), None, 130),
+    # ... and on the wide path (csrc/tcw_sin.cu)
     (2, 1, (128,) * 3, "sin", (0, 1), (1.0, 1.0), 1000),
     (3, 2, (200, 256, 130), "sin", (0, 1, 2), (1.0, 1.0, 0.0), 1000),
 ]

@@ -114,7 +114,7 @@ __device__ __forceinline__ void bulk_load(float* dst_smem, const float* src, uin
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int ND, int LAP>
+template <int ND, int LAP, int ACT>       // ACT: 0 = tanh (checkpoint keeps t = tanh z), 1 = sin (keeps z)
 __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
@@ -300,8 +300,15 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     auto jets = [&](const float (&c)[S][B_NW], float (&h)[S][B_NW]) {
 #pragma unroll
       for (int i = 0; i < B_NW; ++i) {
-        const float t = c[0][i];
-        const float s1 = fmaf(-t, t, 1.0f);
+        float t, s1, s2;
+        if constexpr (ACT == 0) {
+          t = c[0][i];
+          s1 = fmaf(-t, t, 1.0f);
+          s2 = -2.0f * t * s1;
+        } else {
+          sincosf(c[0][i], &t, &s1);
+          s2 = -t;
+        }
         h[0][i] = t;
         float qq = 0.0f;
 #pragma unroll
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
           if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
           h[1 + k][i] = s1 * dz;
         }
-        if (LAP) h[S - 1][i] = fmaf(-2.0f * t * s1, qq, s1 * c[S - 1][i]);
+        if (LAP) h[S - 1][i] = fmaf(s2, qq, s1 * c[S - 1][i]);
       }
     };
     auto load_ck = [&](const float* ck_tile, int l, float (&c)[S][B_NW]) {
@@ -325,8 +332,15 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     auto zbar = [&](const float (&c)[S][B_NW], const float (&ga)[S][B_NW], float (&zb)[S][B_NW]) {
 #pragma unroll
       for (int i = 0; i < B_NW; ++i) {
-        const float t = c[0][i];
-        const float s1 = fmaf(-t, t, 1.0f), s2 = -2.0f * t * s1;
+        float t, s1, s2;
+        if constexpr (ACT == 0) {
+          t = c[0][i];
+          s1 = fmaf(-t, t, 1.0f);
+          s2 = -2.0f * t * s1;
+        } else {
+          sincosf(c[0][i], &t, &s1);
+          s2 = -t;
+        }
         float v0 = ga[0][i] * s1, qq = 0.0f;
         const float gl = LAP ? ga[S - 1][i] : 0.0f;
 #pragma unroll
@@ -341,7 +355,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
           zb[1 + k][i] = vk;
         }
         if (LAP) {
-          const float s3 = -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f);
+          const float s3 = (ACT == 0) ? -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f) : -s1;
           v0 = fmaf(gl, fmaf(s3, qq, s2 * c[S - 1][i]), v0);
           zb[S - 1][i] = gl * s1;
         }
@@ -630,20 +644,26 @@ size_t tc_saved_bytes(const tpx_fcn_desc* net, int64_t n) {
   return (size_t)((n + TILE - 1) / TILE) * ckpt_floats_per_tile(net->n_hidden) * sizeof(float) + dwpart_bytes();
 }
 
-template <int ND, int LAP>
-static int launch_tc_bwd(const BwdArgs& a, int sm_count, cudaStream_t stream) {
+template <int ND, int LAP, int ACT>
+static int launch_tc_bwd_act(const BwdArgs& a, int sm_count, cudaStream_t stream) {
   const size_t smem = (size_t)bwd_smem(a.lay).total * sizeof(float) + 1024;
   if (smem > 227 * 1024) return fail(TPX_E_UNSUPPORTED, "tc_bwd_kernel needs %zu bytes of shared memory", smem);
   const int64_t ntiles = (a.n + TILE - 1) / TILE;
   int64_t grid = sm_count < ntiles ? sm_count : ntiles;
   if (grid > MAX_BWD_CTAS) grid = MAX_BWD_CTAS;
   if (grid < 1) return 0;
-  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tc_bwd_kernel<ND, LAP, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel: shared memory attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-  tc_bwd_kernel<ND, LAP><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
+  tc_bwd_kernel<ND, LAP, ACT><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel launch (%lld CTAs x %d threads, %zu bytes smem): %s", (long long)grid, B_THREADS, smem, cudaGetErrorString(e));
   return 0;
+}
+
+static thread_local int g_bwd_act = TPX_ACT_TANH;      // activation of the network being launched (set by tc_backward)
+template <int ND, int LAP>
+static int launch_tc_bwd(const BwdArgs& a, int sm_count, cudaStream_t stream) {
+  return g_bwd_act == TPX_ACT_SIN ? launch_tc_bwd_act<ND, LAP, 1>(a, sm_count, stream) : launch_tc_bwd_act<ND, LAP, 0>(a, sm_count, stream);
 }
 
 static int launch_tc_bwd_any(const BwdArgs& a, int nd, int lap, int sm_count, cudaStream_t stream) {
@@ -667,6 +687,7 @@ int tc_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet
   a.jet = jet;
   a.img = img; a.gacc = gacc; a.ckpt = ckpt;
   a.dbg = g_tc_debug;
+  g_bwd_act = net->activation;
   const size_t per_tile = ckpt_floats_per_tile(net->n_hidden) * sizeof(float);
   if (saved) {
     const size_t need = (size_t)((n + TILE - 1) / TILE) * per_tile + dwpart_bytes();

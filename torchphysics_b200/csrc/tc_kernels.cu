@@ -119,7 +119,7 @@ struct FwdArgs {
   long long* dbg;   // development: clock64 stamps of one tile (scripts/tc_probe.py N dbgf)
 };
 
-template <int ND, int LAP>
+template <int ND, int LAP, int ACT>       // ACT: 0 = tanh, 1 = sin (tp.models.Sinus; the checkpoint then keeps z instead of tanh z)
 __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
@@ -308,10 +308,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
         float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (4 * HP * TILE) + jw * TILE + lane : nullptr;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float t = tanh_fast(z[0][i]);
-          const float s1 = fmaf(-t, t, 1.0f);
+          float t, s1, s2, keep;           // activation, its first two derivatives, what the reverse sweep keeps
+          if constexpr (ACT == 0) {
+            t = tanh_fast(z[0][i]);
+            s1 = fmaf(-t, t, 1.0f);
+            s2 = -2.0f * t * s1;
+            keep = t;
+          } else {
+            keep = z[0][i];
+            sincosf(keep, &t, &s1);
+            s2 = -t;
+          }
           z[0][i] = t;
-          if (ckl) __stcs(ckl + (0 * HP + i) * TILE, t);
+          if (ckl) __stcs(ckl + (0 * HP + i) * TILE, keep);
           float qq = 0.0f;
 #pragma unroll
           for (int k = 0; k < ND; ++k) {
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
           }
           if (LAP) {
             const float lz = z[S - 1][i];
-            z[S - 1][i] = fmaf(-2.0f * t * s1, qq, s1 * lz);
+            z[S - 1][i] = fmaf(s2, qq, s1 * lz);
             if (ckl) __stcs(ckl + ((S - 1) * HP + i) * TILE, lz);
           }
         }
@@ -416,7 +425,7 @@ long long* g_tc_debug = nullptr;
 bool tc_net_supported(const tpx_fcn_desc* net) {
   static const int disabled = env_flag("TPX_DISABLE_TC");
   if (disabled) return false;
-  if (net->activation != TPX_ACT_TANH) return false;
+  if (net->activation != TPX_ACT_TANH && net->activation != TPX_ACT_SIN) return false;
   if (net->n_hidden < 2) return false;                 // needs at least one hidden x hidden product
   for (int l = 0; l < net->n_hidden; ++l)
     if (net->widths[l] > HP) return false;
@@ -454,18 +463,23 @@ int tc_pack(const tpx_fcn_desc* net, const void* const* params_host, float* img,
   return cudaGetLastError() == cudaSuccess ? 0 : TPX_E_CUDA;
 }
 
-template <int ND, int LAP>
-static int launch_tc_fwd(const FwdArgs& a, int sm_count, cudaStream_t stream) {
+template <int ND, int LAP, int ACT>
+static int launch_tc_fwd_act(const FwdArgs& a, int sm_count, cudaStream_t stream) {
   const FwdSmem so = fwd_smem(a.lay);
   const size_t smem = (size_t)so.total * sizeof(float) + 1024;
   if (smem > 227 * 1024) return TPX_E_UNSUPPORTED;
-  if (cudaFuncSetAttribute(tc_fwd_kernel<ND, LAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TPX_E_CUDA;
+  if (cudaFuncSetAttribute(tc_fwd_kernel<ND, LAP, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TPX_E_CUDA;
   const int64_t ntiles = (a.n + TILE - 1) / TILE, npairs = (ntiles + SLOTS - 1) / SLOTS;
   int64_t grid = sm_count;
   if (grid > npairs) grid = npairs;
   if (grid < 1) return 0;
-  tc_fwd_kernel<ND, LAP><<<(unsigned)grid, THREADS, smem, stream>>>(a);
+  tc_fwd_kernel<ND, LAP, ACT><<<(unsigned)grid, THREADS, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? 0 : TPX_E_CUDA;
+}
+static thread_local int g_fwd_act = TPX_ACT_TANH;      // activation of the network being launched (set by tc_forward)
+template <int ND, int LAP>
+static int launch_tc_fwd(const FwdArgs& a, int sm_count, cudaStream_t stream) {
+  return g_fwd_act == TPX_ACT_SIN ? launch_tc_fwd_act<ND, LAP, 1>(a, sm_count, stream) : launch_tc_fwd_act<ND, LAP, 0>(a, sm_count, stream);
 }
 
 int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float* img, const float* x, int64_t n,
@@ -476,6 +490,7 @@ int tc_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float
   a.img = img; a.x = x; a.n = n; a.u = u; a.du = du; a.lap = lapo;
   a.ckpt = saved;
   a.dbg = g_tc_debug;
+  g_fwd_act = net->activation;
   switch (jet.nd * 2 + lap) {
     case 0: return launch_tc_fwd<0, 0>(a, sm_count, stream);
     case 2: return launch_tc_fwd<1, 0>(a, sm_count, stream);
