@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05 / TMEM) forward-jet kernel for hidden width <= 64, tanh, <= 4 streams.
+// Tensor-core (tcgen05 / TMEM) forward-jet kernel for hidden width <= 64, tanh or sin, <= 4 streams.
 //
 // Work decomposition ("R32"): a tile is 32 collocation points.  The 128 rows of one UMMA are
 // (stream q, point p) = TMEM lane 32 q + p: every stream (value, d_k, Laplacian) of every point
