@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05 / TMEM) reverse kernel for hidden width <= 64, tanh, <= 4 streams.
+// Tensor-core (tcgen05 / TMEM) reverse kernel for hidden width <= 64, tanh or sin, <= 4 streams.
 //
 // It sweeps the layers of one 32-point tile backwards, reading the activation-jet checkpoints the forward
 // kernel saved (tc_kernels.cu: per tile and layer S arrays [64 neurons][32 points]: tanh(z), d_k z, L z).
