@@ -225,3 +225,31 @@ def test_constrained_evaluation_chain_rule_cpu():
     loss.backward()
     for lin, (w, b) in zip(lins, zip(G["dtheta"][0::2], G["dtheta"][1::2])):
         assert relerr(lin.weight.grad.numpy(), w) < 5e-6 and relerr(lin.bias.grad.numpy(), b) < 5e-6
+
+
+def test_points_column_selection_is_a_view_for_contiguous_names():
+    """Points[..., names]: a contiguous column range is a slice (a view: its backward is a slice, not an index_put with
+    accumulation), any other selection keeps advanced indexing; values as in the reference (points.py:150-215)."""
+    import torchphysics_b200 as tp
+    X, T, D = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("D")
+    t = torch.arange(24.0).reshape(2, 3, 4).requires_grad_(True)
+    p = tp.spaces.Points(t, X * T * D)
+    sub = p[..., ["x", "t"]]
+    assert sub.as_tensor.shape == (2, 3, 3) and sub.as_tensor._base is not None          # a view of t
+    assert torch.equal(sub.as_tensor, t[..., :3])
+    swapped = p[..., ["t", "x"]]                                                        # not a contiguous range of columns
+    assert torch.equal(swapped.as_tensor, t[..., [2, 0, 1]])
+    sub.as_tensor.sum().backward()
+    assert torch.equal(t.grad[..., :3], torch.ones(2, 3, 3)) and float(t.grad[..., 3].abs().sum()) == 0.0
+
+
+def test_convective_equals_batched_matrix_product():
+    """(v . grad) u as a broadcast multiply + sum equals the reference's torch.bmm(jac, v) (differentialoperators.py:320-342)."""
+    import torchphysics_b200 as tp
+    x = torch.rand(50, 2, requires_grad=True)
+    u = torch.stack([x[:, 0] ** 2 * x[:, 1], torch.sin(x[:, 0]) + x[:, 1] ** 3, x[:, 0] * x[:, 1]], dim=1)
+    v = torch.rand(50, 2)
+    got = tp.utils.convective(u, v, x)
+    j = tp.utils.jac(u, x)
+    want = torch.bmm(j, v.unsqueeze(2)).squeeze(2)
+    assert got.shape == (50, 3) and torch.allclose(got, want, rtol=1e-6, atol=1e-7)
