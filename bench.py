@@ -63,7 +63,7 @@ def cpu_reference_rate(steps, warmup, n_points):
         x = torch.rand(n_points, D_IN, generator=gen)
         t0 = time.perf_counter()
         out = ref_autograd.poisson_step(seq, x)
-        float(out["loss"])
+        float(out["loss"].detach())
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
