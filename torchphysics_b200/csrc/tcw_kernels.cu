@@ -1,4 +1,4 @@
-// Tensor-core (tcgen05 / TMEM) jet kernels for hidden widths 65..256 ("wide" path), tanh, <= 5 streams.
+// Tensor-core (tcgen05 / TMEM) jet kernels for hidden widths 65..256 ("wide" path), tanh or sin, <= 5 streams.
 // (Written for one 128-neuron block per layer; widths 129..256 run the same kernels on 128 x 128 blocks, see Launch.)
 //
 // Formulation: NEURONS ARE THE UMMA ROWS.  For a hidden matrix W (128 x 128, zero padded) and a tile of
@@ -6,7 +6,8 @@
 //     D[j][n] = sum_i W[j][i] B[n][i]          M = 128 (output neuron j), N = 16 S, K = 128 (input neuron i)
 //   * A = W lives in TMEM for the whole launch (hi | lo tf32 parts, 256 columns), so it costs no shared-memory
 //     bandwidth; B = the activation streams of the tile in shared memory (K-major, 128-byte swizzle, hi | lo);
-//     three tf32 products  W_hi B_hi + W_lo B_hi + W_hi B_lo  give fp32-grade accuracy (tc_common.cuh).
+//     three tf32 products  W_lo B_hi + W_hi B_lo + W_hi B_hi  (small ones first: the accumulator rounds toward zero) give
+//     fp32-grade accuracy (tc_common.cuh).
 //   * TMEM lane = neuron: the thread that reads row j of D owns ALL streams of ALL points of the tile for its
 //     neuron, so tanh, the jet formulas and their adjoints are thread-local -- no stream exchange through shared
 //     memory (the width-64 kernels, whose UMMA rows are (stream, point), need one per layer).
