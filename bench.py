@@ -310,9 +310,10 @@ def run_native(args):
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": kernel_name,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01e_tcbwd_raw.csv (4.313 GB for
-                         # 2^20 points: the 4 KB/point of saved activation jets + points + adjoints), scaled to this N
-                         "traffic": 4.313e9 * N / 2 ** 20, "traffic_unit": "bytes/launch",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of profiles/r01j_tc_raw.csv (4.342 GB for
+                         # 2^20 points: the 4 KB/point of saved activation jets + points + adjoints + the periodic
+                         # flush of the dW accumulators), scaled to this N
+                         "traffic": 4.342e9 * N / 2 ** 20, "traffic_unit": "bytes/launch",
                          "peak_source": peak_src,
                          "algorithmic_flop_per_point": 2 * F_FWD, "ms_per_launch": ms_bwd,
                          "forward_kernel_ms": ms_fwd,
