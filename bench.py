@@ -321,7 +321,7 @@ def run_native(args):
                          "note": "FLOP = algorithmic GEMM FLOP of SURVEY 8(d) (reverse = 2 x forward); the kernel "
                                  "issues 3 tf32 products per algorithmic product (4 for dW; fp32-accurate split) and tf32 "
                                  "runs at half the bf16 rate (1.10 PFLOP/s measured with scripts/umma_probe2.cu), so the "
-                                 "ceiling of frac is ~0.13.  ncu (profiles/r01e): tensor pipe active 25 %, shared-memory "
+                                 "ceiling of frac is ~0.13.  ncu (profiles/r01e, r01j): tensor pipe active 25 %, shared-memory "
                                  "LSU wavefronts 46 % of peak plus the UMMA operand reads of the gradient product "
                                  "(~180-240 KB/tile-layer; 496 KB per tile-layer in total = 3970 port cycles vs 4980 measured): the kernel is bound by shared-memory bandwidth (operand "
                                  "transposition for dW + stream exchange), HBM 1.6 TB/s of 6.5"},
