@@ -34,20 +34,23 @@ class _SquaredErrorMean(torch.autograd.Function):
         from . import _lib
         r = r.contiguous()
         acc = torch.zeros(1, dtype=torch.float64, device=r.device)
-        _lib.check(_lib.lib().tpx_squared_error_mean(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
-                                                     _lib.ptr(acc), _lib.stream_ptr()))
+        with torch.cuda.device(r.device):
+            _lib.check(_lib.lib().tpx_squared_error_mean(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
+                                                         _lib.ptr(acc), _lib.stream_ptr()))
         ctx.save_for_backward(r)
         return acc.to(torch.float32).reshape(())
 
     @staticmethod
+    @torch.autograd.function.once_differentiable      # raw-pointer adjoint: a double backward raises instead of returning zeros
     def backward(ctx, g):
         import ctypes
         from . import _lib
         (r,) = ctx.saved_tensors
         g = g.to(device=r.device, dtype=torch.float32).contiguous()
         gr = torch.empty_like(r)
-        _lib.check(_lib.lib().tpx_squared_error_mean_backward(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
-                                                              _lib.ptr(g), _lib.ptr(gr), _lib.stream_ptr()))
+        with torch.cuda.device(r.device):
+            _lib.check(_lib.lib().tpx_squared_error_mean_backward(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
+                                                                  _lib.ptr(g), _lib.ptr(gr), _lib.stream_ptr()))
         return gr
 
 

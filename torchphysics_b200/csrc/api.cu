@@ -153,6 +153,10 @@ __global__ void unpack_kernel(Layout lay, UnpackArgs ua, const double* __restric
 
 // the packed buffer is [FP32-kernel image | tensor-core image]; the second starts 1 KB aligned
 static size_t tc_image_offset(const Layout& lay) { return (lay.total() + 255) / 256 * 256; }
+// ... followed by the image of the points-as-lanes kernels (1 KB aligned as well)
+static size_t tcp_image_offset(const tpx_fcn_desc* net, const Layout& lay) {
+  return tc_image_offset(lay) + (tc_net_supported(net) ? (tc_packed_floats(net) + 255) / 256 * 256 : 0);
+}
 
 static void fill_dims(const tpx_fcn_desc* net, int* in_w, int* out_w) {
   for (int l = 0; l <= net->n_hidden; ++l) {
@@ -161,13 +165,13 @@ static void fill_dims(const tpx_fcn_desc* net, int* in_w, int* out_w) {
   }
 }
 
-static int sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+static int sm_count() {           // of the CURRENT device (cached per device: a process may drive several)
+  static int cached[64] = {0};
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  cached = n;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
   return n;
 }
 
@@ -192,7 +196,7 @@ int tpx_fcn_packed_floats(const tpx_fcn_desc* net, size_t* n_floats) {
   int rc = make_layout(net, &lay);
   if (rc) return rc;
   if (!n_floats) return fail(TPX_E_ARG, "n_floats is NULL");
-  *n_floats = tc_image_offset(lay) + (tc_net_supported(net) ? tc_packed_floats(net) : 0);
+  *n_floats = tcp_image_offset(net, lay) + (tcp_net_supported(net) ? tcp_packed_floats(net) : 0);
   return 0;
 }
 
@@ -216,6 +220,9 @@ int tpx_fcn_pack(const tpx_fcn_desc* net, const void* const* params_host, float*
   if (cudaGetLastError() != cudaSuccess) return cuda_fail("pack_kernel");
   if (tc_net_supported(net)) {
     if (tc_pack(net, params_host, packed + tc_image_offset(lay), (cudaStream_t)stream)) return cuda_fail("tc_pack");
+  }
+  if (tcp_net_supported(net)) {
+    if (tcp_pack(net, params_host, packed + tcp_image_offset(net, lay), (cudaStream_t)stream)) return cuda_fail("tcp_pack");
   }
   return 0;
 }
@@ -245,6 +252,13 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
   if (jet->lap && !lap) return fail(TPX_E_ARG, "lap is NULL but lap requested");
   a.packed = packed; a.x = x; a.n = n; a.u = u; a.du = du; a.lapo = lap;
   a.stream = (cudaStream_t)stream;
+  if (tcp_supported(net, jet->nd, a.lap) && (!saved || tcp_bwd_supported(net, jet->nd, a.lap))) {
+    float *ck = nullptr, *st = nullptr, *dw = nullptr;
+    if (saved) tcp_saved_split(net, jet->nd, a.lap, (n + 127) / 128, saved, &ck, &st, &dw);
+    rc = tcp_forward(net, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, u, du, lap, ck, st, a.sm_count, a.stream);
+    if (rc) return cuda_fail("tcp_fwd_kernel");
+    return 0;
+  }
   if (tc_supported(net, jet->nd, a.lap)) {
     rc = tc_forward(net, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, u, du, lap, saved, a.sm_count, a.stream);
     if (rc) return cuda_fail("tc_fwd_kernel");
@@ -288,7 +302,7 @@ int tpx_fcn_jet_forward_ws(const tpx_fcn_desc* net, const tpx_jet_desc* jet, con
   rc = check_jet(net, jet, &ja);
   if (rc) return rc;
   const int lp = jet->lap ? 1 : 0;
-  if (tc_supported(net, jet->nd, lp) || !tcw_supported(net, jet->nd, lp) || n <= 0)
+  if (tcp_supported(net, jet->nd, lp) || tc_supported(net, jet->nd, lp) || !tcw_supported(net, jet->nd, lp) || n <= 0)
     return jet_forward(net, jet, packed, x, n, u, du, lap, nullptr, stream);
   if (!packed || !x || !u || !workspace) return fail(TPX_E_ARG, "NULL pointer");
   if (jet->nd > 0 && !du) return fail(TPX_E_ARG, "du is NULL but nd > 0");
@@ -316,7 +330,8 @@ int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_
   if (rc) return rc;
   if (!bytes || n < 0) return fail(TPX_E_ARG, "bad argument");
   const int lap = jet->lap ? 1 : 0;
-  if (tc_bwd_supported(net, jet->nd, lap)) *bytes = tc_saved_bytes(net, n);
+  if (tcp_bwd_supported(net, jet->nd, lap)) *bytes = tcp_saved_bytes(net, jet->nd, lap, n);
+  else if (tc_bwd_supported(net, jet->nd, lap)) *bytes = tc_saved_bytes(net, n);
   else if (tcw_supported(net, jet->nd, lap)) *bytes = tcw_saved_bytes(net, jet->nd, lap, n);
   else *bytes = 0;
   return 0;
@@ -347,7 +362,10 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
     default: rc = TPX_E_UNSUPPORTED;
   }
   if (rc) return fail(rc, "no reverse kernel for HP=%d nd=%d lap=%d d_out=%d", a.lay.HP, jet->nd, jet->lap, a.lay.d_out);
-  if (tc_bwd_supported(net, jet->nd, a.lap)) {
+  if (tcp_bwd_supported(net, jet->nd, a.lap)) {
+    const size_t tcb = tcp_saved_bytes(net, jet->nd, a.lap, (int64_t)a.sm_count * 2 * 128);   // two tiles per SM: the chunk stays in L2
+    if (tcb > *bytes) *bytes = tcb;
+  } else if (tc_bwd_supported(net, jet->nd, a.lap)) {
     const size_t tcb = tc_bwd_workspace_bytes(net, a.sm_count);
     if (tcb > *bytes) *bytes = tcb;
   } else if (tcw_supported(net, jet->nd, a.lap)) {
@@ -372,6 +390,9 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   a.gu = gu; a.gdu = jet->nd > 0 ? gdu : nullptr; a.glap = jet->lap ? glap : nullptr;
   a.gacc = grad_acc; a.ckpt = (float*)workspace; a.ckpt_bytes = workspace_bytes;
   a.stream = (cudaStream_t)stream;
+  if (tcp_bwd_supported(net, jet->nd, a.lap))
+    return tcp_backward(net, a.lay, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
+                        (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);   // the launcher recorded the message
   if (saved && !tc_bwd_supported(net, jet->nd, a.lap)) {
     if (!tcw_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel that reads saved checkpoints");
     const size_t need = tcw_saved_bytes(net, jet->nd, a.lap, n);

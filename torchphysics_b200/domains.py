@@ -554,8 +554,12 @@ class CutDomain(_BooleanDomain):
             return super()._fill_random(out, col, n)
         # generator needs host composition (e.g. a Union): candidates from A, membership of B
         # and the compaction are still kernels; torch only gathers the kept rows.
-        filled, m = 0, n
+        filled, m, rounds = 0, n, 0
         while filled < n:
+            rounds += 1
+            if rounds > 20 or m > 2_000_000_000:      # same limits as Domain._fill_random: an empty cut must not grow until OOM
+                raise RuntimeError(f"rejection sampling of {type(self).__name__} found {filled} of {n} points after {rounds - 1} "
+                                   "rounds: is domain_a contained in domain_b?")
             cand = torch.zeros((int(m), out.shape[1]), dtype=torch.float32, device=out.device)
             self.domain_a._fill_random(cand, col, int(m))
             keep = ~self.domain_b._contains_rows(cand, col, out.device)

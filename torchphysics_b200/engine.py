@@ -109,9 +109,18 @@ class FcnEngine:
         return out
 
     def packed(self, params):
+        with torch.cuda.device(params[0].device):       # launches go to the stream of the tensors' device, not the current one
+            return self._packed_impl(params)
+
+    def _packed_impl(self, params):
         """Packed image of the current parameter values (re-packed when they changed)."""
+        # (data_ptr, version) identifies the VALUE of a module parameter (in-place optimizer updates bump the version; writes
+        # through ``.data`` do not and are not tracked).  A tensor that is not a leaf -- e.g. the first layer with a
+        # NormalizationLayer folded in, models.Sequential -- is a fresh temporary every call: its version is always 0 and the
+        # allocator may hand out the same address again, so such images are always re-packed.
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is None or key != self._packed_key or self._packed.device != params[0].device:
+        fresh = any(p.grad_fn is not None for p in params)
+        if fresh or self._packed is None or key != self._packed_key or self._packed.device != params[0].device:
             dev = params[0].device
             buf = torch.empty(self.packed_floats, dtype=torch.float32, device=dev)
             srcs = [p.detach().contiguous() for p in params]
@@ -144,6 +153,10 @@ class FcnEngine:
         return nbytes.value
 
     def forward_raw(self, packed, x, spec, saved=None):
+        with torch.cuda.device(x.device):
+            return self._forward_raw_impl(packed, x, spec, saved)
+
+    def _forward_raw_impl(self, packed, x, spec, saved=None):
         n = x.shape[0]
         u = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device)
         du = torch.empty((n, self.d_out, spec.nd), dtype=torch.float32, device=x.device) if spec.nd else None
@@ -170,6 +183,10 @@ class FcnEngine:
         return u, du, lap
 
     def backward_raw(self, packed, x, spec, gu, gdu, glap, saved=None):
+        with torch.cuda.device(x.device):
+            return self._backward_raw_impl(packed, x, spec, gu, gdu, glap, saved)
+
+    def _backward_raw_impl(self, packed, x, spec, gu, gdu, glap, saved=None):
         """returns the float64 packed gradient accumulator."""
         n = x.shape[0]
         gacc = torch.zeros(self.packed_floats, dtype=torch.float64, device=x.device)
@@ -188,6 +205,10 @@ class FcnEngine:
         return gacc
 
     def unpack(self, gacc, params, skip_last_bias=False):
+        with torch.cuda.device(gacc.device):
+            return self._unpack_impl(gacc, params, skip_last_bias)
+
+    def _unpack_impl(self, gacc, params, skip_last_bias=False):
         grads = [torch.empty_like(p, dtype=torch.float32) for p in params]
         if skip_last_bias:
             grads[-1] = None
@@ -277,6 +298,7 @@ class _FcnJetFn(torch.autograd.Function):
         return tuple(outs)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable      # raw-pointer adjoint: a double backward raises instead of returning zeros
     def backward(ctx, gu, gdu, glap):
         engine, spec = ctx.engine, ctx.spec
         needs = ctx.needs_input_grad[3:]

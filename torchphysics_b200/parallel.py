@@ -1,6 +1,8 @@
-"""Data parallelism over collocation points: every rank owns N/G points and a
-replica of the parameters; the ONLY exchange per step is one all-reduce of the flat
-parameter gradient with the scalar losses appended.  The reference has no distributed code
+"""Data parallelism over collocation points: every rank owns a replica of the parameters
+(broadcast from rank 0 when training starts) and draws ITS OWN batch of the samplers' n_points from its own
+Philox stream (weak scaling: the global batch is world_size x n_points; ``shard_count`` is the helper for
+callers that want a fixed global batch instead and size their samplers with it).  The ONLY exchange per step
+is one all-reduce of the flat parameter gradient with the scalar losses appended.  The reference has no distributed code
 (it would delegate to Lightning DDP, one bucketed all-reduce set per step)."""
 import torch
 import torch.distributed as dist
@@ -10,6 +12,25 @@ def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def broadcast_module_state(module, src=0):
+    """parameters and buffers of ``module`` take rank ``src``'s values on every rank (one flat broadcast per dtype)."""
+    rank, size = world()
+    if size == 1:
+        return
+    tensors = [t for t in list(module.parameters()) + list(module.buffers()) if t is not None and t.numel() > 0]
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault((t.dtype, t.device), []).append(t)
+    with torch.no_grad():
+        for group in by_dtype.values():
+            flat = torch.cat([t.detach().reshape(-1) for t in group])
+            dist.broadcast(flat, src=src)
+            off = 0
+            for t in group:
+                t.copy_(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
 
 
 class FlatGradAllReduce:

@@ -95,6 +95,10 @@ class Trainer:
         solver.to(self.device)
         solver._device = self.device
         solver.trainer = self
+        if size > 1:
+            # every replica starts from rank 0's weights (what Lightning DDP does for the reference); without this, ranks
+            # whose models were built under different seeds would apply the averaged gradient to diverging copies
+            parallel.broadcast_module_state(solver)
         configured = solver.configure_optimizers()
         schedulers = []
         if isinstance(configured, tuple) or isinstance(configured, list):
