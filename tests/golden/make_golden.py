@@ -440,6 +440,11 @@ if __name__ == "__main__":
         "ns_3x128": lambda: navier_stokes((128, 128, 128), 147, "ns_3x128"),
         # hidden width 256 (config 5 at reduced depth): two 128-neuron blocks per layer on the wide path
         "ritz_2x256": lambda: deep_ritz((256, 256), 139, "ritz_2x256"),
+        # BASELINE.json's configurations at full depth / the point count BASELINE.md section 3 names for the parity run
+        "poisson_4x64_10k": lambda: poisson((64, 64, 64, 64), 10000, "poisson_4x64_10k"),
+        "heat_6x128": lambda: heat((128,) * 6, 1000, "heat_6x128"),
+        "ns_6x128": lambda: navier_stokes((128,) * 6, 1000, "ns_6x128"),
+        "ritz_8x256": lambda: deep_ritz((256,) * 8, 500, "ritz_8x256"),
     }
     for job in (sys.argv[1:] or list(JOBS)):      # `make_golden.py NAME ...` regenerates only those fixtures
         JOBS[job]()

@@ -255,9 +255,7 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
   if (tcp_supported(net, jet->nd, a.lap) && (!saved || tcp_bwd_supported(net, jet->nd, a.lap))) {
     float *ck = nullptr, *st = nullptr, *dw = nullptr;
     if (saved) tcp_saved_split(net, jet->nd, a.lap, (n + 127) / 128, saved, &ck, &st, &dw);
-    rc = tcp_forward(net, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, u, du, lap, ck, st, a.sm_count, a.stream);
-    if (rc) return cuda_fail("tcp_fwd_kernel");
-    return 0;
+    return tcp_forward(net, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, u, du, lap, ck, st, a.sm_count, a.stream);
   }
   if (tc_supported(net, jet->nd, a.lap)) {
     rc = tc_forward(net, a.jet, a.lap, packed + tc_image_offset(a.lay), x, n, u, du, lap, saved, a.sm_count, a.stream);

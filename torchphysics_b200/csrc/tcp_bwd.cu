@@ -4,18 +4,20 @@
 // neurons 16 c .. 16 c + 15) + 1 MMA warp, one 128-point tile in flight.  It sweeps the layers of the tile backwards,
 // reading the checkpoints of tcp_fwd.cu ([layer][stream][64 neurons][128 points]: tanh z | z, d_k z, L z).
 //
-// Reverse step of hidden matrix l (L-1 >= l >= 1), one PASS per stream s (order: Laplacian, d_k ..., value):
+// Reverse step of hidden matrix l (L-1 >= l >= 1): two PASSES, A = streams S-1 .. 2 (Laplacian, d_2, d_3), B = streams 1, 0
+// (d_1, value).  Per pass
 //   activation warps   g_s = adjoint of a_{l,s} (TMEM, product of the previous step; top step: WL^T ubar, thread-local)
 //                      Zbar_{l,s} = adjoint jets(g, checkpoint_l),   a_{l-1,s} = jets(checkpoint_{l-1})
 //                      both scaled by powers of two, split hi / lo (fp16) and stored as 128-byte rows (row = point,
-//                      64 neurons, 128-byte swizzle) into one of two 64 KB staging regions  [Z_hi | Z_lo | A_hi | A_lo]
+//                      64 neurons, 128-byte swizzle) into a 64 KB staging region per stream  [Z_hi | Z_lo | A_hi | A_lo]
+//                      (a ring of three regions: the stores of a stream reuse the region of the stream three before it)
 //   MMA warp           adjoint   D_s[p][i] = sum_j Zbar_s[p][j] W_l[j][i]      A = the Z image (K-major), B = the image of
 //                                row-major W_l read MN-major -> TMEM block s of X, consumed by the next step
 //                      gradient  dW_l[j][i] += sum_p Zbar_s[p][j] a_s[p][i]    K = 128 points: A = [Z_hi ; Z_lo] read MN-major
-//                                (M = 128), B = A_hi, then A_lo (MN-major, N = 64) -> 64 TMEM columns per hidden matrix
-// The same Z image serves both products, and W needs no transposed copy.  A pass of stream s only waits for the adjoint
-// blocks it reads, so the tensor core (70 % busy) runs entirely behind the activation warps; the stores of pass n + 2
-// reuse the region of pass n.
+//                                (M = 128), B = A_lo, then A_hi (MN-major, N = 64) -> 64 TMEM columns per hidden matrix
+// The same Z image serves both products, and W needs no transposed copy.  The adjoint blocks are overwritten pass by pass,
+// so pass A leaves what pass B needs from it in registers (the Laplacian adjoint and the cross terms of the value stream).
+// W_l (16 KB) is fetched with cp.async.bulk behind the previous step.
 //
 // Scales (see tcp_common.cuh): the Z image of stream s carries 2^ez with ez from a bound of |Zbar_s| over the tile
 // (||W||_1 x the exact tile maximum of the stream one step above, measured lazily, pushed through the adjoint-jet formulas
@@ -37,25 +39,28 @@ constexpr int B_MAXL = 5;                 // hidden layers: (L - 1) x 64 accumul
 constexpr int FLUSH_TILES = 4;            // dW accumulators -> fp32 partial sums every 4 tiles (512 points)
 constexpr int MAX_BWD_CTAS = 160;
 constexpr uint32_t T_ACC = 256;           // TMEM column of the first dW accumulator
-constexpr int REGION = 65536;             // bytes of one staging region
+constexpr int REGION = 65536;             // bytes of one staging region (one stream)
+constexpr int NREG = 3;
 constexpr int IMG = 16384;                // bytes of one image (128 rows x 128 B)
 constexpr int BAR_TILE = 5, BAR_ALL = 6;
+constexpr int B_WARPS = 20;               // 16 activation warps, the MMA warp, 3 idle warps that complete its warpgroup
+constexpr int B_THREADS = 32 * B_WARPS;   // (setmaxnreg moves registers between whole warpgroups)
+constexpr int ACT_REGS = 104, MMA_REGS = 64;   // balanced: 4 x 128 x (104 - 96) registers taken = 128 x (96 - 64) released
 
 struct BwdSmem {
-  int wimg, stage, small, acc, mub, mzb, flags, total;   // byte offsets from the 1 KB aligned base
+  int stage, wimg, small, acc, mub, mzb, flags, total;   // byte offsets from the 1 KB aligned base
 };
-// shared accumulators per quadrant: [db: B_MAXL x 64][dW0: MAXIO x 64][dWL: MAXIO x 64]; then [dbL: 4 quads x MAXIO]
-constexpr int ACC_DB = 0, ACC_W0 = B_MAXL * HP, ACC_WL = ACC_W0 + MAXIO * HP, ACC_Q = ACC_WL + MAXIO * HP;
-constexpr int ACC_BL = 4 * ACC_Q, ACC_TOTAL = ACC_BL + 4 * MAXIO;
+// shared accumulators (fp32 atomics): [db: B_MAXL x 64][dW0: MAXIO x 64][dWL: MAXIO x 64][dbL: MAXIO]
+constexpr int ACC_DB = 0, ACC_W0 = B_MAXL * HP, ACC_WL = ACC_W0 + MAXIO * HP, ACC_BL = ACC_WL + MAXIO * HP, ACC_TOTAL = ACC_BL + MAXIO;
 __host__ __device__ inline BwdSmem bwd_smem(const Layout& lay) {
   BwdSmem s;
   s.stage = 0;
-  s.wimg = 2 * REGION;
-  s.small = s.wimg + (lay.L - 1) * 16384;
+  s.wimg = NREG * REGION;                 // ONE weight image (hi | lo): the matrix of the current step
+  s.small = s.wimg + 16384;
   s.acc = s.small + (int)lay.small() * 4;
   s.mub = s.acc + ACC_TOTAL * 4;          // [2 sets][4] tile maxima of |ubar_s|
   s.mzb = s.mub + 2 * 4 * 4;              // [2 sets][B_MAXL steps][4] tile maxima of |Zbar_s|
-  s.flags = s.mzb + 2 * B_MAXL * 4 * 4;   // [2 regions] accumulate flag of the pass's first gradient MMA
+  s.flags = s.mzb + 2 * B_MAXL * 4 * 4;   // [2 passes] accumulate flag of the pass's first gradient MMA
   s.total = s.flags + 16;
   return s;
 }
@@ -94,19 +99,30 @@ __device__ __forceinline__ float reduce8(const float (&v)[8], int lane) {
 __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// streams of pass P (0 = A, 1 = B), in processing order
+template <int S> __host__ __device__ constexpr int pass_count(int P) { return P == 0 ? (S > 2 ? S - 2 : 0) : (S < 2 ? S : 2); }
+template <int S> __host__ __device__ constexpr int pass_stream(int P, int u) { return P == 0 ? S - 1 - u : (S < 2 ? 0 : 1 - u); }
 
 template <int ND, int LAP, int ACT>
-__global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
+__global__ void __launch_bounds__(B_THREADS, 1) tcp_bwd_kernel(BwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_z[2], bar_f[2], bar_d[4];
+  __shared__ uint64_t bar_z[2], bar_f[NREG], bar_d[4], bar_w;
   __shared__ uint32_t tmem_slot;
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const Layout lay = a.lay;
-  const tpx::Layout lay32 = a.lay32;
   const BwdSmem so = bwd_smem(lay);
-  const int L = lay.L, d_in = lay.d_in, d_out = lay.d_out;
+  const int L = lay.L;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* small = reinterpret_cast<float*>(sm + so.small);
   float* accs = reinterpret_cast<float*>(sm + so.acc);
@@ -114,21 +130,17 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
   uint32_t* mzb = reinterpret_cast<uint32_t*>(sm + so.mzb);
   uint32_t* flags = reinterpret_cast<uint32_t*>(sm + so.flags);
 
-  {
-    const int nv = (L - 1) * 1024;
-    const float4* src = reinterpret_cast<const float4*>(a.img + lay.mat(1, 0));
-    float4* dst = reinterpret_cast<float4*>(sm + so.wimg);
-    for (int v = tid; v < nv; v += THREADS) dst[v] = __ldg(src + v);
-    for (int v = tid; v < (int)lay.small(); v += THREADS) small[v] = __ldg(a.img + v);
-    for (int v = tid; v < ACC_TOTAL; v += THREADS) accs[v] = 0.0f;
-    for (int v = tid; v < 2 * 4 + 2 * B_MAXL * 4 + 4; v += THREADS) mub[v] = 0u;     // mub, mzb, flags are contiguous
-  }
+  for (int v = tid; v < (int)lay.small(); v += B_THREADS) small[v] = __ldg(a.img + v);
+  for (int v = tid; v < ACC_TOTAL; v += B_THREADS) accs[v] = 0.0f;
+  for (int v = tid; v < 2 * 4 + 2 * B_MAXL * 4 + 4; v += B_THREADS) mub[v] = 0u;     // mub, mzb, flags are contiguous
   float* dwp = a.dwpart + (size_t)blockIdx.x * ((B_MAXL - 1) * HP * 128);
-  for (int v = tid; v < (L - 1) * HP * 128; v += THREADS) dwp[v] = 0.0f;
+  for (int v = tid; v < (L - 1) * HP * 128; v += B_THREADS) dwp[v] = 0.0f;
   if (warp == ACT_WARPS) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
-    for (int r = 0; r < 2; ++r) { mbar_init(&bar_z[r], ACT_WARPS); mbar_init(&bar_f[r], 1); }
+    for (int r = 0; r < 2; ++r) mbar_init(&bar_z[r], ACT_WARPS);
+    for (int r = 0; r < NREG; ++r) mbar_init(&bar_f[r], 1);
     for (int s = 0; s < 4; ++s) mbar_init(&bar_d[s], 1);
+    mbar_init(&bar_w, 1);
     mbar_init_fence();
   }
   fence_async_smem();
@@ -139,56 +151,95 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
   const int64_t ntiles = (a.n + TP - 1) / TP;
   const uint32_t stage0 = smem_u32(sm + so.stage);
 
-  if (warp == ACT_WARPS) {
-    // =========================== MMA issuer ===========================
-    const uint32_t wbase = smem_u32(sm + so.wimg);
-    constexpr uint32_t idesc_adj = idesc_f16(128, HP, 0, 1);
-    constexpr uint32_t idesc_dw = idesc_f16(128, HP, 1, 1);
-    uint32_t gp = 0;                          // global pass counter
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int l = L - 1; l >= 1; --l) {
-        const uint32_t wh = wbase + (uint32_t)(l - 1) * 16384u, wl = wh + 8192u;
-        const uint32_t tacc = tmem + T_ACC + (uint32_t)(l - 1) * 64u;
-#pragma unroll
-        for (int p = 0; p < S; ++p, ++gp) {
-          const int s = S - 1 - p;
-          const uint32_t r = gp & 1u;
-          mbar_wait(&bar_z[r], (gp >> 1) & 1u);
-          fence_after();
-          const uint32_t acc_flag = flags[r];
-          if (elect_one()) {
-            const uint32_t zh = stage0 + r * REGION, zl = zh + IMG, ah = zh + 2 * IMG, al = zh + 3 * IMG;
-            const uint32_t d = tmem + (uint32_t)s * 64u;
-#pragma unroll
-            for (int kc = 0; kc < 4; ++kc) {
-              const uint64_t bh = desc_sw128(wh + kc * 2048, 16384, 1024), bl = desc_sw128(wl + kc * 2048, 16384, 1024);
-              const uint64_t azh = desc_sw128(zh + kc * 32, 16, 1024), azl = desc_sw128(zl + kc * 32, 16, 1024);
-              mma_f16_ss(d, azl, bh, idesc_adj, kc > 0);
-              mma_f16_ss(d, azh, bl, idesc_adj, 1);
-              mma_f16_ss(d, azh, bh, idesc_adj, 1);
-            }
-            mma_commit(&bar_d[s]);
-#pragma unroll
-            for (int kp = 0; kp < 8; ++kp) {
-              const uint64_t za = desc_sw128(zh + kp * 2048, 16384, 1024);
-              mma_f16_ss(tacc, za, desc_sw128(al + kp * 2048, 16384, 1024), idesc_dw, (kp > 0) ? 1u : acc_flag);
-              mma_f16_ss(tacc, za, desc_sw128(ah + kp * 2048, 16384, 1024), idesc_dw, 1);
-            }
-            mma_commit(&bar_f[r]);
+  if (warp >= ACT_WARPS) {
+    reg_dec<MMA_REGS>();
+    if (warp == ACT_WARPS) {
+      // =========================== weight producer + MMA issuer ===========================
+      const uint32_t wimg = smem_u32(sm + so.wimg);
+      constexpr uint32_t idesc_adj = idesc_f16(128, HP, 0, 1);
+      constexpr uint32_t idesc_dw = idesc_f16(128, HP, 1, 1);
+      const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const int64_t total_steps = my_tiles * (L - 1);
+      uint32_t gs = 0, pp = 0, ph_w = 0, ph_last = 0;
+      constexpr int last_stream = 0;            // the adjoint product issued last in a step
+      if (total_steps > 0 && elect_one()) bulk_load(wimg, a.img + lay.mat(L - 1, 0), 16384u, &bar_w);
+      __syncwarp();
+      int64_t step_no = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tile + gridDim.x < ntiles && lane == 0) {     // the next tile's checkpoints on their way into L2
+          const float* nxt = a.ckpt + (size_t)(tile + gridDim.x) * ((size_t)(L - 1) * S * HP * TP);
+          for (int c = 0; c < (L - 1) * S; ++c) bulk_prefetch_l2(nxt + (size_t)c * HP * TP, HP * TP * 4);
+        }
+        for (int l = L - 1; l >= 1; --l, ++step_no) {
+          const uint32_t wh = wimg, wl = wimg + 8192u;
+          const uint32_t tacc = tmem + T_ACC + (uint32_t)(l - 1) * 64u;
+          if (L > 2 || step_no == 0) {
+            mbar_wait(&bar_w, ph_w);
+            ph_w ^= 1;
           }
-          __syncwarp();
+#pragma unroll
+          for (int P = 0; P < 2; ++P) {
+            const int np = pass_count<S>(P);
+            if (np == 0) continue;
+            mbar_wait(&bar_z[pp & 1u], (pp >> 1) & 1u);
+            fence_after();
+            const uint32_t acc_flag = flags[pp & 1u];
+            if (elect_one()) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (u >= np) continue;
+                const int s = pass_stream<S>(P, u);
+                const uint32_t r = (gs + u) % NREG;
+                const uint32_t zh = stage0 + r * REGION, zl = zh + IMG, ah = zh + 2 * IMG, al = zh + 3 * IMG;
+                const uint32_t d = tmem + (uint32_t)s * 64u;
+#pragma unroll
+                for (int kc = 0; kc < 4; ++kc) {
+                  const uint64_t bh = desc_sw128(wh + kc * 2048, 16384, 1024), bl = desc_sw128(wl + kc * 2048, 16384, 1024);
+                  const uint64_t azh = desc_sw128(zh + kc * 32, 16, 1024), azl = desc_sw128(zl + kc * 32, 16, 1024);
+                  mma_f16_ss(d, azl, bh, idesc_adj, kc > 0);
+                  mma_f16_ss(d, azh, bl, idesc_adj, 1);
+                  mma_f16_ss(d, azh, bh, idesc_adj, 1);
+                }
+                mma_commit(&bar_d[s]);
+#pragma unroll
+                for (int kp = 0; kp < 8; ++kp) {
+                  const uint64_t za = desc_sw128(zh + kp * 2048, 16384, 1024);
+                  mma_f16_ss(tacc, za, desc_sw128(al + kp * 2048, 16384, 1024), idesc_dw, (kp > 0 || u > 0) ? 1u : acc_flag);
+                  mma_f16_ss(tacc, za, desc_sw128(ah + kp * 2048, 16384, 1024), idesc_dw, 1);
+                }
+                mma_commit(&bar_f[r]);
+              }
+            }
+            __syncwarp();
+            gs += np;
+            ++pp;
+          }
+          // the weight image is free once the step's last adjoint product is done: fetch the next step's behind the
+          // activation warps' work (a single hidden matrix stays resident)
+          if (L > 2) {
+            mbar_wait(&bar_d[last_stream], ph_last);
+            ph_last ^= 1;
+            if (step_no + 1 < total_steps) {
+              const int ln = (l > 1) ? l - 1 : L - 1;
+              if (elect_one()) bulk_load(wimg, a.img + lay.mat(ln, 0), 16384u, &bar_w);
+              __syncwarp();
+            }
+          }
         }
       }
     }
   } else {
+    reg_inc<ACT_REGS>();
     // =========================== activation warps ===========================
+    const tpx::Layout lay32 = a.lay32;
+    const int d_in = lay.d_in, d_out = lay.d_out;
     const int quad = warp & 3, chunk = warp >> 2;
     const int j0 = chunk * CHN;
     const int prow = quad * 32 + lane;                       // row of this thread's point in the images
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    const float* W0 = small + lay.w0();
-    const float* WL = small + lay.wl();
-    float* acc = accs + quad * ACC_Q;
+    const float* W0 = small + lay.w0() + j0;
+    const float* WL = small + lay.wl() + j0;
+    const float* bias0 = small + lay.bias(0) + j0;
     float lapw[NDX];
     int dcol[NDX];
 #pragma unroll
@@ -196,19 +247,19 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
       lapw[k] = (LAP && k < ND) ? a.jet.lap_w[k] : 0.0f;
       dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
     }
-    uint32_t gp = 0;                          // global pass counter (same sequence as the MMA warp's)
+    uint32_t gs = 0, pp = 0;                  // stream-slot and pass counters (same sequence as the MMA warp's)
     uint32_t ph_d = 0;                        // bit s: parity of the next completion of bar_d[s] to wait for
     int tcount = 0;                           // tiles accumulated since the last periodic flush
-    // per hidden matrix l (bit / byte l): the accumulator holds products; real exponent of its scale; smallest exponent
+    // per hidden matrix l: the accumulator holds products (bit l of live); real exponent of its scale; smallest exponent
     // sum a stream of the previous tile allowed (all threads keep identical copies: every input of these is CTA-uniform)
     uint32_t live = 0;
     int epi[B_MAXL], emin_prev[B_MAXL];
 #pragma unroll
     for (int l = 0; l < B_MAXL; ++l) { epi[l] = 0; emin_prev[l] = 1 << 20; }
 
-    // all gradient MMAs issued so far have completed (the commit of a pass covers every earlier MMA)
+    // all gradient MMAs issued so far have completed (the commit of a stream covers every earlier MMA)
     auto drain_dw = [&]() {
-      if (gp >= 1) mbar_wait(&bar_f[(gp - 1) & 1u], (((gp - 1) >> 1)) & 1u);
+      if (gs >= 1) mbar_wait(&bar_f[(gs - 1) % NREG], ((gs - 1) / NREG) & 1u);
       fence_after();
     };
     // this thread's 16 columns x 1 lane of accumulator l -> the CTA's fp32 partial sums
@@ -241,15 +292,14 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           float m = 0.0f;
-#pragma unroll
-          for (int o = 0; o < MAXIO; ++o) {
+          for (int o = 0; o < d_out; ++o) {
             const float v = load_ub(s, o);
             m = fmaxf(m, fabsf(v));
             if (s == 0) {
               float sum = v;
 #pragma unroll
               for (int d = 16; d >= 1; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-              if (lane == 0 && o < d_out) accs[ACC_BL + quad * MAXIO + o] += sum;
+              if (lane == 0) atomicAdd(accs + ACC_BL + o, sum);
             }
           }
           m = warp_max_nonneg(m);
@@ -276,7 +326,6 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
         const bool top = (l == L - 1);
         const float* cku = ck_tile + (size_t)(l - 1) * S * HP * TP;                       // checkpoints of layer l
         const float* ckd = (l >= 2) ? ck_tile + (size_t)(l - 2) * S * HP * TP : nullptr;  // of layer l - 1 (layer 0: recomputed)
-        const float* bias0 = small + lay.bias(0) + j0;
         // exact tile maxima from the forward sweep
         float Mz[S], Ma[S];
         Ma[0] = 1.0f; Mz[0] = 0.0f;
@@ -294,193 +343,275 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
 #pragma unroll
         for (int q = 0; q < B_MAXL; ++q) { if (q == l) { my_epi = epi[q]; my_emin = emin_prev[q]; } }
         bool my_live = (live >> l) & 1u;
-        // held across the passes of this step (the adjoint blocks are overwritten pass by pass): the Laplacian block and
-        // everything the value stream's Zbar needs from the other streams
+        // held from pass A to pass B (the adjoint blocks are overwritten pass by pass): the Laplacian block and the cross
+        // terms of the value stream's Zbar
         float gLh[CHN], rv[CHN];
 #pragma unroll
         for (int i = 0; i < CHN; ++i) { gLh[i] = 0.0f; rv[i] = 0.0f; }
 
 #pragma unroll
-        for (int p = 0; p < S; ++p, ++gp) {
-          const int s = S - 1 - p;
-          const bool is_lap = LAP && s == S - 1, is_val = (s == 0);
-          // ---- the adjoint block of this stream
-          if (!top) {
-            mbar_wait(&bar_d[s], (ph_d >> s) & 1u);
-            ph_d ^= (1u << s);
-            fence_after();
-            Ba[s] = wnorm * __uint_as_float(mzb[(set * B_MAXL + (step - 1)) * 4 + s]);
-          } else {
-            Ba[s] = wnorm * __uint_as_float(mub[set * 4 + s]);
-          }
-          // ---- bound of |Zbar_s|
-          float Bz;
-          if (is_lap) {
-            Bz = Ba[s];
-          } else if (!is_val) {
-            Bz = Ba[s];
-            if (LAP) Bz = fmaf(2.0f * fabsf(lapw[s - 1]) * s2_max<ACT>() * Mz[s], Ba[S - 1], Bz);
-          } else {
-            Bz = Ba[0];
-            float q = 0.0f;
+        for (int P = 0; P < 2; ++P) {
+          constexpr int NPmax = 2;
+          const int np = pass_count<S>(P);
+          if (np == 0) continue;
+          float zsc[NPmax], asc[NPmax];
+          int esum_min = 1 << 20;
+          int ezb[NPmax];
+          // ---- adjoint blocks, bounds and scales of the pass's streams
 #pragma unroll
-            for (int k = 0; k < ND; ++k) {
-              Bz = fmaf(s2_max<ACT>() * Mz[1 + k], Ba[1 + k], Bz);
-              q = fmaf(fabsf(lapw[k]) * Mz[1 + k], Mz[1 + k], q);
+          for (int u = 0; u < NPmax; ++u) {
+            if (u >= np) continue;
+            const int s = pass_stream<S>(P, u);
+            const bool is_lap = LAP && s == S - 1, is_val = (s == 0);
+            if (!top) {
+              mbar_wait(&bar_d[s], (ph_d >> s) & 1u);
+              ph_d ^= (1u << s);
+              Ba[s] = wnorm * __uint_as_float(mzb[(set * B_MAXL + (step - 1)) * 4 + s]);
+            } else {
+              Ba[s] = wnorm * __uint_as_float(mub[set * 4 + s]);
             }
-            if (LAP) Bz = fmaf(Ba[S - 1], fmaf(s3_max<ACT>(), q, s2_max<ACT>() * Mz[S - 1]), Bz);
+            float Bz;
+            if (is_lap) {
+              Bz = Ba[s];
+            } else if (!is_val) {
+              Bz = Ba[s];
+              if (LAP) Bz = fmaf(2.0f * fabsf(lapw[s - 1]) * s2_max<ACT>() * Mz[s], Ba[S - 1], Bz);
+            } else {
+              Bz = Ba[0];
+              float q = 0.0f;
+#pragma unroll
+              for (int k = 0; k < ND; ++k) {
+                Bz = fmaf(s2_max<ACT>() * Mz[1 + k], Ba[1 + k], Bz);
+                q = fmaf(fabsf(lapw[k]) * Mz[1 + k], Mz[1 + k], q);
+              }
+              if (LAP) Bz = fmaf(Ba[S - 1], fmaf(s3_max<ACT>(), q, s2_max<ACT>() * Mz[S - 1]), Bz);
+            }
+            ezb[u] = scale_exp_for(Bz);
+            const int esum = (ezb[u] - 127) + (scale_exp_for(Ma[s]) - 127);
+            esum_min = esum < esum_min ? esum : esum_min;
+            ginv_next[s] = inv_of_exp(ezb[u]) * itau;
           }
-          const int ezb = scale_exp_for(Bz), eab = scale_exp_for(Ma[s]);     // biased exponents of the largest safe scales
-          const int esum = (ezb - 127) + (eab - 127);
-          emin_cur = esum < emin_cur ? esum : emin_cur;
-          // ---- accumulator scale: sticky; flush when this tile does not fit, is far below it, or periodically
+          if (!top) fence_after();
+          emin_cur = esum_min < emin_cur ? esum_min : emin_cur;
+          // ---- accumulator scale: sticky; flush when this tile does not fit, or periodically
           {
-            bool need = my_live && (esum < my_epi || esum > my_epi + 24);
-            if (p == 0 && periodic && my_live) need = true;
+            bool need = my_live && esum_min < my_epi;
+            if (P == (pass_count<S>(0) > 0 ? 0 : 1) && periodic && my_live) need = true;
             if (need) {
               drain_dw();
               flush_dw(l, my_epi);
               my_live = false;
             }
-            if (!my_live) my_epi = (esum < my_emin ? esum : my_emin) - 4;
+            if (!my_live) my_epi = (esum_min < my_emin ? esum_min : my_emin) - 4;
           }
-          const int ea = my_epi - (ezb - 127);                                // real exponent of the A-image scale (<= eab - 127)
-          const float zsc = exp_to_float(ezb), asc = exp_to_float(ea + 127);
-          ginv_next[s] = inv_of_exp(ezb) * itau;
-          // ---- staging region of this pass: the MMAs of pass gp - 2 have finished reading it
-          const uint32_t r = gp & 1u;
-          if (gp >= 2) mbar_wait(&bar_f[r], ((gp >> 1) - 1) & 1u);
-          const uint32_t reg = stage0 + r * REGION + (uint32_t)prow * 128u;
-          float ubs[MAXIO];                    // top step: adjoints of this stream's outputs
 #pragma unroll
-          for (int o = 0; o < MAXIO; ++o) ubs[o] = top ? load_ub(s, o) : 0.0f;
-          float mz_local = 0.0f;
+          for (int u = 0; u < NPmax; ++u) {
+            if (u >= np) continue;
+            zsc[u] = exp_to_float(ezb[u]);
+            asc[u] = exp_to_float(my_epi - (ezb[u] - 127) + 127);
+          }
+          // ---- staging regions of the pass's streams: the MMAs of the streams three slots earlier have finished reading
+          uint32_t reg[NPmax];
+#pragma unroll
+          for (int u = 0; u < NPmax; ++u) {
+            if (u >= np) continue;
+            const uint32_t slot = gs + u, r = slot % NREG;
+            if (slot >= NREG) mbar_wait(&bar_f[r], ((slot / NREG) - 1) & 1u);
+            reg[u] = stage0 + r * REGION + (uint32_t)prow * 128u;
+          }
+          float ubs[NPmax][MAXIO];             // top step: adjoints of the pass's output streams
+          if (top) {
+#pragma unroll
+            for (int u = 0; u < NPmax; ++u)
+#pragma unroll
+              for (int o = 0; o < MAXIO; ++o) ubs[u][o] = (u < np) ? load_ub(pass_stream<S>(P, u < np ? u : 0), o) : 0.0f;
+          }
+          float mz_local[NPmax] = {0.0f, 0.0f};
+
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int jj = 8 * h;              // neurons j0 + jj .. + 7
-            // -- adjoint of a_{l,s}
-            float g[8];
+            const uint32_t off = (uint32_t)(((2 * chunk + h) ^ (prow & 7)) << 4);
+            // -- adjoints of a_{l,s} for the pass's streams
+            float g[NPmax][8];
             if (!top) {
-              uint32_t raw[8];
-              tmem_ld8_nowait(tmem + lane_base + s * 64 + j0 + jj, raw);
+              uint32_t raw[NPmax][8];
+#pragma unroll
+              for (int u = 0; u < NPmax; ++u)
+                if (u < np) tmem_ld8_nowait(tmem + lane_base + pass_stream<S>(P, u) * 64 + j0 + jj, raw[u]);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) g[i] = __uint_as_float(raw[i]) * ginv[s];
+              for (int u = 0; u < NPmax; ++u)
+                if (u < np) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) g[u][i] = __uint_as_float(raw[u][i]) * ginv[pass_stream<S>(P, u)];
+                }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float v = 0.0f;
+              for (int u = 0; u < NPmax; ++u)
+                if (u < np) {
 #pragma unroll
-                for (int o = 0; o < MAXIO; ++o)
-                  if (o < d_out) v = fmaf(WL[o * HP + j0 + jj + i], ubs[o], v);
-                g[i] = v;
-              }
+                  for (int i = 0; i < 8; ++i) {
+                    float v = 0.0f;
+                    for (int o = 0; o < d_out; ++o) v = fmaf(WL[o * HP + jj + i], ubs[u][o], v);
+                    g[u][i] = v;
+                  }
+                }
             }
-            // -- Zbar_s of 8 neurons
-            float zb[8];
-            float aup[8];                      // top step only: a_{L-1,s} for dWL
+            // -- Zbar of 8 neurons for the pass's streams (aup: a_{L-1,s} of the top step, for dWL)
+            float zb[NPmax][8], aup[NPmax][8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float keep = __ldcs(cku + (0 * HP + jj + i) * TP);
               float t, s1, s2;
               act_from_keep<ACT>(keep, t, s1, s2);
-              if (is_lap) {
-                float q = 0.0f;
+              if (P == 0) {
+                // streams S-1 .. 2: [Laplacian,] d_k for k >= 1
+                float dz[NDX];
 #pragma unroll
-                for (int k = 0; k < ND; ++k) { const float dz = __ldcs(cku + ((1 + k) * HP + jj + i) * TP); q = fmaf(lapw[k] * dz, dz, q); }
-                const float lz = __ldcs(cku + ((S - 1) * HP + jj + i) * TP);
-                const float s3 = (ACT == 0) ? -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f) : -s1;
-                zb[i] = g[i] * s1;
-                gLh[jj + i] = g[i];
-                rv[jj + i] = g[i] * fmaf(s3, q, s2 * lz);
-                if (top) aup[i] = fmaf(s2, q, s1 * lz);
-              } else if (!is_val) {
-                const float dz = __ldcs(cku + (s * HP + jj + i) * TP);
-                float v = g[i] * s1;
-                if (LAP) v = fmaf(2.0f * lapw[s - 1] * gLh[jj + i] * s2, dz, v);
-                zb[i] = v;
-                rv[jj + i] = fmaf(g[i] * s2, dz, rv[jj + i]);
-                if (top) aup[i] = s1 * dz;
+                for (int k = 0; k < ND; ++k) dz[k] = (LAP || k >= 1) ? __ldcs(cku + ((1 + k) * HP + jj + i) * TP) : 0.0f;
+                float r = 0.0f, gl = 0.0f;
+                if (LAP) {
+                  float q = 0.0f;
+#pragma unroll
+                  for (int k = 0; k < ND; ++k) q = fmaf(lapw[k] * dz[k], dz[k], q);
+                  const float lz = __ldcs(cku + ((S - 1) * HP + jj + i) * TP);
+                  const float s3 = (ACT == 0) ? -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f) : -s1;
+                  gl = g[0][i];
+                  zb[0][i] = gl * s1;
+                  gLh[jj + i] = gl;
+                  r = gl * fmaf(s3, q, s2 * lz);
+                  if (top) aup[0][i] = fmaf(s2, q, s1 * lz);
+                }
+#pragma unroll
+                for (int u = LAP; u < NPmax; ++u)
+                  if (u < np) {
+                    const int k = pass_stream<S>(0, u) - 1;      // direction of this stream (>= 1)
+                    const int kc = (k >= 0 && k < ND) ? k : 0;
+                    float v = g[u][i] * s1;
+                    if (LAP) v = fmaf(2.0f * lapw[kc] * gl * s2, dz[kc], v);
+                    zb[u][i] = v;
+                    r = fmaf(g[u][i] * s2, dz[kc], r);
+                    if (top) aup[u][i] = s1 * dz[kc];
+                  }
+                rv[jj + i] = r;
               } else {
-                zb[i] = fmaf(g[i], s1, rv[jj + i]);
-                if (top) aup[i] = t;
+                // streams 1 (direction 0), 0 (value)
+                float r = rv[jj + i];
+                if (ND >= 1) {
+                  const float dz = __ldcs(cku + (1 * HP + jj + i) * TP);
+                  float v = g[0][i] * s1;
+                  if (LAP) v = fmaf(2.0f * lapw[0] * gLh[jj + i] * s2, dz, v);
+                  zb[0][i] = v;
+                  r = fmaf(g[0][i] * s2, dz, r);
+                  if (top) aup[0][i] = s1 * dz;
+                }
+                constexpr int uv = (S < 2) ? 0 : 1;
+                zb[uv][i] = fmaf(g[uv][i], s1, r);
+                if (top) aup[uv][i] = t;
               }
-              mz_local = fmaxf(mz_local, fabsf(zb[i]));
             }
-            if (is_val) {                      // bias gradient of layer l
-              const float rs = reduce8(zb, lane);
-              if (lane < 8) acc[ACC_DB + l * HP + j0 + jj + lane] += rs;
+#pragma unroll
+            for (int u = 0; u < NPmax; ++u)
+              if (u < np) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mz_local[u] = fmaxf(mz_local[u], fabsf(zb[u][i]));
+              }
+            if (P == 1) {                      // bias gradient of layer l (value stream)
+              constexpr int uv = (S < 2) ? 0 : 1;
+              const float rs = reduce8(zb[uv], lane);
+              if (lane < 8) atomicAdd(accs + ACC_DB + l * HP + j0 + jj + lane, rs);
             }
             if (top) {                         // output-layer weights: dWL[o][j] += sum_p ubar_s[p][o] a_{L-1,s}[p][j]
+              for (int o = 0; o < d_out; ++o) {
+                float w8[8];
 #pragma unroll
-              for (int o = 0; o < MAXIO; ++o)
-                if (o < d_out) {
-                  float w8[8];
+                for (int i = 0; i < 8; ++i) {
+                  float v = 0.0f;
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) w8[i] = ubs[o] * aup[i];
-                  const float rs = reduce8(w8, lane);
-                  if (lane < 8) acc[ACC_WL + o * HP + j0 + jj + lane] += rs;
+                  for (int u = 0; u < NPmax; ++u)
+                    if (u < np) v = fmaf(ubs[u][o], aup[u][i], v);
+                  w8[i] = v;
                 }
+                const float rs = reduce8(w8, lane);
+                if (lane < 8) atomicAdd(accs + ACC_WL + o * HP + j0 + jj + lane, rs);
+              }
             }
-            {
-              uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int v = 0; v < 4; ++v) split2(zb[2 * v] * zsc, zb[2 * v + 1] * zsc, hi[v], lo[v]);
-              const uint32_t off = (uint32_t)(((2 * chunk + h) ^ (prow & 7)) << 4);
-              st_shared_v4(reg + off, hi[0], hi[1], hi[2], hi[3]);
-              st_shared_v4(reg + IMG + off, lo[0], lo[1], lo[2], lo[3]);
-            }
-            // -- a_{l-1,s} of 8 neurons
-            float av[8];
+            for (int u = 0; u < NPmax; ++u)
+              if (u < np) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) split2(zb[u][2 * v] * zsc[u], zb[u][2 * v + 1] * zsc[u], hi[v], lo[v]);
+                st_shared_v4(reg[u] + off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(reg[u] + IMG + off, lo[0], lo[1], lo[2], lo[3]);
+              }
+            // -- a_{l-1,s} of 8 neurons for the pass's streams
+            float av[NPmax][8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float keep;
+              float keep, dzl[NDX], lzl = 0.0f;
               if (ckd) {
                 keep = __ldcs(ckd + (0 * HP + jj + i) * TP);
+#pragma unroll
+                for (int k = 0; k < ND; ++k) {
+                  const bool used = (P == 0) ? (LAP || k >= 1) : (k == 0);
+                  dzl[k] = used ? __ldcs(ckd + ((1 + k) * HP + jj + i) * TP) : 0.0f;
+                }
+                if (LAP && P == 0) lzl = __ldcs(ckd + ((S - 1) * HP + jj + i) * TP);
               } else {
                 float z0 = bias0[jj + i];
-#pragma unroll
-                for (int cc = 0; cc < MAXIO; ++cc)
-                  if (cc < d_in) z0 = fmaf(W0[cc * HP + j0 + jj + i], xr[cc], z0);
+                for (int cc = 0; cc < d_in; ++cc) z0 = fmaf(W0[cc * HP + jj + i], xr[cc], z0);
                 keep = (ACT == 0) ? tanh_fast(z0) : z0;
+#pragma unroll
+                for (int k = 0; k < ND; ++k) dzl[k] = W0[dcol[k] * HP + jj + i];
               }
               float t, s1, s2;
               act_from_keep<ACT>(keep, t, s1, s2);
-              if (is_val) {
-                av[i] = t;
-              } else if (!is_lap) {
-                const float dz = ckd ? __ldcs(ckd + (s * HP + jj + i) * TP) : W0[dcol[s - 1] * HP + j0 + jj + i];
-                av[i] = s1 * dz;
-              } else {
-                float q = 0.0f;
+              if (P == 0) {
+                if (LAP) {
+                  float q = 0.0f;
 #pragma unroll
-                for (int k = 0; k < ND; ++k) {
-                  const float dz = ckd ? __ldcs(ckd + ((1 + k) * HP + jj + i) * TP) : W0[dcol[k] * HP + j0 + jj + i];
-                  q = fmaf(lapw[k] * dz, dz, q);
+                  for (int k = 0; k < ND; ++k) q = fmaf(lapw[k] * dzl[k], dzl[k], q);
+                  av[0][i] = fmaf(s2, q, s1 * lzl);
                 }
-                const float lz = ckd ? __ldcs(ckd + ((S - 1) * HP + jj + i) * TP) : 0.0f;
-                av[i] = fmaf(s2, q, s1 * lz);
+#pragma unroll
+                for (int u = LAP; u < NPmax; ++u)
+                  if (u < np) {
+                    const int k = pass_stream<S>(0, u) - 1;
+                    const int kc = (k >= 0 && k < ND) ? k : 0;
+                    av[u][i] = s1 * dzl[kc];
+                  }
+              } else {
+                if (ND >= 1) av[0][i] = s1 * dzl[0];
+                constexpr int uv = (S < 2) ? 0 : 1;
+                av[uv][i] = t;
               }
             }
-            {
-              uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int v = 0; v < 4; ++v) split2(av[2 * v] * asc, av[2 * v + 1] * asc, hi[v], lo[v]);
-              const uint32_t off = (uint32_t)(((2 * chunk + h) ^ (prow & 7)) << 4);
-              st_shared_v4(reg + 2 * IMG + off, hi[0], hi[1], hi[2], hi[3]);
-              st_shared_v4(reg + 3 * IMG + off, lo[0], lo[1], lo[2], lo[3]);
+            for (int u = 0; u < NPmax; ++u)
+              if (u < np) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) split2(av[u][2 * v] * asc[u], av[u][2 * v + 1] * asc[u], hi[v], lo[v]);
+                st_shared_v4(reg[u] + 2 * IMG + off, hi[0], hi[1], hi[2], hi[3]);
+                st_shared_v4(reg[u] + 3 * IMG + off, lo[0], lo[1], lo[2], lo[3]);
+              }
+          }
+#pragma unroll
+          for (int u = 0; u < NPmax; ++u)
+            if (u < np) {
+              const float m = warp_max_nonneg(mz_local[u]);
+              if (lane == 0) atomicMax(mzb + (set * B_MAXL + step) * 4 + pass_stream<S>(P, u), __float_as_uint(m));
             }
-          }
-          {
-            const float m = warp_max_nonneg(mz_local);
-            if (lane == 0) atomicMax(mzb + (set * B_MAXL + step) * 4 + s, __float_as_uint(m));
-          }
-          if (warp == 0 && lane == 0) flags[r] = my_live ? 1u : 0u;
+          if (warp == 0 && lane == 0) flags[pp & 1u] = my_live ? 1u : 0u;
           my_live = true;
           fence_async_smem();
           fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_z[r]);
+          if (lane == 0) mbar_arrive(&bar_z[pp & 1u]);
+          gs += np;
+          ++pp;
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) ginv[s] = ginv_next[s];
@@ -496,7 +627,6 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
           ph_d ^= (1u << s);
         }
         fence_after();
-        const float* bias0 = small + lay.bias(0) + j0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int jj = 8 * h;
@@ -508,9 +638,7 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float z0 = bias0[jj + i];
-#pragma unroll
-            for (int cc = 0; cc < MAXIO; ++cc)
-              if (cc < d_in) z0 = fmaf(W0[cc * HP + j0 + jj + i], xr[cc], z0);
+            for (int cc = 0; cc < d_in; ++cc) z0 = fmaf(W0[cc * HP + jj + i], xr[cc], z0);
             float t, s1, s2;
             if constexpr (ACT == 0) {
               t = tanh_fast(z0);
@@ -524,7 +652,7 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
             float v = __uint_as_float(raw[0][i]) * ginv[0] * s1, q = 0.0f;
 #pragma unroll
             for (int k = 0; k < ND; ++k) {
-              const float dz = W0[dcol[k] * HP + j0 + jj + i];
+              const float dz = W0[dcol[k] * HP + jj + i];
               const float gk = __uint_as_float(raw[1 + k][i]) * ginv[1 + k];
               v = fmaf(gk * s2, dz, v);
               float vk = gk * s1;
@@ -542,23 +670,21 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
           }
           {
             const float rs = reduce8(zv, lane);
-            if (lane < 8) acc[ACC_DB + 0 * HP + j0 + jj + lane] += rs;
+            if (lane < 8) atomicAdd(accs + ACC_DB + 0 * HP + j0 + jj + lane, rs);
           }
           float rk[NDX];
 #pragma unroll
           for (int k = 0; k < ND; ++k) rk[k] = reduce8(zk[k], lane);
+          for (int cc = 0; cc < d_in; ++cc) {
+            float w8[8];
 #pragma unroll
-          for (int cc = 0; cc < MAXIO; ++cc)
-            if (cc < d_in) {
-              float w8[8];
+            for (int i = 0; i < 8; ++i) w8[i] = zv[i] * xr[cc];
+            float rs = reduce8(w8, lane);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) w8[i] = zv[i] * xr[cc];
-              float rs = reduce8(w8, lane);
-#pragma unroll
-              for (int k = 0; k < ND; ++k)
-                if (dcol[k] == cc) rs += rk[k];
-              if (lane < 8) acc[ACC_W0 + cc * HP + j0 + jj + lane] += rs;
-            }
+            for (int k = 0; k < ND; ++k)
+              if (dcol[k] == cc) rs += rk[k];
+            if (lane < 8) atomicAdd(accs + ACC_W0 + cc * HP + j0 + jj + lane, rs);
+          }
         }
         fence_before();                        // the TMEM reads of this tile precede the next tile's adjoint MMAs (ordered by bar_z)
       }
@@ -576,9 +702,8 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
     __threadfence();
     named_bar_sync(BAR_ALL, 32 * ACT_WARPS);
     const int HP32 = lay32.HP;
-    // small gradients: the four quadrant copies of every entry
-    for (int v = tid; v < ACC_Q; v += 32 * ACT_WARPS) {
-      const float sum = accs[v] + accs[ACC_Q + v] + accs[2 * ACC_Q + v] + accs[3 * ACC_Q + v];
+    for (int v = tid; v < ACC_BL; v += 32 * ACT_WARPS) {
+      const float sum = accs[v];
       const int j = v % HP;
       if (j >= HP32) continue;
       if (v < ACC_W0) {
@@ -592,9 +717,7 @@ __global__ void __maxnreg__(120) tcp_bwd_kernel(BwdArgs a) {
         if (o < d_out) atomicAdd(a.gacc + lay32.wl() + (size_t)o * HP32 + j, (double)sum);
       }
     }
-    if (tid < MAXIO && tid < d_out)
-      atomicAdd(a.gacc + lay32.bl() + tid, (double)accs[ACC_BL + tid] + (double)accs[ACC_BL + MAXIO + tid] +
-                                               (double)accs[ACC_BL + 2 * MAXIO + tid] + (double)accs[ACC_BL + 3 * MAXIO + tid]);
+    if (tid < d_out) atomicAdd(a.gacc + lay32.bl() + tid, (double)accs[ACC_BL + tid]);
     // hidden matrices: rows j (hi) and 64 + j (lo) of the partial sums both belong to dW[j][i]
     if (ntiles > blockIdx.x) {
       for (int l = 1; l < L; ++l)
@@ -652,7 +775,7 @@ static int launch_tcp_bwd_act(const BwdArgs& a, int sm_count, cudaStream_t strea
   if (grid < 1) return 0;
   cudaError_t e = cudaFuncSetAttribute(tcp_bwd_kernel<ND, LAP, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tcp_bwd_kernel: shared memory attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
-  tcp_bwd_kernel<ND, LAP, ACT><<<(unsigned)grid, THREADS, smem, stream>>>(a);
+  tcp_bwd_kernel<ND, LAP, ACT><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tcp_bwd_kernel launch (%lld CTAs, %zu bytes smem): %s", (long long)grid, smem, cudaGetErrorString(e));
   return 0;
@@ -692,10 +815,8 @@ int tcp_backward(const tpx_fcn_desc* net, const tpx::Layout& lay32, const JetArg
     return launch_tcp_bwd_any(a, net->activation, nd, lap, sm_count, stream);
   }
   // no saved checkpoints: chunks of (forward kernel writing checkpoints only) + reverse kernel through the workspace
-  int64_t ctiles = tcp_tiles_in(net, nd, lap, buf_bytes);
+  const int64_t ctiles = tcp_tiles_in(net, nd, lap, buf_bytes);
   if (ctiles < 1) return fail(TPX_E_WORKSPACE, "workspace of %zu bytes holds no tile", buf_bytes);
-  const int64_t cap = (int64_t)sm_count * 4;            // keep the chunk's checkpoints L2-resident (148 x 4 tiles x 384 KB = 227 MB is too much: 2 tiles)
-  (void)cap;
   const int64_t cpts = ctiles * TP;
   const int d_in = net->d_in, d_out = net->d_out;
   float *ck, *st, *dw;

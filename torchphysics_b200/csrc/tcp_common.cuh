@@ -109,6 +109,11 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
                : "r"(taddr));
 }
 
+// register reallocation between warpgroups (the activation warps need more than the 96 registers a 20-warp CTA starts with;
+// the MMA warpgroup needs far fewer)
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- power-of-two scales from bounds
 // scale 2^e with bound * 2^e in [2^14, 2^15) (fp16 max is 65504); returned as the biased exponent field of the scale
 __device__ __forceinline__ int scale_exp_for(float bound) {

@@ -132,7 +132,7 @@ struct FwdArgs {
 };
 
 template <int ND, int LAP, int ACT>
-__global__ void __maxnreg__(120) tcp_fwd_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) tcp_fwd_kernel(FwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
   constexpr uint32_t RY = 256;               // TMEM column of region Y (X = 0)
@@ -471,12 +471,15 @@ template <int ND, int LAP, int ACT>
 static int launch_tcp_fwd_act(const FwdArgs& a, int sm_count, cudaStream_t stream) {
   const size_t smem = (size_t)fwd_smem(a.lay).total + 1024;
   if (smem > 227 * 1024) return TPX_E_UNSUPPORTED;
-  if (cudaFuncSetAttribute(tcp_fwd_kernel<ND, LAP, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TPX_E_CUDA;
+  cudaError_t e = cudaFuncSetAttribute(tcp_fwd_kernel<ND, LAP, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(TPX_E_CUDA, "tcp_fwd_kernel: shared memory attribute (%zu bytes): %s", smem, cudaGetErrorString(e));
   const int64_t ntiles = (a.n + TP - 1) / TP;
   int64_t grid = sm_count < ntiles ? sm_count : ntiles;
   if (grid < 1) return 0;
   tcp_fwd_kernel<ND, LAP, ACT><<<(unsigned)grid, THREADS, smem, stream>>>(a);
-  return cudaGetLastError() == cudaSuccess ? 0 : TPX_E_CUDA;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TPX_E_CUDA, "tcp_fwd_kernel launch (%lld CTAs, %zu bytes smem): %s", (long long)grid, smem, cudaGetErrorString(e));
+  return 0;
 }
 template <int ND, int LAP>
 static int launch_tcp_fwd(const FwdArgs& a, int act, int sm_count, cudaStream_t stream) {
