@@ -252,9 +252,9 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
   if (jet->lap && !lap) return fail(TPX_E_ARG, "lap is NULL but lap requested");
   a.packed = packed; a.x = x; a.n = n; a.u = u; a.du = du; a.lapo = lap;
   a.stream = (cudaStream_t)stream;
-  if (tcp_supported(net, jet->nd, a.lap) && (!saved || tcp_bwd_supported(net, jet->nd, a.lap))) {
+  if (tcp_supported(net, jet->nd, a.lap) && (!saved || tce_bwd_supported(net, jet->nd, a.lap))) {
     float *ck = nullptr, *st = nullptr, *dw = nullptr;
-    if (saved) tcp_saved_split(net, jet->nd, a.lap, (n + 127) / 128, saved, &ck, &st, &dw);
+    if (saved) tce_saved_split(net, jet->nd, a.lap, (n + 127) / 128, saved, &ck, &st, &dw);
     return tcp_forward(net, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, u, du, lap, ck, st, a.sm_count, a.stream);
   }
   if (tc_supported(net, jet->nd, a.lap)) {
@@ -328,7 +328,7 @@ int tpx_fcn_saved_bytes(const tpx_fcn_desc* net, const tpx_jet_desc* jet, int64_
   if (rc) return rc;
   if (!bytes || n < 0) return fail(TPX_E_ARG, "bad argument");
   const int lap = jet->lap ? 1 : 0;
-  if (tcp_bwd_supported(net, jet->nd, lap)) *bytes = tcp_saved_bytes(net, jet->nd, lap, n);
+  if (tce_bwd_supported(net, jet->nd, lap)) *bytes = tce_saved_bytes(net, jet->nd, lap, n);
   else if (tc_bwd_supported(net, jet->nd, lap)) *bytes = tc_saved_bytes(net, n);
   else if (tcw_supported(net, jet->nd, lap)) *bytes = tcw_saved_bytes(net, jet->nd, lap, n);
   else *bytes = 0;
@@ -360,8 +360,8 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
     default: rc = TPX_E_UNSUPPORTED;
   }
   if (rc) return fail(rc, "no reverse kernel for HP=%d nd=%d lap=%d d_out=%d", a.lay.HP, jet->nd, jet->lap, a.lay.d_out);
-  if (tcp_bwd_supported(net, jet->nd, a.lap)) {
-    const size_t tcb = tcp_saved_bytes(net, jet->nd, a.lap, (int64_t)a.sm_count * 2 * 128);   // two tiles per SM: the chunk stays in L2
+  if (tce_bwd_supported(net, jet->nd, a.lap)) {
+    const size_t tcb = tce_saved_bytes(net, jet->nd, a.lap, (int64_t)a.sm_count * 2 * 128);   // two tiles per SM: the chunk stays in L2
     if (tcb > *bytes) *bytes = tcb;
   } else if (tc_bwd_supported(net, jet->nd, a.lap)) {
     const size_t tcb = tc_bwd_workspace_bytes(net, a.sm_count);
@@ -388,8 +388,8 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   a.gu = gu; a.gdu = jet->nd > 0 ? gdu : nullptr; a.glap = jet->lap ? glap : nullptr;
   a.gacc = grad_acc; a.ckpt = (float*)workspace; a.ckpt_bytes = workspace_bytes;
   a.stream = (cudaStream_t)stream;
-  if (tcp_bwd_supported(net, jet->nd, a.lap))
-    return tcp_backward(net, a.lay, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
+  if (tce_bwd_supported(net, jet->nd, a.lap))
+    return tce_backward(net, a.lay, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
                         (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);   // the launcher recorded the message
   if (saved && !tc_bwd_supported(net, jet->nd, a.lap)) {
     if (!tcw_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel that reads saved checkpoints");

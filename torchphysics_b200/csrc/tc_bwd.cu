@@ -30,6 +30,7 @@
 
 #include "fcn_common.cuh"
 #include "tc_common.cuh"
+#include "tcp_common.cuh"
 #include "tc_kernels.h"
 #include "tc_layout.cuh"
 #include "tpx_internal.h"
@@ -41,7 +42,10 @@ constexpr int B_CH = 16;                 // neurons per warp group (= columns on
 constexpr int B_GROUPS = HP / B_CH;      // warp groups: the 4 quadrant warps that share one chunk of neurons
 constexpr int B_NW = B_CH / 4;           // neurons per warp in the compute phase
 constexpr int B_EPI_WARPS = 4 * B_GROUPS;
-constexpr int B_THREADS = 32 * (B_EPI_WARPS + 1);
+// 16 activation warps, the MMA warp and 3 idle warps that complete its warpgroup: setmaxnreg moves registers between whole
+// warpgroups, and a 17-warp CTA is otherwise held to 96 registers per thread (5 warps on one scheduler's register file)
+constexpr int B_THREADS = 32 * 20;
+constexpr int B_ACT_REGS = 104, B_MMA_REGS = 64;     // 4 x 128 x (104 - 96) taken = 128 x (96 - 64) released
 constexpr uint32_t B_TMEM_COLS = 512;
 constexpr uint32_t T_D = 0, T_AH = 64, T_AL = 128, T_DW = 192;   // TMEM columns
 // The TMEM accumulators of dW round toward zero on every add (one ulp of the running sum): over the ~450 tiles of a CTA
@@ -151,7 +155,10 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   const int64_t ntiles = (a.n + TILE - 1) / TILE;
   const int64_t my_tiles = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (warp == B_EPI_WARPS) {
+  if (warp > B_EPI_WARPS) {
+    tcp::reg_dec<B_MMA_REGS>();          // idle warps of the MMA warpgroup
+  } else if (warp == B_EPI_WARPS) {
+    tcp::reg_dec<B_MMA_REGS>();
     // =========================== weight producer + MMA issuer ===========================
     const uint32_t ring = smem_u32(sm + so.wring), zt = smem_u32(sm + so.zt), at = smem_u32(sm + so.at);
     constexpr uint32_t idesc = idesc_tf32(128, HP);
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 #endif
     }
   } else {
+    tcp::reg_inc<B_ACT_REGS>();
     // =========================== activation warps ===========================
     // warp = grp * 4 + quad: TMEM quadrant quad (= stream quad), group neurons [16 grp, 16 grp + 16);
     // compute phase: neurons jn .. jn + 3, all streams

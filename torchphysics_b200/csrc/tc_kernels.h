@@ -37,16 +37,17 @@ int tcws_backward(const Layout& lay, const JetArgs& jet, int lap, const float* p
 // points-as-lanes fp16-split path (hidden width <= 64; tcp_fwd.cu, tcp_bwd.cu): supersedes tc_* where it applies
 bool tcp_net_supported(const tpx_fcn_desc* net);
 bool tcp_supported(const tpx_fcn_desc* net, int nd, int lap);
-bool tcp_bwd_supported(const tpx_fcn_desc* net, int nd, int lap);
 size_t tcp_packed_floats(const tpx_fcn_desc* net);
 int tcp_pack(const tpx_fcn_desc* net, const void* const* params_host, float* img, cudaStream_t stream);
 size_t tcp_ckpt_floats_per_tile(int L, int S);
-size_t tcp_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n);   // checkpoints + tile statistics + dW partial sums
-int64_t tcp_tiles_in(const tpx_fcn_desc* net, int nd, int lap, size_t bytes);
-void tcp_saved_split(const tpx_fcn_desc* net, int nd, int lap, int64_t ntiles, float* base, float** ckpt, float** stats, float** dwpart);
+// reverse kernel of that path (tce_bwd.cu: rows = (stream, point), split-fp16 operand images)
+bool tce_bwd_supported(const tpx_fcn_desc* net, int nd, int lap);
+size_t tce_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n);   // checkpoints + tile statistics + dW partial sums
+int64_t tce_tiles_in(const tpx_fcn_desc* net, int nd, int lap, size_t bytes);
+void tce_saved_split(const tpx_fcn_desc* net, int nd, int lap, int64_t ntiles, float* base, float** ckpt, float** stats, float** dwpart);
 int tcp_forward(const tpx_fcn_desc* net, const JetArgs& jet, int lap, const float* img, const float* x, int64_t n,
                 float* u, float* du, float* lapo, float* ckpt, float* stats, int sm_count, cudaStream_t stream);
-int tcp_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet, int lap, const float* img, const float* x,
+int tce_backward(const tpx_fcn_desc* net, const Layout& lay32, const JetArgs& jet, int lap, const float* img, const float* x,
                  int64_t n, const float* gu, const float* gdu, const float* glap, double* gacc, float* buf, size_t buf_bytes,
                  int saved, int sm_count, cudaStream_t stream);
 extern long long* g_tc_debug;   // development: device buffer of >= 512 int64 timestamps, or NULL
