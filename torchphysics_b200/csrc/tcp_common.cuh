@@ -75,6 +75,9 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_byte
 __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {   // fp16 x fp16 -> fp32
   return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {  // bf16 x bf16 -> fp32
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
@@ -136,6 +139,13 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// two values -> (hi, lo) bf16 pairs (x = hi + lo to 16 significant bits, fp32 exponent range), element 0 in the low half
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 
 // warp-wide maximum of non-negative floats in one instruction
