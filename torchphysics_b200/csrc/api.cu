@@ -282,7 +282,7 @@ int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
 }
 
 // points per chunk of the wide tensor-core path when its activation arrays live in a caller workspace
-static const int64_t kWideChunkPoints = 65536;
+static const int64_t kWideChunkPoints = 262144;
 static int64_t wide_chunk_points(const tpx_fcn_desc* net, int nd, int lap, size_t workspace_bytes) {
   const size_t fixed = tcw_saved_bytes(net, nd, lap, 0);          // per-CTA partial sums of the reverse kernel
   const size_t per16 = tcw_saved_bytes(net, nd, lap, 16) - fixed; // bytes of one 16-point tile

@@ -7,12 +7,11 @@
 // Per hidden matrix l (1 <= l < L) the reverse step issues two products:
 //   adjoint   D[128 x 64] = Zbar_l[128 x 64] W_l            A = Zbar (hi/lo) in TMEM, B = W_l^T image (K-major)
 //   gradient  dW_l[j, i] += sum_r Zbar_l[r, j] a_{l-1}[r, i] r = all 128 rows (4 streams x 32 points) is the K
-//             dimension.  Round 2: both operands are two-term bf16 splits (hi + lo = 16 significant bits, fp32 exponent
-//             range: no scaling; what the sum over >= 128 rows needs, scripts/fp16_split_emul.py) stored as 128-byte
-//             rows (row = K index, 64 neurons) with one 8-byte store per 4 neurons and read MN-major by kind::f16 MMAs:
-//             Zbar stacked [hi ; lo] on M = 128, a_{l-1} as [hi | lo] (N = 128) or two N = 64 chains.  Half the bytes
-//             and a quarter of the store instructions of the round-1 transposed tf32 operands; the operand images are
-//             double buffered.  dW_l accumulates in TMEM and is flushed every FLUSH_TILES tiles.
+//             dimension: both operands are written TRANSPOSED into shared memory (row = neuron, K = row
+//             index, 128-byte swizzle; one conflict-free scalar store per element), Zbar stacked as
+//             [hi ; lo] on M = 128 and a_{l-1} as two N = 64 operands hi / lo, so two chains give
+//             hi*hi + lo*hi + hi*lo + lo*lo.  dW_l accumulates in TMEM over ALL tiles of the CTA and is
+//             read out once at the end of the kernel.
 //
 // Activation step (16 warps = 4 neuron groups x 4 TMEM quadrants, lane = point).  A TMEM quadrant holds ONE
 // stream, but the adjoint formulas couple all streams of a point, so the step is split like the forward's:
@@ -77,8 +76,8 @@ constexpr int ACC_DB = 0, ACC_W0 = MAXL * HP, ACC_WL = ACC_W0 + MAXIO * HP, ACC_
 __host__ __device__ inline BwdSmem bwd_smem(const TcLayout& lay) {
   BwdSmem s;
   s.wring = 0;                            // (hi, lo) x 4096: one product image, refetched per phase
-  s.zt = 8192;                            // two operand-image buffers of 64 KB: [Z_hi | Z_lo | A_hi | A_lo], each 128 rows x 128 B (bf16)
-  s.at = s.zt + 16384;                    // (second buffer)
+  s.zt = 8192;                            // 128 rows x 128 K
+  s.at = s.zt + 16384;                    // 128 rows (a_hi 0-63, a_lo 64-127) x 128 K
   s.ex = s.at + 16384;
   s.acc = s.ex + B_GROUPS * BX_GROUP;
   s.small = s.acc + ACC_TOTAL;
@@ -124,7 +123,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   constexpr int S = 1 + ND + LAP;
   constexpr int NDX = ND > 0 ? ND : 1;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_a, bar_z[2], bar_d, bar_f[2], bar_w;
+  __shared__ uint64_t bar_a, bar_z, bar_d, bar_f, bar_w;
   __shared__ uint32_t tmem_slot;
   float* sm = reinterpret_cast<float*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
   const TcLayout lay = a.lay;
@@ -142,8 +141,9 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
   if (warp == B_EPI_WARPS) tmem_alloc(&tmem_slot, B_TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bar_a, B_EPI_WARPS);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bar_z[b], B_EPI_WARPS); mbar_init(&bar_f[b], 1); }
+    mbar_init(&bar_z, B_EPI_WARPS);
     mbar_init(&bar_d, 1);
+    mbar_init(&bar_f, 1);
     mbar_init(&bar_w, 1);
     mbar_init_fence();
   }
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     const uint32_t ring = smem_u32(sm + so.wring), zt = smem_u32(sm + so.zt), at = smem_u32(sm + so.at);
     constexpr uint32_t idesc = idesc_tf32(128, HP);
     const int64_t total_phases = my_tiles * nphase;
-    uint32_t ph_a = 0, ph_w = 0, ph_d = 0;
+    uint32_t ph_a = 0, ph_z = 0, ph_w = 0, ph_d = 0;
     auto phase_src = [&](int64_t g) -> const float* {
       const int l = (L - 1) - (int)(g % nphase);
       return a.img + lay.mat(l, 2);
@@ -214,28 +214,28 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       }
       // ... and it only needs the TMEM A operand: the activation warps write the transposed operands of the gradient
       // product (the longest phase of a step) while it runs, and signal them separately
-      mbar_wait(&bar_z[g & 1], (uint32_t)(g >> 1) & 1u);
+      mbar_wait(&bar_z, ph_z);
+      ph_z ^= 1;
       fence_after();
       if (elect_one()) {
         const uint32_t tW = tmem + T_DW + dw_col(L, l);
-        const uint32_t zh = zt + (uint32_t)(g & 1) * 65536u, ah = zh + 32768u, al = zh + 49152u;   // Z_lo = Z_hi + 16 KB, A_lo = A_hi + 16 KB
         if (dw_is_wide(L, l)) {
-          constexpr uint32_t idesc_w = tcp::idesc_bf16(128, 2 * HP, 1, 1);
+          constexpr uint32_t idesc_w = idesc_tf32(128, 2 * HP);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tcp::mma_f16_ss(tW, tcp::desc_sw128(zh + ks * 2048, 16384, 1024), tcp::desc_sw128(ah + ks * 2048, 16384, 1024), idesc_w,
-                            (ks > 0 || !first_tile) ? 1u : 0u);
+          for (int ks = 0; ks < 16; ++ks)
+            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 16384 + (ks & 3) * 32),
+                        idesc_w, (ks > 0 || !first_tile) ? 1u : 0u);
         } else {
-          constexpr uint32_t idesc_n = tcp::idesc_bf16(128, HP, 1, 1);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tcp::mma_f16_ss(tW, tcp::desc_sw128(zh + ks * 2048, 16384, 1024), tcp::desc_sw128(al + ks * 2048, 16384, 1024), idesc_n,
-                            (ks > 0 || !first_tile) ? 1u : 0u);
+          for (int ks = 0; ks < 16; ++ks)
+            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32), desc_k_sw128(at + (ks >> 2) * 16384 + (ks & 3) * 32),
+                        idesc, (ks > 0 || !first_tile) ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tcp::mma_f16_ss(tW, tcp::desc_sw128(zh + ks * 2048, 16384, 1024), tcp::desc_sw128(ah + ks * 2048, 16384, 1024), idesc_n, 1);
+          for (int ks = 0; ks < 16; ++ks)
+            mma_tf32_ss(tW, desc_k_sw128(zt + (ks >> 2) * 16384 + (ks & 3) * 32),
+                        desc_k_sw128(at + 8192u + (ks >> 2) * 16384 + (ks & 3) * 32), idesc, 1);
         }
-        mma_commit(&bar_f[g & 1]);           // the gradient product only gates the reuse of its operands
+        mma_commit(&bar_f);                  // the gradient product only gates the reuse of its operands
       }
       __syncwarp();
 #ifdef TPX_TIMELINE
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       lapw[k] = (LAP && k < ND) ? a.jet.lap_w[k] : 0.0f;
       dcol[k] = (k < ND) ? a.jet.dcol[k] : 0;
     }
-    uint32_t ph_d = 0;
-    uint32_t gstep = 0;                  // global step counter (the MMA warp's g): operand-image buffer = gstep & 1
+    uint32_t ph_d = 0, ph_f = 0;
+    bool dw_pending = false;             // a gradient product may still be reading Zt / At
     bool flush_now = false;              // first step of a tile that follows FLUSH_TILES tiles of accumulation
     int tcount = 0;
     // this thread's slice of the hidden dW accumulators -> the CTA's fp32 partial sums (hi rows j and lo rows 64 + j of a
@@ -290,9 +290,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
     };
     // transposed operands: element (row = neuron, K = 32 s + lane); 128-byte swizzle:
     //   offset = s * atom + row * 32 + ((lane / 4) ^ (row % 8)) * 4 + lane % 4
-    // operand images: row = 32 s + lane (the K index), 128 bytes = 64 neurons (bf16); this thread's 4 neurons are 8 bytes at
-    // 16-byte chunk (jn / 8) ^ (row & 7) (the 128-byte swizzle)
-    const uint32_t img_off = smem_u32(sm + so.zt) + (uint32_t)lane * 128u + (uint32_t)((((jn >> 3) ^ (lane & 7)) << 4) + ((jn & 7) << 1));
+    float* Zt = sm + so.zt + jn * 32 + (lane & 3);
+    float* At = sm + so.at + jn * 32 + (lane & 3);
+    int xo[B_NW];
+#pragma unroll
+    for (int i = 0; i < B_NW; ++i) xo[i] = ((lane >> 2) ^ ((jn + i) & 7)) << 2;
     if (!owner) {                        // rows of an unused quadrant: a zero A operand, written once
       float zero[B_CH];
 #pragma unroll
@@ -432,36 +434,33 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       // (2) transposed operands of the gradient product, in the shadow of the adjoint product
       float ap[S][B_NW];
       jets(cprev, ap);
-      // the gradient product of two steps ago has finished reading this image buffer
-      if (gstep >= 2) mbar_wait(&bar_f[gstep & 1], ((gstep >> 1) - 1) & 1u);
+      if (dw_pending) {                  // the previous gradient product must have finished reading Zt / At
+        mbar_wait(&bar_f, ph_f);
+        ph_f ^= 1;
+      }
       if (flush_now) {                   // every gradient product so far has completed; the next ones start from zero
-        if (gstep >= 1) mbar_wait(&bar_f[(gstep - 1) & 1], ((gstep - 1) >> 1) & 1u);
         fence_after();
         flush_dw();
         fence_before();
         flush_now = false;
       }
       TPX_STAMP(5);
-      {
-        const uint32_t base = img_off + (gstep & 1) * 65536u;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          uint32_t h0, l0, h1, l1;
-          tcp::split2_bf16(zb[s][0], zb[s][1], h0, l0);
-          tcp::split2_bf16(zb[s][2], zb[s][3], h1, l1);
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + s * 4096), "r"(h0), "r"(h1) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + s * 4096 + 16384), "r"(l0), "r"(l1) : "memory");
-          tcp::split2_bf16(ap[s][0], ap[s][1], h0, l0);
-          tcp::split2_bf16(ap[s][2], ap[s][3], h1, l1);
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + s * 4096 + 32768), "r"(h0), "r"(h1) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(base + s * 4096 + 49152), "r"(l0), "r"(l1) : "memory");
+      for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int i = 0; i < B_NW; ++i) {
+          const float zh = tf32_hi(zb[s][i]);
+          Zt[s * 4096 + i * 32 + xo[i]] = zh;
+          Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
+          const float ah = tf32_hi(ap[s][i]);
+          At[s * 4096 + i * 32 + xo[i]] = ah;
+          At[s * 4096 + (64 + i) * 32 + xo[i]] = ap[s][i] - ah;
         }
-      }
+      dw_pending = true;
       TPX_STAMP(6);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_z[gstep & 1]);
-      ++gstep;
+      if (lane == 0) mbar_arrive(&bar_z);
       TPX_STAMP(7);
 #ifdef TPX_TIMELINE
       if (dbgp) dbgp -= 16;
@@ -472,28 +471,6 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       if (lane < B_NW) acc[ACC_DB + l * HP + jn + lane] += r;
     };
 
-    // checkpoints of the top two layers and the output adjoints of a tile are fetched while the previous tile finishes
-    // (its first-layer section): a tile start does not wait for HBM
-    float ck[S][B_NW], ckn[S][B_NW];         // checkpoints of the current layer and of the one below (prefetched)
-    float g[S][MAXIO];                       // adjoints of this point's output streams
-    auto load_g = [&](int64_t t) {
-      const int64_t gpx = t * TILE + lane;
-      const bool vx = gpx < a.n;
-#pragma unroll
-      for (int o = 0; o < MAXIO; ++o) {
-        const bool on = vx && o < d_out;
-        g[0][o] = (on && a.gu) ? __ldg(a.gu + gpx * d_out + o) : 0.0f;
-#pragma unroll
-        for (int k = 0; k < ND; ++k) g[1 + k][o] = (on && a.gdu) ? __ldg(a.gdu + (gpx * d_out + o) * ND + k) : 0.0f;
-        if (LAP) g[S - 1][o] = (on && a.glap) ? __ldg(a.glap + gpx * d_out + o) : 0.0f;
-      }
-    };
-    if (blockIdx.x < ntiles) {
-      const float* ck0 = a.ckpt + (size_t)blockIdx.x * ((size_t)L * 4 * HP * TILE);
-      load_ck(ck0, L - 1, ck);
-      load_ck(ck0, L - 2, ckn);
-      load_g(blockIdx.x);
-    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       flush_now = tcount > 0 && tcount % FLUSH_TILES == 0;
       ++tcount;
@@ -504,12 +481,22 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
                  ? a.dbg + (warp == 0 ? 0 : 256) + (L - 1) * 16 : nullptr;
 #endif
       const float* ck_tile = a.ckpt + (size_t)tile * ((size_t)L * 4 * HP * TILE);
-      const bool has_next = tile + gridDim.x < ntiles;
-      const float* ck_next = a.ckpt + (size_t)(tile + gridDim.x) * ((size_t)L * 4 * HP * TILE);
+      float ck[S][B_NW], ckn[S][B_NW];       // checkpoints of the current layer and of the one below (prefetched)
+      load_ck(ck_tile, L - 1, ck);
+      load_ck(ck_tile, L - 2, ckn);
       // ------------------------------------------------ output layer + last hidden layer (l = L - 1)
       {
         float ga[S][B_NW], zb[S][B_NW];
         {
+          float g[S][MAXIO];                 // adjoints of this point's output streams
+#pragma unroll
+          for (int o = 0; o < MAXIO; ++o) {
+            const bool on = valid && o < d_out;
+            g[0][o] = (on && a.gu) ? __ldg(a.gu + gp * d_out + o) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) g[1 + k][o] = (on && a.gdu) ? __ldg(a.gdu + (gp * d_out + o) * ND + k) : 0.0f;
+            if (LAP) g[S - 1][o] = (on && a.glap) ? __ldg(a.glap + gp * d_out + o) : 0.0f;
+          }
           if (warp == 0) {                   // output bias: sum of the value-stream adjoints
 #pragma unroll
             for (int o = 0; o < MAXIO; ++o) {
@@ -563,13 +550,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       // ------------------------------------------------ first layer: z = W0 x + b0, d_k z = W0[:, dcol_k], L z = 0
       {
         float ga[S][B_NW], zb[S][B_NW];
-        if (has_next) {                      // ck and g are dead: the next tile's top checkpoints and adjoints
-          load_ck(ck_next, L - 1, ck);
-          load_g(tile + gridDim.x);
-        }
         fetch_adjoint(ga);
         zbar(ckn, ga, zb);
-        if (has_next) load_ck(ck_next, L - 2, ckn);
         add_bias(0, zb);
         float rk[NDX];
 #pragma unroll
@@ -586,8 +568,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
           }
       }
     }
-    if (gstep >= 1) {                        // the last gradient product of this CTA
-      mbar_wait(&bar_f[(gstep - 1) & 1], ((gstep - 1) >> 1) & 1u);
+    if (dw_pending) {                        // the last gradient product of this CTA
+      mbar_wait(&bar_f, ph_f);
       fence_after();
     }
 

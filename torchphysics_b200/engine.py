@@ -273,7 +273,7 @@ def save_budget_bytes(device):
     if env is not None:
         return int(float(env) * 2 ** 30)
     free, _total = torch.cuda.mem_get_info(device)
-    return int(0.3 * free)
+    return int(0.6 * free)
 
 
 class _FcnJetFn(torch.autograd.Function):
