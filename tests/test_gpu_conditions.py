@@ -415,3 +415,77 @@ def test_native_squared_error_mean(shape):
         assert abs(float(out) - float(ref)) <= 2e-6 * abs(float(ref))
         g = src.grad if b is not None else src.grad[1:].reshape(shape)
         assert torch.allclose(g, a.grad, rtol=1e-6, atol=0)
+
+
+def test_operators_on_expressions_of_a_native_output():
+    """laplacian(u * g, x), grad(u ** 2, x): the reference differentiates any autograd graph
+    (differentialoperators.py:11-66); here pointwise expressions of a native output carry derivative streams
+    (jets.ExprEvaluation).  Oracle: the same residual through torch.autograd in float64 on the CPU."""
+    import torchphysics_b200 as tp
+    G = load("poisson_4x64")
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(64,) * 4).cuda()
+    _load_params(model, G["params"])
+    xs = torch.from_numpy(G["x"])
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(xs, X))
+
+    def weight(x):
+        return x[:, :1] * (1.0 - x[:, :1]) * torch.sin(math.pi * x[:, 1:])
+
+    def residual(u, x):
+        v = u * weight(x)                                  # hard-constraint style ansatz written inline
+        return tp.utils.laplacian(v, x) + (tp.utils.grad(u ** 2, x) ** 2).sum(dim=1, keepdim=True)
+
+    cond = tp.conditions.PINNCondition(model, sampler, residual)
+    for it in range(2):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+    # oracle
+    seq = ref_autograd.fcn_from_params(G["params"], dtype=torch.float64)
+    x = xs.double().requires_grad_(True)
+    u = seq(x)
+    v = u * weight(x)
+    r = ref_autograd.laplacian(v, x) + (ref_autograd.grad(u ** 2, x) ** 2).sum(dim=1, keepdim=True)
+    loss_ref = (r ** 2).sum(dim=1).mean()
+    loss_ref.backward()
+    assert abs(float(loss) - float(loss_ref)) < TOL * abs(float(loss_ref))
+    ref_grads = [p.grad.numpy() for p in ref_autograd.linear_params(seq)]
+    for a, w in zip(_grads(model), ref_grads):
+        assert a is not None and relerr(a, w) < TOL
+
+
+def test_adaptive_activation_function_is_native():
+    """tp.models.AdaptiveActivationFunction (reference activation_fn.py:5-38): tanh(scaling * a * z) with a trainable a.
+    Parity of loss, dLoss/dtheta and dLoss/da with the same network through torch.autograd in float64."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(11)
+    X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
+    act = tp.models.AdaptiveActivationFunction(torch.nn.Tanh(), inital_a=0.8, scaling=1.5)
+    model = tp.models.FCN(X, U, hidden=(48, 48, 48), activations=act).cuda()
+    xs = torch.rand(311, 2)
+    cond = tp.conditions.PINNCondition(model, tp.samplers.DataSampler(tp.spaces.Points(xs, X)),
+                                       lambda u, x: tp.utils.laplacian(u, x) + u * u - tp.utils.grad(u, x)[:, :1])
+    for it in range(2):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+    assert model._native_engine() is not False
+    # oracle: the same layers in float64 on the CPU
+    lins = [m for m in model.sequential if isinstance(m, torch.nn.Linear)]
+    Ws = [l.weight.detach().cpu().double().requires_grad_(True) for l in lins]
+    bs = [l.bias.detach().cpu().double().requires_grad_(True) for l in lins]
+    a = torch.tensor(float(act.a), dtype=torch.float64, requires_grad=True)
+    x = xs.double().requires_grad_(True)
+    h = x
+    for i in range(len(lins) - 1):
+        h = torch.tanh(1.5 * a * (h @ Ws[i].T + bs[i]))
+    u = h @ Ws[-1].T + bs[-1]
+    r = ref_autograd.laplacian(u, x) + u * u - ref_autograd.grad(u, x)[:, :1]
+    loss_ref = (r ** 2).sum(dim=1).mean()
+    loss_ref.backward()
+    assert abs(float(loss) - float(loss_ref)) < TOL * abs(float(loss_ref))
+    for l, W, b in zip(lins, Ws, bs):
+        assert relerr(l.weight.grad.cpu().numpy(), W.grad.numpy()) < TOL
+        assert relerr(l.bias.grad.cpu().numpy(), b.grad.numpy()) < TOL
+    assert abs(float(act.a.grad) - float(a.grad)) < TOL * abs(float(a.grad))

@@ -1,0 +1,126 @@
+"""Host logic of jets.ExprEvaluation: derivative streams through pointwise expressions of native model outputs
+(reference semantics: differentialoperators.py:11-66 differentiate ANY autograd graph, e.g. laplacian(u * g, x)).
+The native evaluation is replaced by an analytic stand-in with the same protocol, so this runs without a GPU."""
+import math
+
+import torch
+
+from torchphysics_b200 import jets, operators
+from torchphysics_b200.engine import JetSpec
+
+
+class AnalyticEvaluation:
+    """u0 = sin(a x0) cos(b x1), u1 = exp(0.3 x0) x1^2 with exact streams, on tracked leaves."""
+
+    def __init__(self, x_leaf):
+        self.leaf = x_leaf
+        self.batch_shape = tuple(x_leaf.shape[:-1])
+        self.leaf_cols = {id(x_leaf): (x_leaf, [0, 1])}
+        self.spec = JetSpec((), None)
+        self.a, self.b = 1.3, 0.7
+
+    def columns_of(self, var):
+        return [0, 1] if var is self.leaf else None
+
+    def leaf_for_col(self, col):
+        return self.leaf, col
+
+    def ensure(self, need):
+        self.spec = need
+        return True
+
+    def _x(self):
+        x = self.leaf.detach()
+        return x[..., 0], x[..., 1]
+
+    def value(self):
+        x0, x1 = self._x()
+        return torch.stack([torch.sin(self.a * x0) * torch.cos(self.b * x1), torch.exp(0.3 * x0) * x1 ** 2], dim=-1)
+
+    def first(self, out_cols, in_col):
+        x0, x1 = self._x()
+        a, b = self.a, self.b
+        d = [[a * torch.cos(a * x0) * torch.cos(b * x1), -b * torch.sin(a * x0) * torch.sin(b * x1)],
+             [0.3 * torch.exp(0.3 * x0) * x1 ** 2, 2 * torch.exp(0.3 * x0) * x1]]
+        return torch.stack([d[m][in_col] for m in out_cols], dim=-1)
+
+    def second(self, out_cols):
+        x0, x1 = self._x()
+        a, b = self.a, self.b
+        w = dict(zip(self.spec.dcols, self.spec.lap_w))
+        dd = [[-a * a * torch.sin(a * x0) * torch.cos(b * x1), -b * b * torch.sin(a * x0) * torch.cos(b * x1)],
+              [0.09 * torch.exp(0.3 * x0) * x1 ** 2, 2 * torch.exp(0.3 * x0)]]
+        return torch.stack([sum(w.get(k, 0.0) * dd[m][k] for k in (0, 1)) for m in out_cols], dim=-1)
+
+
+def _setup(n=64):
+    torch.manual_seed(0)
+    x = torch.rand(n, 2, dtype=torch.float64).requires_grad_(True)
+    ev = AnalyticEvaluation(x)
+    u = jets.JetTensor.wrap(ev.value(), ev, [0, 1])
+    return x, ev, u
+
+
+def _reference(fn, x):
+    """the same expression through plain torch autograd (the reference's definition)"""
+    a, b = 1.3, 0.7
+    u = torch.stack([torch.sin(a * x[:, 0]) * torch.cos(b * x[:, 1]), torch.exp(0.3 * x[:, 0]) * x[:, 1] ** 2], dim=-1)
+    out = fn(u, x)
+    g = torch.autograd.grad(out.sum(), x, create_graph=True)[0]
+    lap = sum(torch.autograd.grad(g[:, i].sum(), x, create_graph=True)[0][:, i] for i in range(2))
+    return out, g, lap[:, None]
+
+
+def _check(fn):
+    x, ev, u = _setup()
+    expr = fn(u, x)
+    assert isinstance(expr, jets.JetTensor) and isinstance(expr._jet, jets.ExprEvaluation)
+    g = operators.grad(expr, x)
+    lap = operators.laplacian(expr, x)
+    out_r, g_r, lap_r = _reference(fn, x.detach().clone().requires_grad_(True))
+    assert torch.allclose(expr.as_subclass(torch.Tensor), out_r, rtol=1e-12, atol=1e-12)
+    assert torch.allclose(g, g_r, rtol=1e-10, atol=1e-10)
+    assert torch.allclose(lap, lap_r, rtol=1e-9, atol=1e-9)
+
+
+def test_product_of_output_and_coordinate_function():
+    _check(lambda u, x: u[:, :1] * torch.sin(math.pi * x[:, :1]) * x[:, 1:])          # u * g(x)
+
+
+def test_power_sum_and_scalars():
+    _check(lambda u, x: u[:, :1] ** 2 + 3.0 * u[:, 1:] - 1.5)
+
+
+def test_unary_functions_and_division():
+    _check(lambda u, x: torch.exp(u[:, :1]) / (2.0 + torch.cos(u[:, 1:])))
+
+
+def test_join_and_slice_of_an_expression():
+    def fn(u, x):
+        both = torch.cat([u[:, :1] * u[:, 1:], torch.tanh(u[:, :1])], dim=-1)
+        return both[:, 1:] - both[:, :1]
+    _check(fn)
+
+
+def test_nested_expressions():
+    _check(lambda u, x: (u[:, :1] * x[:, :1] + u[:, 1:]) * (u[:, :1] - x[:, 1:] ** 2))
+
+
+def test_div_of_an_expression():
+    x, ev, u = _setup()
+    v = u * torch.cat([x[:, 1:], x[:, :1]], dim=-1)             # vector field (u0 x1, u1 x0)
+    d = operators.div(v, x)
+    xr = x.detach().clone().requires_grad_(True)
+    a, b = 1.3, 0.7
+    ur = torch.stack([torch.sin(a * xr[:, 0]) * torch.cos(b * xr[:, 1]), torch.exp(0.3 * xr[:, 0]) * xr[:, 1] ** 2], dim=-1)
+    vr = ur * torch.cat([xr[:, 1:], xr[:, :1]], dim=-1)
+    dr = sum(torch.autograd.grad(vr[:, i].sum(), xr, create_graph=True)[0][:, i] for i in range(2))[:, None]
+    assert torch.allclose(d, dr, rtol=1e-10, atol=1e-10)
+
+
+def test_non_pointwise_functions_still_raise():
+    import pytest
+    from torchphysics_b200 import _lib
+    x, ev, u = _setup()
+    t = torch.cumsum(u, dim=0)
+    assert not isinstance(t, jets.JetTensor) or getattr(t, "_jet", None) is None

@@ -78,6 +78,13 @@ class JetEvaluation:
             return None
         return hit[1]
 
+    def leaf_for_col(self, col):
+        """(leaf tensor, index within it) of input column ``col``, or (None, None)."""
+        for leaf, cols in self.leaf_cols.values():
+            if col in cols:
+                return leaf, cols.index(col)
+        return None, None
+
     def ensure(self, need):
         """make sure the computed streams cover ``need``; returns False if impossible."""
         if self.spec.covers(need):
@@ -152,6 +159,13 @@ class JoinedEvaluation:
 
     def ensure(self, need):
         return all(ev.ensure(need) for ev, _ in self.parts)
+
+    def leaf_for_col(self, col):
+        return self.parts[0][0].leaf_for_col(col)
+
+    @property
+    def spec(self):
+        return self.parts[0][0].spec
 
     def _gather(self, out_cols, fn):
         pieces, run_ev, run_cols = [], None, []
@@ -239,6 +253,9 @@ class ConstrainedEvaluation:
         self._cache.clear()
         return self.inner.ensure(need)
 
+    def leaf_for_col(self, col):
+        return self.inner.leaf_for_col(col)
+
     @property
     def spec(self):
         return self.inner.spec
@@ -279,6 +296,191 @@ def _grad_or_zero(scalar, eps):
     return torch.zeros_like(eps) if g is None else g
 
 
+class ExprEvaluation:
+    """Streams of a POINTWISE torch expression of native model outputs (``u * g``, ``u ** 2 + v``, ``torch.sin(u) * x`` ...),
+    same protocol as ``JetEvaluation``: what lets ``laplacian(u * g, x)`` work as in the reference, whose operators
+    differentiate any autograd graph (``differentialoperators.py:11-44``).
+
+    Operands are native evaluations (their derivative streams come from the kernel), tensors with a torch graph to the
+    coordinate leaves (``torch.sin(x)``: differentiated by torch.autograd) and constants.  With every operand v_i moved
+    along its own derivative, phi_k(eps) = f(v_1 + eps d_k v_1, ..., v_m + eps d_k v_m):
+        d_k out  = phi_k'(0),      d_kk out = phi_k''(0) + sum_i f_{v_i} d_kk v_i
+    so the weighted Laplacian is  sum_k c_k phi_k''(0) + psi'(0),  psi(eps) = f(v_i + eps L v_i); the derivatives of phi
+    and psi are taken by torch.autograd on the pointwise expression (the network is never re-traversed) and keep their graph
+    to the operands' streams, hence to the parameters."""
+
+    def __init__(self, fn, operands, base):
+        self.fn = fn                             # fn(*tensors) -> tensor (..., m)
+        self.operands = operands                 # [("jet", evaluation, cols, value tensor) | ("plain", tensor)]
+        self.base = base                         # a native evaluation among the operands (leaves, spec)
+        self.batch_shape = base.batch_shape
+        self._cache = {}
+
+    def columns_of(self, var):
+        return self.base.columns_of(var)
+
+    def leaf_for_col(self, col):
+        return self.base.leaf_for_col(col)
+
+    @property
+    def spec(self):
+        return self.base.spec
+
+    def ensure(self, need):
+        self._cache.clear()
+        seen, ok = set(), True
+        for op in self.operands:
+            if op[0] == "jet" and id(op[1]) not in seen:
+                seen.add(id(op[1]))
+                ok = op[1].ensure(need) and ok
+        return ok
+
+    # -- operand streams ---------------------------------------------------------------------
+    @staticmethod
+    def _value(op):
+        return op[3] if op[0] == "jet" else op[1]
+
+    def _first_of(self, op, in_col):
+        if op[0] == "jet":
+            return op[1].first(op[2], in_col).reshape(op[3].shape)
+        t = op[1]
+        leaf, idx = self.leaf_for_col(in_col)
+        if not (isinstance(t, torch.Tensor) and t.requires_grad and leaf is not None):
+            return None
+        if t.dim() == 0 or t.shape[:len(self.batch_shape)] != tuple(self.batch_shape):
+            return None                          # not a per-point quantity: constant along the coordinates
+        cols = []
+        for m in range(t.shape[-1]) if t.dim() > len(self.batch_shape) else [None]:
+            comp = t if m is None else t[..., m]
+            g = torch.autograd.grad(comp.sum(), leaf, create_graph=True, allow_unused=True)[0]
+            cols.append(torch.zeros(self.batch_shape, device=t.device, dtype=t.dtype) if g is None else g[..., idx])
+        return cols[0] if t.dim() == len(self.batch_shape) else torch.stack(cols, dim=-1)
+
+    def _second_of(self, op):
+        if op[0] == "jet":
+            return op[1].second(op[2]).reshape(op[3].shape)
+        acc = None
+        spec = self.spec
+        for c, w in zip(spec.dcols, spec.lap_w or ()):
+            if w == 0.0:
+                continue
+            d1 = self._first_of(op, c)
+            if d1 is None or not d1.requires_grad:
+                continue
+            leaf, idx = self.leaf_for_col(c)
+            cols = []
+            for m in range(d1.shape[-1]) if d1.dim() > len(self.batch_shape) else [None]:
+                comp = d1 if m is None else d1[..., m]
+                g = torch.autograd.grad(comp.sum(), leaf, create_graph=True, allow_unused=True)[0]
+                cols.append(torch.zeros(self.batch_shape, device=d1.device, dtype=d1.dtype) if g is None else g[..., idx])
+            d2 = cols[0] if d1.dim() == len(self.batch_shape) else torch.stack(cols, dim=-1)
+            acc = w * d2 if acc is None else acc + w * d2
+        return acc
+
+    def _path(self, dirs, order):
+        """(phi'(0), phi''(0)) of phi(eps) = fn(v_i + eps * dirs_i) (dirs_i None: the operand stays fixed)"""
+        vals = [self._value(op) for op in self.operands]
+        ref = vals[0]
+        eps = torch.zeros((*self.batch_shape, 1), device=ref.device, dtype=ref.dtype, requires_grad=True)
+        moved = []
+        for v, d in zip(vals, dirs):
+            if d is None:
+                moved.append(v)
+            else:
+                e = eps if v.dim() > len(self.batch_shape) else eps[..., 0]
+                moved.append(v + e * d)
+        out = self.fn(*moved)
+        d1 = torch.stack([_grad_or_zero(out[..., m].sum(), eps)[..., 0] for m in range(out.shape[-1])], dim=-1)
+        if order == 1:
+            return d1, None
+        d2 = torch.stack([_grad_or_zero(d1[..., m].sum(), eps)[..., 0] for m in range(out.shape[-1])], dim=-1)
+        return d1, d2
+
+    # -- JetEvaluation protocol ----------------------------------------------------------------
+    def value(self):
+        if "value" not in self._cache:
+            self._cache["value"] = self.fn(*[self._value(op) for op in self.operands])
+        return self._cache["value"]
+
+    def first(self, out_cols, in_col):
+        key = ("d", in_col)
+        if key not in self._cache:
+            self._cache[key] = self._path([self._first_of(op, in_col) for op in self.operands], 1)[0]
+        return JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
+
+    def second(self, out_cols):
+        if "lap" not in self._cache:
+            spec = self.spec
+            acc = self._path([self._second_of(op) for op in self.operands], 1)[0]
+            for c, w in zip(spec.dcols, spec.lap_w):
+                if w != 0.0:
+                    acc = acc + w * self._path([self._first_of(op, c) for op in self.operands], 2)[1]
+            self._cache["lap"] = acc
+        return JetEvaluation._columns(self._cache["lap"], out_cols, self._cache["lap"].dim() - 1)
+
+    def plain(self):
+        raise NotImplementedError("an expression of native evaluations has no generic autograd graph to the coordinates")
+
+
+def _pointwise_functions():
+    T = torch.Tensor
+    fns = {torch.add, torch.sub, torch.mul, torch.div, torch.true_divide, torch.neg, torch.pow, torch.square, torch.sqrt,
+           torch.exp, torch.log, torch.sin, torch.cos, torch.tanh, torch.sigmoid, torch.abs,
+           T.add, T.sub, T.mul, T.div, T.true_divide, T.neg, T.pow, T.square, T.sqrt, T.exp, T.log, T.sin, T.cos, T.tanh,
+           T.sigmoid, T.abs, T.__add__, T.__radd__, T.__sub__, T.__rsub__, T.__mul__, T.__rmul__, T.__truediv__,
+           T.__rtruediv__, T.__neg__, T.__pow__, T.__rpow__}
+    return fns
+
+
+_POINTWISE = _pointwise_functions()
+_JOINS = {torch.cat, torch.concat, torch.column_stack, torch.hstack}
+
+
+def _derive_expression(func, args, kwargs, out):
+    """JetTensor of ``out = func(*args, **kwargs)`` if func is pointwise (or a join along the last axis) and the operands
+    are native outputs of one point set, plain tensors and numbers; None otherwise."""
+    if not isinstance(out, torch.Tensor) or out.dim() < 1:
+        return None
+    join = func in _JOINS
+    if not join and func not in _POINTWISE:
+        return None
+    if kwargs and (set(kwargs) - {"dim", "alpha"}):
+        return None
+    seq = list(args[0]) if join else list(args)
+    if join:
+        dim = kwargs.get("dim", args[1] if len(args) > 1 else (0 if func in (torch.cat, torch.concat) else -1))
+        if func in (torch.cat, torch.concat) and dim not in (-1, out.dim() - 1):
+            return None
+        if func in (torch.column_stack, torch.hstack) and out.dim() != 2:
+            return None
+    operands, slots, base = [], [], None
+    for a in seq:
+        ev, cols = jet_of(a)
+        if ev is not None:
+            if base is not None and tuple(ev.batch_shape) != tuple(base.batch_shape):
+                return None
+            base = base or ev
+            operands.append(("jet", ev, cols, a.as_subclass(torch.Tensor)))
+            slots.append(len(operands) - 1)
+        elif isinstance(a, torch.Tensor):
+            operands.append(("plain", a.as_subclass(torch.Tensor)))
+            slots.append(len(operands) - 1)
+        elif isinstance(a, (int, float, bool)):
+            slots.append(("const", a))
+        else:
+            return None
+    if base is None or tuple(out.shape[:len(base.batch_shape)]) != tuple(base.batch_shape) or out.dim() != len(base.batch_shape) + 1:
+        return None
+    kw = dict(kwargs or {})
+
+    def fn(*tensors):
+        rebuilt = [tensors[sl] if isinstance(sl, int) else sl[1] for sl in slots]
+        if join:
+            return func(rebuilt, *args[1:], **kw)
+        return func(*rebuilt, **kw)
+    return JetTensor.wrap(out, ExprEvaluation(fn, operands, base), range(out.shape[-1]))
+
+
 class JetTensor(torch.Tensor):
     """A tensor of model outputs that remembers its JetEvaluation and output columns."""
 
@@ -303,6 +505,10 @@ class JetTensor(torch.Tensor):
                 src, dim, start, length = a
                 if dim in (-1, src.dim() - 1) and isinstance(start, int):
                     return JetTensor.wrap(out, src._jet, src._cols[start:start + length])
+        else:
+            derived = _derive_expression(func, args, kwargs, out)
+            if derived is not None:
+                return derived
         return out
 
 
@@ -365,13 +571,14 @@ def plain_of(t):
     ev, cols = jet_of(t)
     if ev is None:
         if isinstance(t, torch.Tensor) and _derives_from_native_evaluation(t):
-            # e.g. laplacian(u ** 2, x) or a HardConstraint output: torch.autograd would silently drop the
-            # dependence on x through the network
+            # e.g. laplacian(torch.cumsum(u, 0), x): not a pointwise expression (those carry streams, ExprEvaluation);
+            # torch.autograd would silently drop the dependence on x through the network
             from . import _lib
             raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED,
-                                "a differential operator was applied to a FUNCTION of a native model output (only the "
-                                "model output itself, or column slices of it, carry derivative streams); apply the "
-                                "operator to the model output and combine the results (product / chain rule)")
+                                "a differential operator was applied to a function of a native model output that is not a "
+                                "pointwise arithmetic expression (+ - * / ** neg, sin cos exp log tanh sqrt ..., cat along "
+                                "the last axis: those carry derivative streams); apply the operator to the model output and "
+                                "combine the results")
         return t
     full = ev.plain()
     if cols == list(range(full.shape[-1])) and t.dim() == full.dim():

@@ -85,9 +85,15 @@ def _fc_layers(hidden, input_dim, output_dim, activations, xavier_gains, linear_
     return layers
 
 
+def _inner_activation(m):
+    """the activation a module applies after an optional trainable input scale (``AdaptiveActivationFunction``)"""
+    return m.activation_fn if isinstance(m, AdaptiveActivationFunction) or type(m).__name__ == "AdaptiveActivationFunction" else m
+
+
 def _activation_kind(mods):
     kinds = set()
     for m in mods:
+        m = _inner_activation(m)
         if isinstance(m, nn.Tanh):
             kinds.add("tanh")
         elif isinstance(m, Sinus) or type(m).__name__ == "Sinus":
@@ -162,6 +168,16 @@ class _NativeFcnMixin:
         params = None
         if first_layer is not None:
             params = list(first_layer) + eng.params()[2:]
+        # AdaptiveActivationFunction (reference activation_fn.py:5-38): s(scaling * a * (W h + b)) = s((c W) h + c b) with
+        # c = scaling * a -- the trainable slope folded into the layer's parameters as a differentiable torch expression, so
+        # the kernels see a plain tanh / sin network and autograd carries dLoss/d(cW), dLoss/d(cb) on to W, b and a
+        acts = [seq[2 * i + 1] for i in range(len(eng.linears) - 1)]
+        if any(_inner_activation(m) is not m for m in acts):
+            params = list(eng.params()) if params is None else list(params)
+            for i, m in enumerate(acts):
+                if _inner_activation(m) is not m:
+                    c = m.scaling * m.a
+                    params[2 * i], params[2 * i + 1] = c * params[2 * i], c * params[2 * i + 1]
         ev = jets.JetEvaluation(eng, x2d, batch_shape, leaf_cols, hints, key, generic, spec, params)
         return jets.JetTensor.wrap(ev.value(), ev, range(eng.d_out))
 
