@@ -533,6 +533,26 @@ def run_native(args):
                 blocks[key] = blk
             except Exception as e:                           # never lose the headline line over the extras
                 blocks[key] = {"error": repr(e)[:300]}
+        if world == 1:
+            # the literal config 1 once more with the whole training step (sampler -> jets -> residual -> loss -> reverse -> Adam)
+            # captured in ONE CUDA graph (tp.solver.Trainer(cuda_graph=True)): launch-bound at this size when run eagerly
+            try:
+                import torchphysics_b200 as tp
+                torch.manual_seed(0)
+                model, cond, _ = build_config(tp, 1, 10000, ctx.dev)
+                solver = tp.solver.Solver([cond], optimizer_setting=tp.solver.OptimizerSetting(torch.optim.Adam, lr=1e-3))
+                tr = tp.solver.Trainer(max_steps=303, cuda_graph=True, device=ctx.dev)
+                tr.fit(solver)
+                if tr.graphed:
+                    blocks["1_10k_graph"] = {"workload": CONFIGS[1]["name"] + " + Adam update", "points_per_gpu_per_step": 10000,
+                                             "value": 10000 / (tr.graph_step_ms * 1e-3), "unit": "points/s", "ms_per_step": tr.graph_step_ms,
+                                             "what": "one CUDA-graph launch per training step (300 replays timed with CUDA events): "
+                                                     "device-resident Philox key, device-resident Adam step count",
+                                             "final_loss": float(tr.losses[-1])}
+                else:
+                    blocks["1_10k_graph"] = {"error": "the step was not captured"}
+            except Exception as e:
+                blocks["1_10k_graph"] = {"error": repr(e)[:300]}
         if rank == 0:
             line["configs"] = blocks
     if rank == 0:

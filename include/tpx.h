@@ -190,6 +190,13 @@ int tpx_region_contains(const tpx_region* region, const float* points, int64_t n
 int tpx_sample_uniform(const tpx_shape* shape, uint64_t seed, uint64_t offset, int64_t n, float* out,
                        int32_t row_stride, void* stream);
 
+/* The same with the Philox key in DEVICE memory, for CUDA-graph capture of a whole training step (a replayed launch cannot
+ * receive a fresh key as an argument): tpx_key_advance replaces *key_dev by splitmix64(*key_dev) (one thread), the sampling
+ * launch that follows reads it.  Replaces the per-call host draw of sampler_base.py:130 / the domains' torch.rand calls. */
+int tpx_key_advance(uint64_t* key_dev, void* stream);
+int tpx_sample_uniform_dkey(const tpx_shape* shape, const uint64_t* key_dev, uint64_t offset, int64_t n, float* out,
+                            int32_t row_stride, void* stream);
+
 /* Rejection sampling without a host round trip (replaces the host-synchronising loop of
  * domainoperations/sampler_helper.py:50-76 and the filter loop of
  * samplers/random_samplers.py:60-90): n_candidates points of `generator` are tested
@@ -248,6 +255,11 @@ typedef struct tpx_tensor_list {
 
 int tpx_adam_step(const tpx_tensor_list* list, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int32_t step, void* stream);
+
+/* The same update with the step count in device memory (CUDA-graph capture): *step_dev is incremented, then used for the
+ * bias corrections on the device.  Replaces torch.optim.Adam(capturable=True) behind solver.py:111-136. */
+int tpx_adam_step_dstep(const tpx_tensor_list* list, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int32_t* step_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,12 +39,15 @@ EXPORTS = (
     "tpx_sample_uniform",
     "tpx_sample_reject_workspace_bytes",
     "tpx_sample_uniform_reject",
+    "tpx_key_advance",
+    "tpx_sample_uniform_dkey",
     "tpx_sample_grid",
     "tpx_boundary_normal",
     "tpx_sample_keys",
     "tpx_sample_lhs",
     "tpx_union_pick",
     "tpx_adam_step",
+    "tpx_adam_step_dstep",
     "tpx_squared_error_mean",
     "tpx_squared_error_mean_backward",
 )

@@ -202,6 +202,26 @@ __global__ void sample_kernel(tpx_shape s, uint64_t seed, uint64_t offset, int64
   }
 }
 
+// the same with the Philox key in device memory (a CUDA-graph replay cannot receive a fresh key as a launch argument)
+__global__ void sample_dkey_kernel(tpx_shape s, const uint64_t* __restrict__ key, uint64_t offset, int64_t n, float* __restrict__ out,
+                                   int stride) {
+  const Philox ph(*key);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float q[2];
+    shape_sample(s, ph(offset + (uint64_t)i, 0), q);
+    float* row = out + i * stride + s.col;
+    row[0] = q[0];
+    if (shape_dim(s.kind) > 1) row[1] = q[1];
+  }
+}
+// key <- splitmix64(key): one fresh key per sampling call of a captured step
+__global__ void key_advance_kernel(uint64_t* key) {
+  uint64_t x = *key + 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  *key = x ^ (x >> 31);
+}
+
 // Rejection sampling = three launches, no host round trip:
 //   count   : every CTA generates its CPB candidates, tests them, stores #accepted
 //   scan    : one CTA turns the per-CTA counts into exclusive offsets (+ running total)
@@ -513,6 +533,23 @@ int tpx_sample_uniform(const tpx_shape* shape, uint64_t seed, uint64_t offset, i
   if (!out) return fail(TPX_E_ARG, "NULL pointer");
   sample_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*shape, seed, offset, n, out, row_stride);
   return cudaGetLastError() == cudaSuccess ? 0 : cuda_fail("sample_kernel");
+}
+
+int tpx_key_advance(uint64_t* key_dev, void* stream) {
+  if (!key_dev) return fail(TPX_E_ARG, "NULL pointer");
+  key_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(key_dev);
+  return cudaGetLastError() == cudaSuccess ? 0 : cuda_fail("key_advance_kernel");
+}
+
+int tpx_sample_uniform_dkey(const tpx_shape* shape, const uint64_t* key_dev, uint64_t offset, int64_t n, float* out,
+                            int32_t row_stride, void* stream) {
+  int rc = check_shape(shape, row_stride);
+  if (rc) return rc;
+  if (n < 0) return fail(TPX_E_ARG, "n < 0");
+  if (n == 0) return 0;
+  if (!out || !key_dev) return fail(TPX_E_ARG, "NULL pointer");
+  sample_dkey_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(*shape, key_dev, offset, n, out, row_stride);
+  return cudaGetLastError() == cudaSuccess ? 0 : cuda_fail("sample_dkey_kernel");
 }
 
 int tpx_sample_reject_workspace_bytes(int64_t n_candidates, size_t* bytes) {

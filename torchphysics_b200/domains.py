@@ -36,6 +36,17 @@ class _Rng:
 
     def __init__(self):
         self.stream = 0
+        self.device_key = None          # int64 tensor holding the 64-bit key on the GPU (CUDA-graph capture), or None
+
+    def use_device_key(self, device):
+        """From now on the samplers without rejection read their key from GPU memory and advance it with a one-thread
+        kernel per call (``tpx_key_advance`` / ``tpx_sample_uniform_dkey``): a sampling call becomes capturable in a CUDA
+        graph, and every replay of the graph draws fresh points.  The starting key comes from torch's generator."""
+        if device is None:
+            self.device_key = None
+            return
+        k = self.next_key()
+        self.device_key = torch.tensor([k - (1 << 64) if k >= (1 << 63) else k], dtype=torch.int64, device=device)
 
     @staticmethod
     def _mix(x):
@@ -50,6 +61,11 @@ class _Rng:
 
 
 _rng = _Rng()
+
+
+def use_device_key(device):
+    """see ``_Rng.use_device_key`` (``None`` switches back to host-drawn keys)"""
+    _rng.use_device_key(device)
 
 
 def set_rank_stream(rank):
@@ -218,8 +234,17 @@ class Domain:
             raise NotImplementedError
         shape, shapes, ops = gen
         lib = _lib.lib()
-        key = _rng.next_key()
         stride = out.shape[1]
+        dkey = _rng.device_key
+        if dkey is not None and dkey.device == out.device:
+            if ops:
+                raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "rejection sampling reads its counters on the host and cannot "
+                                    "run with a device-resident key (CUDA-graph capture of the step)")
+            _lib.check(lib.tpx_key_advance(_lib.ptr(dkey), _lib.stream_ptr()))
+            _lib.check(lib.tpx_sample_uniform_dkey(ctypes.byref(shape), _lib.ptr(dkey), ctypes.c_uint64(0), ctypes.c_int64(n),
+                                                   _lib.ptr(out), ctypes.c_int32(stride), _lib.stream_ptr()))
+            return
+        key = _rng.next_key()
         if not ops:
             _lib.check(lib.tpx_sample_uniform(ctypes.byref(shape), ctypes.c_uint64(key), ctypes.c_uint64(0),
                                               ctypes.c_int64(n), _lib.ptr(out), ctypes.c_int32(stride),

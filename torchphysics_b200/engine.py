@@ -120,6 +120,8 @@ class FcnEngine:
         # allocator may hand out the same address again, so such images are always re-packed.
         key = tuple((p.data_ptr(), p._version) for p in params)
         fresh = any(p.grad_fn is not None for p in params)
+        if params[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            fresh = True                  # the captured step must contain the pack launch: the parameters change between replays
         if fresh or self._packed is None or key != self._packed_key or self._packed.device != params[0].device:
             dev = params[0].device
             buf = torch.empty(self.packed_floats, dtype=torch.float32, device=dev)

@@ -18,6 +18,25 @@ class Adam(torch.optim.Optimizer):
             raise ValueError(f"Invalid beta parameters: {betas}")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
+    def use_device_step(self, enable=True):
+        """Keep the step count of every parameter group in GPU memory (``tpx_adam_step_dstep``): ``step()`` then has no
+        host-side state that changes from call to call and can be captured in a CUDA graph.  Switching it off writes the
+        device counts back into ``state[p]['step']``."""
+        if enable:
+            self._dev_steps = {}
+            for gi, group in enumerate(self.param_groups):          # created now: a capture cannot copy from the host
+                ps = [p for p in group["params"] if p.is_cuda]
+                if ps:
+                    n = max([int(self.state[p]["step"]) for p in ps if p in self.state and len(self.state[p])] or [0])
+                    self._dev_steps[gi] = torch.tensor([n], dtype=torch.int32, device=ps[0].device)
+        else:
+            for gi, t in getattr(self, "_dev_steps", {}).items():
+                n = int(t.item())
+                for p in self.param_groups[gi]["params"]:
+                    if p in self.state and len(self.state[p]):
+                        self.state[p]["step"] = n
+            self._dev_steps = None
+
     @staticmethod
     def covers(optimizer_args):
         """True if torch.optim.Adam(**optimizer_args) is exactly what this class computes."""
@@ -28,17 +47,54 @@ class Adam(torch.optim.Optimizer):
             return False
         return optimizer_args.get("betas", (0.9, 0.999))[0] >= 0.5
 
+    def _step_on_device(self, gi, group, lr, dev_steps):
+        todo = []
+        for p in group["params"]:
+            if p.grad is None:
+                continue
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or p.grad.is_sparse:
+                raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "native Adam needs contiguous float32 CUDA parameters")
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            todo.append((p, st))
+        if not todo:
+            return
+        if len(todo) > _lib.TPX_MAX_TENSORS:
+            raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, f"{len(todo)} parameter tensors in one group (max {_lib.TPX_MAX_TENSORS})")
+        if gi not in dev_steps:
+            dev_steps[gi] = torch.tensor([int(todo[0][1]["step"])], dtype=torch.int32, device=todo[0][0].device)
+        tl = _lib.TensorList()
+        tl.n = len(todo)
+        for i, (p, st) in enumerate(todo):
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            tl.param[i], tl.grad[i] = p.data_ptr(), g.data_ptr()
+            tl.exp_avg[i], tl.exp_avg_sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            tl.numel[i] = p.numel()
+        with torch.cuda.device(todo[0][0].device):
+            _lib.check(_lib.lib().tpx_adam_step_dstep(
+                ctypes.byref(tl), ctypes.c_float(lr), ctypes.c_float(group["betas"][0]), ctypes.c_float(group["betas"][1]),
+                ctypes.c_float(group["eps"]), ctypes.c_float(group["weight_decay"]), _lib.ptr(dev_steps[gi]), _lib.stream_ptr()))
+        for p, _ in todo:
+            torch.autograd.graph.increment_version(p)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        dev_steps = getattr(self, "_dev_steps", None)
+        for gi, group in enumerate(self.param_groups):
             lr = group["lr"]
             if isinstance(lr, torch.Tensor):
                 lr = float(lr)
             chunk, step_of_chunk = [], None
+            if dev_steps is not None:
+                self._step_on_device(gi, group, lr, dev_steps)
+                continue
 
             def flush():
                 if not chunk:

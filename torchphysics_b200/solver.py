@@ -74,12 +74,21 @@ class Solver(nn.Module):
                               "frequency": setting.scheduler_frequency}]
 
 
+class _GraphCaptureFailed(RuntimeError):
+    pass
+
+
 class Trainer:
     """The slice of ``pl.Trainer`` the reference's examples use:
     ``Trainer(devices=1, accelerator='gpu', max_steps=K).fit(solver)``."""
 
-    def __init__(self, max_steps=1000, accelerator="gpu", devices=1, device=None, **unused):
+    def __init__(self, max_steps=1000, accelerator="gpu", devices=1, device=None, cuda_graph=False, **unused):
         self.max_steps = max_steps
+        # cuda_graph=True: after a few eager steps the WHOLE step (samplers with a device-resident Philox key -> forward jets
+        # -> residual -> loss -> reverse sweep -> gradient all-reduce -> Adam with a device-resident step count) is captured
+        # once and replayed: one graph launch per step instead of ~40 kernel launches (small batches are launch bound)
+        self.cuda_graph = cuda_graph
+        self.graphed = False
         if device is None:
             if accelerator in ("gpu", "cuda", "auto") and torch.cuda.is_available():
                 device = torch.device("cuda", torch.cuda.current_device())
@@ -87,6 +96,57 @@ class Trainer:
                 device = torch.device("cpu")
         self.device = torch.device(device)
         self.losses = []
+
+    def _fit_graphed(self, solver, optimizer, reducer, size, eager_steps=3):
+        """runs all ``max_steps`` steps: ``eager_steps`` eagerly (the conditions learn their jet specs, buffers are pooled),
+        then one captured step replayed; returns the number of steps done (0 if the step cannot be captured)."""
+        import warnings
+
+        def one_step():
+            optimizer.zero_grad(set_to_none=True)
+            loss = solver.training_step(None, 0)
+            loss.backward()
+            (mean_loss,) = reducer([loss])
+            optimizer.step()
+            return mean_loss if size > 1 else loss.detach()
+
+        n_eager = min(eager_steps, self.max_steps)
+        for _ in range(n_eager):
+            self.losses.append(one_step())
+        if n_eager == self.max_steps:
+            return n_eager
+        try:
+            domains.use_device_key(self.device)
+            optimizer.use_device_step(True)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = one_step()                     # (recorded, not run)
+        except Exception as err:                             # e.g. a sampler that reads its counters on the host
+            domains.use_device_key(None)
+            optimizer.use_device_step(False)
+            torch.cuda.synchronize(self.device)
+            import os
+            import traceback
+            detail = traceback.format_exc() if os.environ.get("TPX_DEBUG") else ""
+            warnings.warn(f"the training step could not be captured in a CUDA graph ({err!r}); continuing eagerly\n{detail}")
+            return n_eager
+        self.graphed = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_eager, self.max_steps):
+            graph.replay()
+            self.losses.append(static_loss.reshape(-1)[:1].clone().reshape(()))
+        e1.record()
+        e1.synchronize()
+        self.graph_step_ms = e0.elapsed_time(e1) / max(1, self.max_steps - n_eager)
+        solver.n_training_step = self.max_steps
+        torch.cuda.synchronize(self.device)
+        domains.use_device_key(None)
+        optimizer.use_device_step(False)
+        self._graph = graph
+        self._last = self.losses[-1]
+        return self.max_steps
 
     def fit(self, solver):
         rank, size = parallel.world()
@@ -111,7 +171,11 @@ class Trainer:
         params = [p for p in solver.parameters() if p.requires_grad]
         reducer = parallel.FlatGradAllReduce(params, n_scalars=1)
         closure_based = isinstance(optimizer, torch.optim.LBFGS)
-        for step in range(self.max_steps):
+        first = 0
+        if (self.cuda_graph and self.device.type == "cuda" and not closure_based and not schedulers
+                and isinstance(optimizer, optim.Adam)):
+            first = self._fit_graphed(solver, optimizer, reducer, size)
+        for step in range(first, self.max_steps):
             def closure():
                 optimizer.zero_grad(set_to_none=True)
                 loss = solver.training_step(None, step)
