@@ -253,3 +253,59 @@ def test_convective_equals_batched_matrix_product():
     j = tp.utils.jac(u, x)
     want = torch.bmm(j, v.unsqueeze(2)).squeeze(2)
     assert got.shape == (50, 3) and torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+class _ToySolver(torch.nn.Module):
+    """the slice of tp.solver.Solver that Trainer.fit drives, on CPU tensors (no native kernels involved)"""
+
+    def __init__(self, seed):
+        super().__init__()
+        torch.manual_seed(seed)                       # every rank builds DIFFERENT initial weights on purpose
+        self.net = torch.nn.Linear(3, 1)
+        self.register_buffer("shift", torch.full((1,), float(seed)))
+        self.n_training_step = 0
+
+    def on_train_start(self):
+        pass
+
+    def configure_optimizers(self):
+        return torch.optim.SGD(self.parameters(), lr=0.05)
+
+    def training_step(self, batch=None, idx=None):
+        from torchphysics_b200 import parallel
+        rank, _ = parallel.world()
+        g = torch.Generator().manual_seed(100 + rank)                 # every rank owns its own batch
+        x = torch.rand(16, 3, generator=g)
+        return ((self.net(x) - x.sum(dim=1, keepdim=True)) ** 2).mean()
+
+
+def _ddp_worker(rank, size, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from torchphysics_b200 import solver
+    s = _ToySolver(seed=rank + 1)
+    solver.Trainer(max_steps=5, device="cpu").fit(s)
+    # plain lists: a tensor in a Queue is shared through a file descriptor that dies with this process
+    out.put((rank, s.net.weight.detach().reshape(-1).tolist(), s.net.bias.detach().tolist(), float(s.shift)))
+    dist.destroy_process_group()
+
+
+def test_trainer_broadcasts_rank0_state_gloo_world2():
+    """Data-parallel training starts every replica from rank 0's parameters and buffers (what Lightning DDP does for the
+    reference): ranks that built their models under different seeds hold identical weights after K steps."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    (_, w0, b0, s0), (_, w1, b1, s1) = res
+    assert w0 == w1 and b0 == b1
+    assert s0 == s1 == 1.0                                             # buffers follow rank 0 too
+    torch.manual_seed(1)
+    assert w0 != torch.nn.Linear(3, 1).weight.detach().reshape(-1).tolist()   # ... and they did train
