@@ -243,9 +243,11 @@ def test_native_adam_equals_torch_adam():
     assert isinstance(trainer.optimizer, tp.optim.Adam)
 
 
-def test_operator_on_a_function_of_the_model_output_fails_loudly():
-    """grad(x * u, x) through torch.autograd would silently miss du/dx (the native evaluation has no graph to the
-    coordinates): the operators refuse instead of returning a wrong derivative."""
+def test_operator_on_a_function_of_the_model_output():
+    """grad(x * u, x), laplacian(u * u, x): pointwise expressions of the model output carry derivative streams (product /
+    chain rule on the native streams, jets.ExprEvaluation) as in the reference, where they are ordinary autograd graphs; a
+    function that is NOT pointwise (torch.autograd would silently miss du/dx: the native evaluation has no graph to the
+    coordinates) is refused instead of returning a wrong derivative."""
     import torchphysics_b200 as tp
     from torchphysics_b200 import _lib
     X, U = tp.spaces.R2("x"), tp.spaces.R1("u")
@@ -253,14 +255,15 @@ def test_operator_on_a_function_of_the_model_output_fails_loudly():
     coords, pts = tp.spaces.Points(torch.rand(64, 2).cuda(), X).track_coord_gradients()
     u = model(pts).as_tensor
     x = coords["x"]
-    with pytest.raises(_lib.TpxError):
-        tp.utils.grad(x[:, :1] * u, x)
-    with pytest.raises(_lib.TpxError):
-        tp.utils.laplacian(u * u, x)
-    # the supported spelling of the same thing: operators on the model output, combined by the product rule
     g = tp.utils.grad(u, x)
-    want = torch.cat([u + x[:, :1] * g[:, :1], x[:, :1] * g[:, 1:]], dim=1)
-    assert want.shape == (64, 2)
+    want = torch.cat([u + x[:, :1] * g[:, :1], x[:, :1] * g[:, 1:]], dim=1)       # product rule by hand
+    got = tp.utils.grad(x[:, :1] * u, x)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)
+    lap_u = tp.utils.laplacian(u, x)
+    want2 = 2.0 * (g * g).sum(dim=1, keepdim=True) + 2.0 * u * lap_u            # Lap(u^2) = 2 |grad u|^2 + 2 u Lap u
+    assert torch.allclose(tp.utils.laplacian(u * u, x), want2, rtol=1e-4, atol=1e-5)
+    with pytest.raises(_lib.TpxError):
+        tp.utils.grad(torch.cumsum(u, dim=0), x)
 
 
 def test_hard_constraint_streams_by_chain_rule_match_reference():

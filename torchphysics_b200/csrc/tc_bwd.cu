@@ -29,6 +29,7 @@
 #include <cstring>
 
 #include "fcn_common.cuh"
+#include "f32x2.cuh"
 #include "tc_common.cuh"
 #include "tcp_common.cuh"
 #include "tc_kernels.h"
@@ -306,26 +307,42 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 
     // activation jets of a layer from its checkpoints (t, d_k z, L z) -> (a, d_k a, L a)
     auto jets = [&](const float (&c)[S][B_NW], float (&h)[S][B_NW]) {
+      if constexpr (ACT == 0) {              // tanh: neuron pairs in packed fp32 (f32x2.cuh), bit-identical to the scalar formulas
 #pragma unroll
-      for (int i = 0; i < B_NW; ++i) {
-        float t, s1, s2;
-        if constexpr (ACT == 0) {
-          t = c[0][i];
-          s1 = fmaf(-t, t, 1.0f);
-          s2 = -2.0f * t * s1;
-        } else {
+        for (int i = 0; i < B_NW; i += 2) {
+          const F2 t = f2(c[0][i], c[0][i + 1]);
+          const F2 s1 = fma2(neg(t), t, f2(1.0f));
+          const F2 s2 = (f2(-2.0f) * t) * s1;
+          h[0][i] = t.v.x; h[0][i + 1] = t.v.y;
+          F2 qq = f2(0.0f);
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            const F2 dz = f2(c[1 + k][i], c[1 + k][i + 1]);
+            if (LAP) qq = fma2(f2(lapw[k]) * dz, dz, qq);
+            const F2 hk = s1 * dz;
+            h[1 + k][i] = hk.v.x; h[1 + k][i + 1] = hk.v.y;
+          }
+          if (LAP) {
+            const F2 hl = fma2(s2, qq, s1 * f2(c[S - 1][i], c[S - 1][i + 1]));
+            h[S - 1][i] = hl.v.x; h[S - 1][i + 1] = hl.v.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < B_NW; ++i) {
+          float t, s1, s2;
           sincosf(c[0][i], &t, &s1);
           s2 = -t;
-        }
-        h[0][i] = t;
-        float qq = 0.0f;
+          h[0][i] = t;
+          float qq = 0.0f;
 #pragma unroll
-        for (int k = 0; k < ND; ++k) {
-          const float dz = c[1 + k][i];
-          if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
-          h[1 + k][i] = s1 * dz;
+          for (int k = 0; k < ND; ++k) {
+            const float dz = c[1 + k][i];
+            if (LAP) qq = fmaf(lapw[k] * dz, dz, qq);
+            h[1 + k][i] = s1 * dz;
+          }
+          if (LAP) h[S - 1][i] = fmaf(s2, qq, s1 * c[S - 1][i]);
         }
-        if (LAP) h[S - 1][i] = fmaf(s2, qq, s1 * c[S - 1][i]);
       }
     };
     auto load_ck = [&](const float* ck_tile, int l, float (&c)[S][B_NW]) {
@@ -338,36 +355,60 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 
     // adjoints of the pre-activation streams of a layer from the adjoints of its activation streams (thread-local)
     auto zbar = [&](const float (&c)[S][B_NW], const float (&ga)[S][B_NW], float (&zb)[S][B_NW]) {
+      if constexpr (ACT == 0) {              // tanh: neuron pairs in packed fp32, bit-identical to the scalar formulas below
 #pragma unroll
-      for (int i = 0; i < B_NW; ++i) {
-        float t, s1, s2;
-        if constexpr (ACT == 0) {
-          t = c[0][i];
-          s1 = fmaf(-t, t, 1.0f);
-          s2 = -2.0f * t * s1;
-        } else {
+        for (int i = 0; i < B_NW; i += 2) {
+          const F2 t = f2(c[0][i], c[0][i + 1]);
+          const F2 s1 = fma2(neg(t), t, f2(1.0f));
+          const F2 s2 = (f2(-2.0f) * t) * s1;
+          F2 v0 = f2(ga[0][i], ga[0][i + 1]) * s1, qq = f2(0.0f);
+          const F2 gl = LAP ? f2(ga[S - 1][i], ga[S - 1][i + 1]) : f2(0.0f);
+#pragma unroll
+          for (int k = 0; k < ND; ++k) {
+            const F2 dz = f2(c[1 + k][i], c[1 + k][i + 1]);
+            const F2 gk = f2(ga[1 + k][i], ga[1 + k][i + 1]);
+            v0 = fma2(gk * s2, dz, v0);
+            F2 vk = gk * s1;
+            if (LAP) {
+              qq = fma2(f2(lapw[k]) * dz, dz, qq);
+              vk = fma2((f2(2.0f * lapw[k]) * gl) * s2, dz, vk);
+            }
+            zb[1 + k][i] = vk.v.x; zb[1 + k][i + 1] = vk.v.y;
+          }
+          if (LAP) {
+            const F2 s3 = (f2(-2.0f) * s1) * fma2(f2(-3.0f) * t, t, f2(1.0f));
+            v0 = fma2(gl, fma2(s3, qq, s2 * f2(c[S - 1][i], c[S - 1][i + 1])), v0);
+            const F2 zl = gl * s1;
+            zb[S - 1][i] = zl.v.x; zb[S - 1][i + 1] = zl.v.y;
+          }
+          zb[0][i] = v0.v.x; zb[0][i + 1] = v0.v.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < B_NW; ++i) {
+          float t, s1, s2;
           sincosf(c[0][i], &t, &s1);
           s2 = -t;
-        }
-        float v0 = ga[0][i] * s1, qq = 0.0f;
-        const float gl = LAP ? ga[S - 1][i] : 0.0f;
+          float v0 = ga[0][i] * s1, qq = 0.0f;
+          const float gl = LAP ? ga[S - 1][i] : 0.0f;
 #pragma unroll
-        for (int k = 0; k < ND; ++k) {
-          const float dz = c[1 + k][i];
-          v0 = fmaf(ga[1 + k][i] * s2, dz, v0);
-          float vk = ga[1 + k][i] * s1;
-          if (LAP) {
-            qq = fmaf(lapw[k] * dz, dz, qq);
-            vk = fmaf(2.0f * lapw[k] * gl * s2, dz, vk);
+          for (int k = 0; k < ND; ++k) {
+            const float dz = c[1 + k][i];
+            v0 = fmaf(ga[1 + k][i] * s2, dz, v0);
+            float vk = ga[1 + k][i] * s1;
+            if (LAP) {
+              qq = fmaf(lapw[k] * dz, dz, qq);
+              vk = fmaf(2.0f * lapw[k] * gl * s2, dz, vk);
+            }
+            zb[1 + k][i] = vk;
           }
-          zb[1 + k][i] = vk;
+          if (LAP) {
+            const float s3 = -s1;
+            v0 = fmaf(gl, fmaf(s3, qq, s2 * c[S - 1][i]), v0);
+            zb[S - 1][i] = gl * s1;
+          }
+          zb[0][i] = v0;
         }
-        if (LAP) {
-          const float s3 = (ACT == 0) ? -2.0f * s1 * fmaf(-3.0f * t, t, 1.0f) : -s1;
-          v0 = fmaf(gl, fmaf(s3, qq, s2 * c[S - 1][i]), v0);
-          zb[S - 1][i] = gl * s1;
-        }
-        zb[0][i] = v0;
       }
     };
     // in: adjoint product of the previous step, rows of this warp's stream -> exchange buffer -> all streams of
@@ -418,10 +459,11 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
           hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
         }
 #pragma unroll
-        for (int i = 0; i < B_CH; ++i) {
-          const float h = tf32_hi(hi[i]);
-          lo[i] = hi[i] - h;
-          hi[i] = h;
+        for (int i = 0; i < B_CH; i += 2) {
+          const float h0 = tf32_hi(hi[i]), h1 = tf32_hi(hi[i + 1]);
+          const F2 l = fma2(f2(-1.0f), f2(h0, h1), f2(hi[i], hi[i + 1]));      // x - hi, exact
+          lo[i] = l.v.x; lo[i + 1] = l.v.y;
+          hi[i] = h0; hi[i + 1] = h1;
         }
         tmem_st16(tAh + jc, hi);
         tmem_st16(tAl + jc, lo);
@@ -448,13 +490,19 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
 #pragma unroll
       for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int i = 0; i < B_NW; ++i) {
-          const float zh = tf32_hi(zb[s][i]);
-          Zt[s * 4096 + i * 32 + xo[i]] = zh;
-          Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zb[s][i] - zh;
-          const float ah = tf32_hi(ap[s][i]);
-          At[s * 4096 + i * 32 + xo[i]] = ah;
-          At[s * 4096 + (64 + i) * 32 + xo[i]] = ap[s][i] - ah;
+        for (int i = 0; i < B_NW; i += 2) {
+          const float zh0 = tf32_hi(zb[s][i]), zh1 = tf32_hi(zb[s][i + 1]);
+          const F2 zl = fma2(f2(-1.0f), f2(zh0, zh1), f2(zb[s][i], zb[s][i + 1]));       // x - hi, exact
+          Zt[s * 4096 + i * 32 + xo[i]] = zh0;
+          Zt[s * 4096 + (i + 1) * 32 + xo[i + 1]] = zh1;
+          Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zl.v.x;
+          Zt[s * 4096 + (64 + i + 1) * 32 + xo[i + 1]] = zl.v.y;
+          const float ah0 = tf32_hi(ap[s][i]), ah1 = tf32_hi(ap[s][i + 1]);
+          const F2 al = fma2(f2(-1.0f), f2(ah0, ah1), f2(ap[s][i], ap[s][i + 1]));
+          At[s * 4096 + i * 32 + xo[i]] = ah0;
+          At[s * 4096 + (i + 1) * 32 + xo[i + 1]] = ah1;
+          At[s * 4096 + (64 + i) * 32 + xo[i]] = al.v.x;
+          At[s * 4096 + (64 + i + 1) * 32 + xo[i + 1]] = al.v.y;
         }
       dw_pending = true;
       TPX_STAMP(6);

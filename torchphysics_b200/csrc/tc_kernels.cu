@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "fcn_common.cuh"
+#include "f32x2.cuh"
 #include "tc_common.cuh"
 #include "tc_kernels.h"
 #include "tc_layout.cuh"
@@ -306,19 +307,49 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
         }
         // ---- compute: thread-local jets of 8 neurons (all streams of this point)
         float* ckl = a.ckpt ? a.ckpt + ((size_t)tile * L + l) * (4 * HP * TILE) + jw * TILE + lane : nullptr;
+        if constexpr (ACT == 0) {
+          // tanh: neuron pairs in packed fp32 (f32x2.cuh): the same operations as the scalar path, two per instruction
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            const float x0 = z[0][i], x1 = z[0][i + 1];
+            float e0, e1, r0, r1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fabsf(x0) * -2.885390081777927f));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fabsf(x1) * -2.885390081777927f));
+            const F2 e = f2(e0, e1);
+            const F2 d = e + f2(1.0f);
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.v.x));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.v.y));
+            F2 r = f2(r0, r1);
+            r = r * fma2(neg(d), r, f2(2.0f));
+            const F2 ta = (f2(1.0f) + neg(e)) * r;
+            const F2 t = f2(copysignf(ta.v.x, x0), copysignf(ta.v.y, x1));
+            const F2 s1 = fma2(neg(t), t, f2(1.0f));
+            const F2 s2 = (f2(-2.0f) * t) * s1;
+            z[0][i] = t.v.x; z[0][i + 1] = t.v.y;
+            if (ckl) { __stcs(ckl + (0 * HP + i) * TILE, t.v.x); __stcs(ckl + (0 * HP + i + 1) * TILE, t.v.y); }
+            F2 qq = f2(0.0f);
+#pragma unroll
+            for (int k = 0; k < ND; ++k) {
+              const F2 dz = f2(z[1 + k][i], z[1 + k][i + 1]);
+              if (LAP) qq = fma2(f2(lapw[k]) * dz, dz, qq);
+              const F2 a = s1 * dz;
+              z[1 + k][i] = a.v.x; z[1 + k][i + 1] = a.v.y;
+              if (ckl) { __stcs(ckl + ((1 + k) * HP + i) * TILE, dz.v.x); __stcs(ckl + ((1 + k) * HP + i + 1) * TILE, dz.v.y); }
+            }
+            if (LAP) {
+              const F2 lz = f2(z[S - 1][i], z[S - 1][i + 1]);
+              const F2 a = fma2(s2, qq, s1 * lz);
+              z[S - 1][i] = a.v.x; z[S - 1][i + 1] = a.v.y;
+              if (ckl) { __stcs(ckl + ((S - 1) * HP + i) * TILE, lz.v.x); __stcs(ckl + ((S - 1) * HP + i + 1) * TILE, lz.v.y); }
+            }
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float t, s1, s2, keep;           // activation, its first two derivatives, what the reverse sweep keeps
-          if constexpr (ACT == 0) {
-            t = tanh_fast(z[0][i]);
-            s1 = fmaf(-t, t, 1.0f);
-            s2 = -2.0f * t * s1;
-            keep = t;
-          } else {
-            keep = z[0][i];
-            sincosf(keep, &t, &s1);
-            s2 = -t;
-          }
+          keep = z[0][i];
+          sincosf(keep, &t, &s1);
+          s2 = -t;
           z[0][i] = t;
           if (ckl) __stcs(ckl + (0 * HP + i) * TILE, keep);
           float qq = 0.0f;
@@ -334,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
             z[S - 1][i] = fmaf(s2, qq, s1 * lz);
             if (ckl) __stcs(ckl + ((S - 1) * HP + i) * TILE, lz);
           }
+        }
         }
         TPX_FSTAMP(3);
         if (!last) {
@@ -355,10 +387,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
                 hi[4 * v] = w4.x; hi[4 * v + 1] = w4.y; hi[4 * v + 2] = w4.z; hi[4 * v + 3] = w4.w;
               }
 #pragma unroll
-              for (int i = 0; i < CH; ++i) {
-                const float h = tf32_hi(hi[i]);
-                lo[i] = hi[i] - h;
-                hi[i] = h;
+              for (int i = 0; i < CH; i += 2) {
+                const float h0 = tf32_hi(hi[i]), h1 = tf32_hi(hi[i + 1]);
+                const F2 l = fma2(f2(-1.0f), f2(h0, h1), f2(hi[i], hi[i + 1]));      // x - hi, exact
+                lo[i] = l.v.x; lo[i + 1] = l.v.y;
+                hi[i] = h0; hi[i + 1] = h1;
               }
               tmem_st16(tAh + j0 + c * CH, hi);
               tmem_st16(tAl + j0 + c * CH, lo);
