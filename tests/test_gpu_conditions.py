@@ -524,3 +524,36 @@ def test_trainer_replays_the_whole_step_as_one_cuda_graph():
     assert abs(tail_g - tail_e) < 0.5 * tail_e                 # same training up to the sampling noise
     st = graphed.optimizer.state[next(iter(graphed.optimizer.state))]
     assert int(st["step"]) == 150
+
+
+def test_micro_batched_condition_equals_the_single_batch(monkeypatch):
+    """A batch whose checkpoints exceed the HBM budget is evaluated slice by slice (forward saving -> reverse per slice,
+    gradients accumulated): same loss and dLoss/dtheta as the batch in one piece."""
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import conditions, engine
+    G = load("heat_3x128")
+    X, T, U = tp.spaces.R2("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
+    model = tp.models.FCN(X * T, U, hidden=(128,) * 3).cuda()
+    _load_params(model, G["params"])
+    pts = torch.rand(3001, 3)
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(pts, X * T))
+    cond = tp.conditions.PINNCondition(model, sampler, lambda u, x, t: tp.utils.grad(u, t) - tp.utils.laplacian(u, x))
+
+    def run():
+        out = None
+        for _ in range(2):                        # the first call learns the jet spec
+            model.zero_grad(set_to_none=True)
+            loss = cond(device="cuda")
+            loss.backward()
+            out = (float(loss.detach()), [None if p.grad is None else p.grad.clone() for p in model.parameters()])
+        return out
+
+    loss1, g1 = run()
+    monkeypatch.setattr(engine, "save_budget_bytes", lambda device: 4 << 20)          # forces ~5 slices
+    assert cond._micro_batches(sampler.sample_points(device="cuda")) > 1
+    loss2, g2 = run()
+    assert abs(loss1 - loss2) < 1e-6 * abs(loss1)
+    for a, b in zip(g1, g2):
+        assert (a is None) == (b is None)                 # the output bias keeps grad None (reference parity)
+        if a is not None:
+            assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())

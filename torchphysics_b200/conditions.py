@@ -54,6 +54,35 @@ class _SquaredErrorMean(torch.autograd.Function):
         return gr
 
 
+class _MicroBatchedLoss(torch.autograd.Function):
+    """loss of a condition with a mean reduction as the weighted sum over row slices of the batch, each slice taken through
+    forward (saving its checkpoints) and reverse before the next one starts; the parameter gradients are accumulated here and
+    handed to autograd in ``backward`` (scaled by the incoming adjoint)."""
+
+    @staticmethod
+    def forward(ctx, cond, x, chunks, *params):
+        n = len(x)
+        bounds = [round(i * n / chunks) for i in range(chunks + 1)]
+        total, grads = None, [None] * len(params)
+        with torch.enable_grad():
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                if hi == lo:
+                    continue
+                part = cond._loss_on(x[lo:hi]) * ((hi - lo) / n)
+                gs = torch.autograd.grad(part, params, allow_unused=True)
+                for i, g in enumerate(gs):
+                    if g is not None:
+                        grads[i] = g if grads[i] is None else grads[i] + g
+                total = part.detach() if total is None else total + part.detach()
+        ctx.grads = grads
+        return total
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        return (None, None, None) + tuple(None if gr is None else gr * g for gr in ctx.grads)
+
+
 def _fusable_residual(r):
     # (a 1-D residual is not a batch of rows for SquaredError: torch.sum(., dim=[]) reduces everything)
     return (isinstance(r, torch.Tensor) and r.is_cuda and r.dtype == torch.float32 and r.dim() >= 2 and r.numel() > 0
@@ -112,6 +141,35 @@ class SingleModuleCondition(Condition):
             self.last_unreduced_loss = None
         else:
             x = self.sampler.sample_points(device=device)
+        chunks = self._micro_batches(x)
+        if chunks > 1:
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _MicroBatchedLoss.apply(self, x, chunks, *params)
+        return self._loss_on(x)
+
+    def _micro_batches(self, x):
+        """how many slices the batch is evaluated in.  A batch whose activation-jet checkpoints do not fit the HBM budget
+        would otherwise run forward -> (recompute forward in chunks -> reverse): one forward sweep too many.  With a mean
+        reduction the loss is the weighted sum of the slices' losses, so each slice runs forward (saving) -> reverse on its
+        own and the gradients add up (``_MicroBatchedLoss``): two sweeps per point instead of three."""
+        if self.sampler.is_adaptive or self.reduce_fn is not torch.mean or not torch.is_grad_enabled():
+            return 1
+        t = x.as_tensor
+        eng_of = getattr(self.module, "_native_engine", None)
+        if not t.is_cuda or t.dim() != 2 or eng_of is None:
+            return 1
+        spec = getattr(self.module, "_jet_hints", {}).get(id(self))
+        eng = eng_of()
+        if spec is None or eng is False:
+            return 1
+        from .engine import save_budget_bytes
+        need = eng.saved_bytes(spec, t.shape[0])
+        budget = save_budget_bytes(t.device)
+        if need == 0 or need <= budget:
+            return 1
+        return min(int(-(-need // max(budget // 2, 1))), 64)
+
+    def _loss_on(self, x):
         x_coordinates, x = x.track_coord_gradients()
         data = {}
         for name in self.data_functions:
