@@ -318,3 +318,23 @@ def union_boundary_normal(A, B, pts):
     with np.errstate(invalid="ignore", divide="ignore"):
         na, nb = boundary_normal(("boundary", A), pts), boundary_normal(("boundary", B), pts)
     return np.where(on_a[:, None], na, nb)
+
+
+# boundary of an intersection A & B of two primitives (domainoperations/intersection.py:112-206)
+def intersection_boundary_contains(A, B, pts):
+    pts = np.asarray(pts, f32)
+    on_a, on_b = boundary_contains(("boundary", A), pts), boundary_contains(("boundary", B), pts)
+    return (on_a & contains(B, pts)) | (on_b & contains(A, pts))
+
+
+def intersection_boundary_normal(A, B, pts):
+    """normal of A where the point lies on A's boundary, the normal of B elsewhere (intersection.py:197-206); the
+    same selection as for a union"""
+    return union_boundary_normal(A, B, pts)
+
+
+def intersection_boundary_grid_d(A, B, d):
+    """density grid (intersection.py:185-196): both boundary grids at density d, each kept inside the other domain"""
+    ga = boundary_grid(("boundary", A), int(np.ceil(f32(d) * boundary_volume(("boundary", A)))))      # domain.py:273-287
+    gb = boundary_grid(("boundary", B), int(np.ceil(f32(d) * boundary_volume(("boundary", B)))))
+    return np.concatenate([ga[contains(B, ga)], gb[contains(A, gb)]])

@@ -347,6 +347,42 @@ def union_boundary():
     save("union_boundary", **out)
 
 
+# ---------------------------------------------------------------------------- boundary of an intersection
+def intersection_boundary():
+    """boundary of Parallelogram & Circle (a lens) and of a Circle & axis-aligned square (reference
+    domainoperations/intersection.py:112-206, sampler_helper.py:129-266)."""
+    X = tp.spaces.R2("x")
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    bite = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    sq = tp.domains.Parallelogram(X, [0.0, -0.5], [1.5, -0.5], [0.0, 1.0])
+    out = {}
+    g = torch.Generator().manual_seed(51)
+    for nm, dom in (("lens", para & bite), ("corner", circ & sq)):
+        b = dom.boundary
+        ga = dom.domain_a.boundary.sample_grid(150).as_tensor
+        gb = dom.domain_b.boundary.sample_grid(150).as_tensor
+        on = torch.cat([ga, gb], dim=0)
+        far = torch.rand(300, 2, generator=g) * 3.0 - 1.5
+        cand = torch.cat([on, on + (torch.rand(on.shape, generator=g) * 4e-5 - 2e-5), far], dim=0)
+        inside = b._contains(tp.spaces.Points(cand.clone(), X)).reshape(-1)
+        out["cand_" + nm], out["in_" + nm] = cand, inside
+        onb = cand[inside]
+        out["on_" + nm] = onb
+        out["normal_" + nm] = b.normal(tp.spaces.Points(onb.clone(), X))
+        out["vol_" + nm] = b.volume().reshape(-1)
+        for n in (40, 200):
+            torch.manual_seed(52)
+            gr = b.sample_grid(n)
+            out[f"ngrid_{nm}_{n}"] = np.array(len(gr))
+            out[f"grid_{nm}_{n}"] = gr.as_tensor
+        torch.manual_seed(53)
+        out["n_random_" + nm] = np.array(len(b.sample_random_uniform(n=500)))
+        out["n_grid_d_" + nm] = np.array(len(b.sample_grid(d=30.0)))
+        out["grid_d_" + nm] = b.sample_grid(d=30.0).as_tensor
+    save("intersection_boundary", **out)
+
+
 # ---------------------------------------------------------------------------- hard constraint (SURVEY f3)
 def poisson_hard_constraint(hidden, n, name):
     """Poisson residual on tp.models.HardConstraint(FCN, g): the output transform g(u, x) = x1 (1 - x1) x2 (1 - x2) u
@@ -435,6 +471,7 @@ if __name__ == "__main__":
         "boundaries": boundaries,
         "cut_boundary": cut_boundary,
         "union_boundary": union_boundary,
+        "intersection_boundary": intersection_boundary,
         # hidden width 128 (configs 2 and 3 of BASELINE.json at reduced depth): the wide tensor-core path
         "heat_3x128": lambda: heat((128, 128, 128), 211, "heat_3x128"),
         "ns_3x128": lambda: navier_stokes((128, 128, 128), 147, "ns_3x128"),

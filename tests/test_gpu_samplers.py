@@ -372,6 +372,72 @@ def test_cut_boundary_matches_reference():
     assert torch.isfinite(loss)
 
 
+def test_intersection_boundary_matches_reference():
+    """boundary of A & B (a lens, and a disc clipped by a square): membership bit for bit, normals, volume, grid / random
+    counts and the density grid point for point (reference intersection.py:112-206)."""
+    import warnings
+    import torchphysics_b200 as tp
+    from tests.test_oracle_golden import INTERSECTIONS
+    G = load("intersection_boundary")
+    X = tp.spaces.R2("x")
+    para = tp.domains.Parallelogram(X, [-0.25, -0.5], [0.75, -0.25], [0.0, 0.6])
+    bite = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    sq = tp.domains.Parallelogram(X, [0.0, -0.5], [1.5, -0.5], [0.0, 1.0])
+    for nm, dom in (("lens", para & bite), ("corner", circ & sq)):
+        A, B = INTERSECTIONS[nm]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            b = dom.boundary
+            cand = tp.spaces.Points(torch.from_numpy(G["cand_" + nm]).cuda(), X)
+            assert np.array_equal(b._contains(cand).reshape(-1).cpu().numpy(), G["in_" + nm]), nm
+            assert abs(float(b.volume()) - float(G["vol_" + nm][0])) < 1e-5
+            nrm = b.normal(tp.spaces.Points(torch.from_numpy(G["on_" + nm]).cuda(), X)).cpu().numpy()
+            assert np.allclose(nrm, G["normal_" + nm], rtol=1e-6, atol=1e-7), nm
+            for n in (40, 200):
+                g = b.sample_grid(n, device="cuda").as_tensor.cpu().numpy()
+                assert len(g) == int(G[f"ngrid_{nm}_{n}"]) == n
+                if nm == "corner":               # axis-aligned clip: the reference keeps its own grid points exactly
+                    assert np.allclose(g, G[f"grid_{nm}_{n}"], rtol=1e-6, atol=1e-6)
+            torch.manual_seed(11)
+            p = b.sample_random_uniform(n=3000, device="cuda").as_tensor.cpu().numpy()
+            assert len(p) == 3000
+            assert geometry.intersection_boundary_contains(A, B, p).mean() > 0.97
+            d = b.sample_grid(d=30.0, device="cuda").as_tensor.cpu().numpy()
+            assert len(d) == int(G["n_grid_d_" + nm])
+            assert np.allclose(d, G["grid_d_" + nm], rtol=1e-6, atol=1e-6)
+            r = b.sample_random_uniform(d=50.0, device="cuda")
+            assert 0 < len(r) <= int(np.ceil(50.0 * float(b.volume()))) + 2
+
+
+def test_product_boundary_is_the_union_of_the_two_faces():
+    """(A x B).boundary = (dA x B) + (A x dB) (reference product.py:100-106): every point lies on one of the two faces,
+    the faces are drawn in proportion to their volumes, membership agrees with the oracle's shape tests."""
+    import warnings
+    import torchphysics_b200 as tp
+    X, T = tp.spaces.R2("x"), tp.spaces.R1("t")
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    ival = tp.domains.Interval(T, -0.3, 0.8)
+    A, B = ("circle", [0.1, -0.2], 0.9), ("interval", -0.3, 0.8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        b = (circ * ival).boundary
+        assert b.space == X * T
+        vol_side, vol_caps = 2 * np.pi * 0.9 * 1.1, np.pi * 0.81 * 2.0
+        assert abs(float(b.volume()) - (vol_side + vol_caps)) < 1e-4
+        torch.manual_seed(5)
+        pts = b.sample_random_uniform(n=6000, device="cuda")
+        assert len(pts) == 6000 and pts.space == X * T
+        p = pts.as_tensor.cpu().numpy()
+        side = geometry.boundary_contains(("boundary", A), p[:, :2]) & geometry.contains(B, p[:, 2:])
+        caps = geometry.contains(A, p[:, :2]) & geometry.boundary_contains(("boundary", B), p[:, 2:])
+        assert (side | caps).all()
+        assert abs(side.mean() - vol_side / (vol_side + vol_caps)) < 0.03
+        assert b._contains(pts).all()
+        off = tp.spaces.Points(torch.tensor([[0.1, -0.2, 0.2], [3.0, 0.0, 0.8]], device="cuda"), X * T)
+        assert not b._contains(off).any()
+
+
 def test_union_boundary_matches_reference():
     """boundary of A + B: overlapping shapes and two squares sharing an edge (normal-agreement test of reference
     union.py:161-192): membership bit for bit, normals, volume, counts."""

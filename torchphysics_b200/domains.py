@@ -589,7 +589,7 @@ class CutDomain(_BooleanDomain):
             self.domain_a._fill_random(cand, col, int(m))
             keep = ~self.domain_b._contains_rows(cand, col, out.device)
             good = self._select(cand, keep, n - filled)
-            out[filled:filled + len(good), col:col + self.dim] = good[:, col:col + self.dim]
+            out[filled:filled + len(good), col:col + self.space.dim] = good[:, col:col + self.space.dim]
             got = len(good)
             filled += got
             m = 5 * m if got == 0 else int(m * (n - filled) / got * 1.1) + 16
@@ -612,7 +612,7 @@ class CutDomain(_BooleanDomain):
         a = self._select(a, ~self.domain_b._contains_rows(a, 0, dev))
         if len(a) >= n:
             return a[:n]
-        extra = torch.empty((n - len(a), self.dim), dtype=torch.float32, device=dev)
+        extra = torch.empty((n - len(a), self.space.dim), dtype=torch.float32, device=dev)
         self._fill_random(extra, 0, n - len(a))
         return torch.cat([a, extra], dim=0)
 
@@ -810,6 +810,42 @@ class UnionBoundaryDomain(CutBoundaryDomain):
         return torch.where(a._contains(points), a.normal(points), b.normal(points))
 
 
+class IntersectionBoundaryDomain(CutBoundaryDomain):
+    """Boundary of ``A & B`` for two basic shapes (reference ``domainoperations/intersection.py:112-206``): the part of A's
+    boundary inside B plus the part of B's boundary inside A.  Same machinery as the boundary of a cut: one region program
+    over the boundary shapes, random points alternating between the two boundaries with rejection by that program."""
+
+    def _program(self, col):
+        a, b = self.domain.domain_a, self.domain.domain_b
+        S, AND, OR = _lib.TPX_OP_SHAPE, _lib.TPX_OP_AND, _lib.TPX_OP_OR
+        shapes = [a.boundary._shape(col), b._shape(col), b.boundary._shape(col), a._shape(col)]
+        # (on dA and in B) or (on dB and in A)
+        ops = [S | (0 << 8), S | (1 << 8), AND, S | (2 << 8), S | (3 << 8), AND, OR]
+        return shapes, ops
+
+    def _get_volume(self):
+        warnings.warn("Exact volume of this intersection-boundary is not known, will use the estimate: volume = boundary_a + "
+                      "boundary_b. If you need the exact volume for sampling, use domain.set_volume()")
+        return _F32(self.domain.domain_a.boundary._volume_value()) + _F32(self.domain.domain_b.boundary._volume_value())
+
+    def _parts_with_d(self, sample, d, params, device):
+        """density mode (intersection.py:150-163 / 185-196): both boundaries at density d, each kept inside the other domain"""
+        dev = _compute_device(device)
+        a, b = self.domain.domain_a, self.domain.domain_b
+        pa = sample(a.boundary, d, dev).as_tensor
+        pa = self._masked(pa, b._contains_rows(pa, 0, dev))
+        pb = sample(b.boundary, d, dev).as_tensor
+        pb = self._masked(pb, a._contains_rows(pb, 0, dev))
+        return Points(torch.cat([pa, pb], dim=0).to(device), self.space)
+
+    def normal(self, points, params=Points.empty(), device="cpu"):
+        if not isinstance(points, Points):
+            points = Points(points, self.space)
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+        on_a = a._contains(points)
+        return torch.where(on_a, a.normal(points), b.normal(points))
+
+
 class IntersectionDomain(_BooleanDomain):
     """domain_a and domain_b (reference ``domainoperations/intersection.py:14-109``)."""
 
@@ -856,7 +892,7 @@ class IntersectionDomain(_BooleanDomain):
         a = self._select(a, self.domain_b._contains_rows(a, 0, dev))
         if len(a) >= n:
             return a[:n]
-        extra = torch.empty((n - len(a), self.dim), dtype=torch.float32, device=dev)
+        extra = torch.empty((n - len(a), self.space.dim), dtype=torch.float32, device=dev)
         self._fill_random(extra, 0, n - len(a))
         return torch.cat([a, extra], dim=0)
 
@@ -908,7 +944,7 @@ class UnionDomain(_BooleanDomain):
                                              ctypes.c_int32(stride), ctypes.c_int32(stride), ctypes.c_float(ratio),
                                              ctypes.c_uint64(_rng.next_key()), ctypes.c_uint64(0), _lib.ptr(tmp),
                                              _lib.stream_ptr()))
-        out[:n, col:col + self.dim] = tmp[:, col:col + self.dim]
+        out[:n, col:col + self.space.dim] = tmp[:, col:col + self.space.dim]
 
     def _append(self, ta, tb):
         keep = ~self.domain_a._contains_rows(tb, 0, tb.device)
@@ -980,6 +1016,10 @@ class ProductDomain(Domain):
 
 
 UnionDomain.boundary = property(lambda self: UnionBoundaryDomain(self))
+IntersectionDomain.boundary = property(lambda self: IntersectionBoundaryDomain(self))
+# product.py:100-106: (dA x B) + (A x dB), no normals
+ProductDomain.boundary = property(lambda self: UnionDomain(ProductDomain(self.domain_a.boundary, self.domain_b),
+                                                           ProductDomain(self.domain_a, self.domain_b.boundary)))
 
 
 # function sets / function samplers live in the same namespaces as in the reference
