@@ -150,6 +150,11 @@ CASES = [
     # ... and on the wide path (csrc/tcw_sin.cu)
     (2, 1, (128,) * 3, "sin", (0, 1), (1.0, 1.0), 1000),
     (3, 2, (200, 256, 130), "sin", (0, 1, 2), (1.0, 1.0, 0.0), 1000),
+    # narrow but deeper than the resident-weight kernels hold (> 5 hidden layers): one zero-padded 128-neuron block per
+    # layer on the wide path instead of the FP32 CUDA-core kernels
+    (2, 1, (64,) * 6, "tanh", (0, 1), (1.0, 1.0), 3000),
+    (3, 2, (20,) * 8, "tanh", (0, 1, 2), (1.0, 1.0, 0.0), 500),
+    (2, 1, (50,) * 7, "sin", (0, 1), (1.0, 1.0), 1000),
 ]
 
 

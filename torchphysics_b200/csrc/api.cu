@@ -42,7 +42,10 @@ static int make_layout(const tpx_fcn_desc* net, Layout* lay) {
     if (net->widths[l] < 1) return fail(TPX_E_ARG, "width[%d]=%d", l, net->widths[l]);
     if (net->widths[l] > wmax) wmax = net->widths[l];
   }
-  const int hp = pad_width(wmax);
+  int hp = pad_width(wmax);
+  // narrow nets with more hidden matrices than the resident-weight kernels hold run on the layer-major tensor-core
+  // kernels as one zero-padded 128-neuron block per layer
+  if (hp > 0 && hp < 128 && tcw_takes_narrow(net)) hp = 128;
   if (hp < 0) return fail(TPX_E_UNSUPPORTED, "hidden width %d > %d", wmax, TPX_MAX_WIDTH);
   lay->L = net->n_hidden;
   lay->HP = hp;

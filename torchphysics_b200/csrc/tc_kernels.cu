@@ -455,9 +455,8 @@ using namespace tc;
 
 long long* g_tc_debug = nullptr;
 
-bool tc_net_supported(const tpx_fcn_desc* net) {
-  static const int disabled = env_flag("TPX_DISABLE_TC");
-  if (disabled) return false;
+// shape test only (no debug switch): the packed layout depends on it
+bool tc_net_fits(const tpx_fcn_desc* net) {
   if (net->activation != TPX_ACT_TANH && net->activation != TPX_ACT_SIN) return false;
   if (net->n_hidden < 2) return false;                 // needs at least one hidden x hidden product
   for (int l = 0; l < net->n_hidden; ++l)
@@ -467,6 +466,11 @@ bool tc_net_supported(const tpx_fcn_desc* net) {
   const TcLayout lay{net->n_hidden, net->d_in, net->d_out};
   if ((size_t)fwd_smem(lay).total * sizeof(float) + 1024 > 227 * 1024) return false;
   return true;
+}
+
+bool tc_net_supported(const tpx_fcn_desc* net) {
+  static const int disabled = env_flag("TPX_DISABLE_TC");
+  return !disabled && tc_net_fits(net);
 }
 
 bool tc_supported(const tpx_fcn_desc* net, int nd, int lap) {

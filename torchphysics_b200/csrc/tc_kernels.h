@@ -9,6 +9,8 @@
 
 namespace tpx {
 bool tc_net_supported(const tpx_fcn_desc* net);                 // network shape has a tensor-core kernel
+bool tc_net_fits(const tpx_fcn_desc* net);                      // ... its shape part (no debug switch)
+bool tcw_takes_narrow(const tpx_fcn_desc* net);                 // narrow but too deep for tc: one padded 128-neuron block on tcw
 bool tc_supported(const tpx_fcn_desc* net, int nd, int lap);    // ... and so has this jet
 size_t tc_packed_floats(const tpx_fcn_desc* net);
 int tc_pack(const tpx_fcn_desc* net, const void* const* params_host, float* img, cudaStream_t stream);

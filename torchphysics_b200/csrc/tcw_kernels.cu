@@ -1406,6 +1406,14 @@ using namespace TCW_NS;
 #define tcw_forward tcws_forward
 #define tcw_backward tcws_backward
 #else
+bool tcw_takes_narrow(const tpx_fcn_desc* net) {
+  if (net->activation != TPX_ACT_TANH && net->activation != TPX_ACT_SIN) return false;
+  if (net->n_hidden < 2 || net->d_in > MAXD || net->d_out > MAXO) return false;
+  for (int l = 0; l < net->n_hidden; ++l)
+    if (net->widths[l] > 64) return false;
+  return !tc_net_fits(net);
+}
+
 bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   static const int disabled = tcw::env_flag("TPX_DISABLE_TCW");
   if (disabled) return false;
@@ -1413,7 +1421,8 @@ bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   if (net->n_hidden < 2) return false;
   int wmax = 0;
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
-  if (wmax <= 64 || wmax > 2 * HW) return false;     // 129..256: two 128-neuron blocks per layer
+  if (wmax > 2 * HW) return false;                   // 129..256: two 128-neuron blocks per layer
+  if (wmax <= 64 && !tcw_takes_narrow(net)) return false;
   if (net->d_in > MAXD || net->d_out > MAXO) return false;
   if (lap && nd == 0) return false;
   if (nd < 0 || nd > 3) return false;
