@@ -534,25 +534,27 @@ def run_native(args):
             except Exception as e:                           # never lose the headline line over the extras
                 blocks[key] = {"error": repr(e)[:300]}
         if world == 1:
-            # the literal config 1 once more with the whole training step (sampler -> jets -> residual -> loss -> reverse -> Adam)
-            # captured in ONE CUDA graph (tp.solver.Trainer(cuda_graph=True)): launch-bound at this size when run eagerly
-            try:
-                import torchphysics_b200 as tp
-                torch.manual_seed(0)
-                model, cond, _ = build_config(tp, 1, 10000, ctx.dev)
-                solver = tp.solver.Solver([cond], optimizer_setting=tp.solver.OptimizerSetting(torch.optim.Adam, lr=1e-3))
-                tr = tp.solver.Trainer(max_steps=303, cuda_graph=True, device=ctx.dev)
-                tr.fit(solver)
-                if tr.graphed:
-                    blocks["1_10k_graph"] = {"workload": CONFIGS[1]["name"] + " + Adam update", "points_per_gpu_per_step": 10000,
-                                             "value": 10000 / (tr.graph_step_ms * 1e-3), "unit": "points/s", "ms_per_step": tr.graph_step_ms,
-                                             "what": "one CUDA-graph launch per training step (300 replays timed with CUDA events): "
-                                                     "device-resident Philox key, device-resident Adam step count",
-                                             "final_loss": float(tr.losses[-1])}
-                else:
-                    blocks["1_10k_graph"] = {"error": "the step was not captured"}
-            except Exception as e:
-                blocks["1_10k_graph"] = {"error": repr(e)[:300]}
+            # the literal config 1 (10,000 points) and config 4 (host-bound when run eagerly: ~100 small launches per step) once
+            # more with the whole training step (samplers -> jets -> residual -> loss -> reverse -> Adam) captured in ONE CUDA
+            # graph (tp.solver.Trainer(cuda_graph=True))
+            import torchphysics_b200 as tp
+            for key, k, n in (("1_10k_graph", 1, 10000), ("4_graph", 4, points_per_rank(4, 1))):
+                try:
+                    torch.manual_seed(0)
+                    model, cond, _ = build_config(tp, k, n, ctx.dev)
+                    solver = tp.solver.Solver([cond], optimizer_setting=tp.solver.OptimizerSetting(torch.optim.Adam, lr=1e-3))
+                    tr = tp.solver.Trainer(max_steps=303 if k == 1 else 103, cuda_graph=True, device=ctx.dev)
+                    tr.fit(solver)
+                    if tr.graphed:
+                        blocks[key] = {"workload": CONFIGS[k]["name"] + " + Adam update", "points_per_gpu_per_step": n,
+                                       "value": n / (tr.graph_step_ms * 1e-3), "unit": CONFIGS[k]["unit"], "ms_per_step": tr.graph_step_ms,
+                                       "what": "one CUDA-graph launch per training step (replays timed with CUDA events): "
+                                               "device-resident Philox key, device-resident Adam step count",
+                                       "final_loss": float(tr.losses[-1])}
+                    else:
+                        blocks[key] = {"error": "the step was not captured"}
+                except Exception as e:
+                    blocks[key] = {"error": repr(e)[:300]}
         if rank == 0:
             line["configs"] = blocks
     if rank == 0:

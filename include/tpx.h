@@ -30,7 +30,7 @@ extern "C" {
 #define TPX_MAX_DIN 8       /* columns of the model input                          */
 #define TPX_MAX_ND 3        /* derivative directions propagated through the net    */
 #define TPX_MAX_WIDTH 256   /* widest hidden layer                                 */
-#define TPX_MAX_DOUT 256
+#define TPX_MAX_DOUT 4096   /* outputs; more than 256 only on the wide tensor-core path (hidden width <= 128) */
 
 #define TPX_E_ARG (-1)       /* invalid argument                      */
 #define TPX_E_UNSUPPORTED (-2) /* valid network, but no kernel for it  */

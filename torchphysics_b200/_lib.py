@@ -11,7 +11,7 @@ TPX_MAX_HIDDEN = 16
 TPX_MAX_DIN = 8
 TPX_MAX_ND = 3
 TPX_MAX_WIDTH = 256
-TPX_MAX_DOUT = 256
+TPX_MAX_DOUT = 4096
 TPX_ACT_TANH = 0
 TPX_ACT_SIN = 1
 

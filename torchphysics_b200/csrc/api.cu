@@ -96,7 +96,7 @@ __global__ void pack_kernel(Layout lay, PackArgs pa, float* __restrict__ packed)
     } else if (e < lay.hidden_base(1)) {
       const int j = (int)(e - lay.b0());
       if (j < pa.out_w[0]) v = pa.b[0][j];
-    } else if (e < lay.wl()) {
+    } else if (e < lay.hidden_base(lay.L)) {
       const size_t per = 2 * (size_t)HP * HP + HP;
       const size_t r = e - lay.hidden_base(1);
       const int l = 1 + (int)(r / per);
@@ -112,10 +112,14 @@ __global__ void pack_kernel(Layout lay, PackArgs pa, float* __restrict__ packed)
         const int j = (int)(q - 2 * (size_t)HP * HP);
         if (j < pa.out_w[l]) v = pa.b[l][j];
       }
+    } else if (e < lay.wl()) {               // wide_out only: WLt[i][j] = WL[j][i], rows of dop() columns
+      const size_t q = e - lay.hidden_base(lay.L);
+      const int i = (int)(q / lay.dop()), j = (int)(q % lay.dop());
+      if (j < lay.d_out && i < pa.in_w[lay.L]) v = pa.W[lay.L][(size_t)j * pa.in_w[lay.L] + i];
     } else if (e < lay.bl()) {
       const size_t q = e - lay.wl();
       const int o = (int)(q / HP), i = (int)(q % HP);
-      if (i < pa.in_w[lay.L]) v = pa.W[lay.L][(size_t)o * pa.in_w[lay.L] + i];
+      if (o < lay.d_out && i < pa.in_w[lay.L]) v = pa.W[lay.L][(size_t)o * pa.in_w[lay.L] + i];
     } else {
       const int o = (int)(e - lay.bl());
       if (o < lay.d_out) v = pa.b[lay.L][o];
@@ -267,6 +271,7 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
   }
   if (saved && tcw_supported(net, jet->nd, a.lap))     // the launcher recorded the message
     return (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(a.lay, a.jet, a.lap, packed, x, n, u, du, lap, saved, a.sm_count, a.stream);
+  if (a.lay.d_out > 256) return fail(TPX_E_UNSUPPORTED, "d_out=%d > 256 runs on the wide tensor-core path only (hidden width <= 128, d_in <= 4)", a.lay.d_out);
   switch (a.lay.HP) {
     case 32: rc = launch_fwd<32>(a); break;
     case 64: rc = launch_fwd<64>(a); break;
@@ -355,6 +360,11 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
   int rc = fill_launch(net, jet, &a);
   if (rc) return rc;
   if (!bytes) return fail(TPX_E_ARG, "bytes is NULL");
+  if (a.lay.d_out > 256) {                   // no FP32 kernel: the wide tensor-core path or nothing
+    if (!tcw_supported(net, jet->nd, a.lap)) return fail(TPX_E_UNSUPPORTED, "no reverse kernel for d_out=%d", a.lay.d_out);
+    *bytes = tcw_saved_bytes(net, jet->nd, a.lap, kWideChunkPoints);
+    return 0;
+  }
   switch (a.lay.HP) {
     case 32: rc = bwd_workspace<32>(jet->nd, a.lap, a.lay.L, a.lay.d_out, a.sm_count, bytes); break;
     case 64: rc = bwd_workspace<64>(jet->nd, a.lap, a.lay.L, a.lay.d_out, a.sm_count, bytes); break;
@@ -423,6 +433,7 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
       return 0;
     }
   }
+  if (a.lay.d_out > 256) return fail(TPX_E_UNSUPPORTED, "d_out=%d > 256 runs on the wide tensor-core path only (hidden width <= 128, d_in <= 4)", a.lay.d_out);
   switch (a.lay.HP) {
     case 32: rc = launch_bwd<32>(a); break;
     case 64: rc = launch_bwd<64>(a); break;

@@ -27,12 +27,18 @@ struct Layout {
   __host__ __device__ size_t hidden_base(int l) const {  // l in 1..L-1
     return (size_t)d_in * HP + HP + (size_t)(l - 1) * (2 * (size_t)HP * HP + HP);
   }
+  // 9 or more outputs on a 128-wide image (DeepONet trunks; the DeepONet inner product folded into the output layer): the
+  // output layer is stored like a hidden matrix -- Wt [HP][DOP] | W [DOP][HP] | b [DOP], DOP = d_out padded to 128-neuron
+  // blocks, padding zero -- so that the layer-major tensor-core kernels treat it as matrix L, block by block
+  __host__ __device__ bool wide_out() const { return HP == 128 && d_out > 8; }
+  __host__ __device__ size_t dop() const { return (size_t)((d_out + 127) / 128) * 128; }
   __host__ __device__ size_t wt(int l) const { return hidden_base(l); }
-  __host__ __device__ size_t w(int l) const { return hidden_base(l) + (size_t)HP * HP; }
-  __host__ __device__ size_t b(int l) const { return hidden_base(l) + 2 * (size_t)HP * HP; }
-  __host__ __device__ size_t wl() const { return hidden_base(L); }
-  __host__ __device__ size_t bl() const { return wl() + (size_t)d_out * HP; }
-  __host__ __device__ size_t total() const { return bl() + (size_t)((d_out + 3) / 4) * 4; }
+  __host__ __device__ size_t wts(int l) const { return (l == L && wide_out()) ? dop() : (size_t)HP; }   // row stride of wt(l)
+  __host__ __device__ size_t w(int l) const { return l == L ? wl() : hidden_base(l) + (size_t)HP * HP; }
+  __host__ __device__ size_t b(int l) const { return l == L ? bl() : hidden_base(l) + 2 * (size_t)HP * HP; }
+  __host__ __device__ size_t wl() const { return wide_out() ? hidden_base(L) + (size_t)HP * dop() : hidden_base(L); }
+  __host__ __device__ size_t bl() const { return wl() + (wide_out() ? dop() : (size_t)d_out) * HP; }
+  __host__ __device__ size_t total() const { return bl() + (wide_out() ? dop() : (size_t)((d_out + 3) / 4) * 4); }
 };
 
 struct JetArgs {

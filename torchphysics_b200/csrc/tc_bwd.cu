@@ -643,34 +643,34 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       for (int o = 0; o < MAXIO; ++o)
         if (o < d_out) atomicAdd(a.gacc + lay32.bl() + o, (double)acc[ACC_BL + o]);
     }
-    // hidden matrices: rows j (hi, quadrants 0-1) and 64 + j (lo, quadrants 2-3) both add into dW[j][i]; a wide
-    // accumulator also holds the a_lo products in columns 64 + i
-    __threadfence();                        // the reductions into the partial sums of every activation warp ...
-    named_bar_sync(15, 32 * B_EPI_WARPS);   // ... have been performed before anyone reads them back
-    if (my_tiles > 0) {
-      const int j = (quad & 1) * 32 + lane;
-      for (int l = 1; l < L; ++l) {
-        const uint32_t tW = tmem + T_DW + dw_col(L, l) + lane_base;
-        float w[B_CH];
-        tmem_ld16(tW + jc, w);
-        if (dw_is_wide(L, l)) {
-          float w2[B_CH];
-          tmem_ld16(tW + HP + jc, w2);
-#pragma unroll
-          for (int i = 0; i < B_CH; ++i) w[i] += w2[i];
-        }
-#pragma unroll
-        for (int i = 0; i < B_CH; ++i) {
-          const int col = jc + i;
-          const double part = (quad < 2) ? (double)__ldcg(dwp + ((size_t)(l - 1) * HP + col) * HP + j) : 0.0;   // added once
-          if (j < HP32 && col < HP32) atomicAdd(a.gacc + lay32.w(l) + (size_t)j * HP32 + col, (double)w[i] + part);
-        }
-      }
-    }
+    // hidden matrices: what is left in the TMEM accumulators joins the CTA's fp32 partial sums (a warp adds 128 consecutive bytes
+    // per instruction); tc_dw_reduce_kernel sums the CTAs in float64.  (One float64 atomic per element, quadrant and CTA straight
+    // into the gradient image -- 32 rows 512 bytes apart per warp instruction -- was a fixed ~60 us per launch.)
+    if (my_tiles > 0) flush_dw();
   }
   fence_before();
   __syncthreads();
   if (warp == B_EPI_WARPS) tmem_dealloc(tmem, B_TMEM_COLS);
+}
+
+// hidden dW: float64 sum over CTAs of the fp32 partial sums [CTA][matrix][input neuron i][output neuron j], added to the gradient
+// image (one writer per element; launches of one sweep are ordered on the stream)
+__global__ void __launch_bounds__(256) tc_dw_reduce_kernel(const float* __restrict__ dwpart, int nctas, int L, Layout lay32,
+                                                           double* __restrict__ gacc) {
+  const int e = blockIdx.x * 256 + threadIdx.x;              // = ((l - 1) * HP + i) * HP + j
+  if (e >= (L - 1) * HP * HP) return;
+  const int j = e % HP, i = (e / HP) % HP, l = 1 + e / (HP * HP);
+  if (j >= lay32.HP || i >= lay32.HP) return;
+  double acc = 0.0;
+  int c = 0;
+  constexpr size_t PER = (size_t)(MAXL - 1) * HP * HP;
+  for (; c + 4 <= nctas; c += 4) {
+    const float v0 = __ldcg(dwpart + (size_t)c * PER + e), v1 = __ldcg(dwpart + (size_t)(c + 1) * PER + e);
+    const float v2 = __ldcg(dwpart + (size_t)(c + 2) * PER + e), v3 = __ldcg(dwpart + (size_t)(c + 3) * PER + e);
+    acc += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+  }
+  for (; c < nctas; ++c) acc += (double)__ldcg(dwpart + (size_t)c * PER + e);
+  gacc[lay32.w(l) + (size_t)j * lay32.HP + i] += acc;
 }
 
 }  // namespace tc
@@ -713,6 +713,10 @@ static int launch_tc_bwd_act(const BwdArgs& a, int sm_count, cudaStream_t stream
   tc_bwd_kernel<ND, LAP, ACT><<<(unsigned)grid, B_THREADS, smem, stream>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_bwd_kernel launch (%lld CTAs x %d threads, %zu bytes smem): %s", (long long)grid, B_THREADS, smem, cudaGetErrorString(e));
+  const int L = a.lay.L;
+  tc_dw_reduce_kernel<<<((L - 1) * HP * HP + 255) / 256, 256, 0, stream>>>(a.dwpart, (int)grid, L, a.lay32, a.gacc);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(TPX_E_CUDA, "tc_dw_reduce_kernel launch: %s", cudaGetErrorString(e));
   return 0;
 }
 

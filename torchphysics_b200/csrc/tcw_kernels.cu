@@ -59,7 +59,8 @@ constexpr int PROD_WARPS = 8;
 constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;
 constexpr int THREADS = 32 * (MMA_WARP + 1);
 constexpr int MAXD = 4;            // d_in supported by the layer-0 code
-constexpr int MAXO = 8;            // d_out supported by the output-layer kernels
+constexpr int MAXO = 8;            // d_out supported by the CUDA-core output-layer kernels
+constexpr int MAXO_WIDE = TPX_MAX_DOUT;   // ... 9 or more outputs (hidden width <= 128): the output layer is one more UMMA product per 128 outputs
 constexpr int FWD = 0, ADJ = 1;
 // The TMEM accumulator of dW rounds toward zero on every add (one ulp of the running sum): after thousands of steps of a
 // CTA the sum would be ~1e-4 short.  Every FLUSH steps the loader warps move it into a per-CTA fp32 array in global
@@ -784,7 +785,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
   fence_after();
   const uint32_t tmem = tmem_slot;
   if (warp < 4) {                              // W^T into TMEM: lane = input neuron i, K = output neuron j
-    const float* Wrow = a.packed + lay.wt(l) + (size_t)(a.kb * HW + warp * 32 + lane) * lay.HP + a.jb * HW;
+    const float* Wrow = a.packed + lay.wt(l) + (size_t)(a.kb * HW + warp * 32 + lane) * lay.wts(l) + a.jb * HW;
     const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c = 0; c < HW / 16; ++c) {
@@ -967,14 +968,16 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
     }
     mbar_wait_w(&bar_done, 0);
     fence_after();
-    __threadfence();                             // this thread's own reductions into dwp have been performed at L2
-    double* g = a.gacc + lay.w(l) + (size_t)(a.jb * HW + j) * lay.HP + a.kb * HW;
+    // the rest of the TMEM accumulator joins the CTA's fp32 partial sums (a warp adds 128 consecutive bytes per instruction);
+    // w_dw_reduce_kernel then sums the CTAs in float64.  (One float64 atomic per element and CTA straight into the gradient
+    // image -- 32 different 1 KB-strided rows per warp instruction -- cost ~60 us per launch, more than the whole sweep of a
+    // 16,384-point batch.)
 #pragma unroll 1
     for (int c = 0; c < HW / 16; ++c) {
       float d[16];
       tmem_ld16(tq + T_DW + c * 16, d);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) atomicAdd(g + c * 16 + e, (double)d[e] + (double)__ldcg(dwp + (c * 16 + e) * HW));
+      for (int e = 0; e < 16; ++e) atomicAdd(dwp + (c * 16 + e) * HW, d[e]);
     }
   } else {
     // =========================== a_{l-1}^T producers + adjoint-jet epilogue: lane = input neuron i ===========================
@@ -1112,6 +1115,22 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
   fence_before();
   __syncthreads();
   if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// dW of one 128 x 128 block: float64 sum of the per-CTA fp32 partial sums [CTA][input neuron i][output neuron j] of w_rev_kernel,
+// added to the gradient image (one writer per element: launches of one sweep are ordered on the stream)
+__global__ void __launch_bounds__(256) w_dw_reduce_kernel(const float* __restrict__ dwpart, int nctas, double* __restrict__ g, int hp) {
+  const int e = blockIdx.x * 256 + threadIdx.x;          // = i * HW + j
+  if (e >= HW * HW) return;
+  double acc = 0.0;
+  int c = 0;
+  for (; c + 4 <= nctas; c += 4) {
+    const float v0 = __ldcg(dwpart + (size_t)c * (HW * HW) + e), v1 = __ldcg(dwpart + (size_t)(c + 1) * (HW * HW) + e);
+    const float v2 = __ldcg(dwpart + (size_t)(c + 2) * (HW * HW) + e), v3 = __ldcg(dwpart + (size_t)(c + 3) * (HW * HW) + e);
+    acc += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+  }
+  for (; c < nctas; ++c) acc += (double)__ldcg(dwpart + (size_t)c * (HW * HW) + e);
+  g[(size_t)(e % HW) * hp + e / HW] += acc;
 }
 
 // =============================================================================================================
@@ -1277,6 +1296,51 @@ __global__ void __launch_bounds__(OUT_THREADS, (DO <= 2) ? 3 : 2) w_out_bwd_kern
   if (hb == 0 && threadIdx.x < d_out) atomicAdd(a.gacc + lay.bl() + threadIdx.x, (double)red[(DO + 1) * HW + threadIdx.x]);
 }
 
+// ---- 9 or more outputs (Layout::wide_out: DeepONet trunks, the DeepONet inner product folded into the output layer): the output
+// layer runs as matrix L of the layer kernels, one 128-output block (a.jb) at a time ------------------------------------------
+// forward: w_layer_kernel<FWD> with part_out leaves the raw products W_L a_{L-1} as [tile][n = s * 16 + p][128]; this kernel adds the
+// bias to the value stream and writes the caller's u / du / lap arrays (a warp reads 128-byte rows, consecutive outputs)
+template <int ND, int LAP>
+__global__ void __launch_bounds__(OUT_THREADS) w_out_gather_kernel(WArgs a, const float* __restrict__ raw, float* __restrict__ u,
+                                                                   float* __restrict__ du, float* __restrict__ lapo) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  const int d_out = a.lay.d_out, c0 = a.jb * HW;
+  const int cols = d_out - c0 < HW ? d_out - c0 : HW;          // outputs of this block
+  const int64_t total = a.n * cols;
+  for (int64_t e = (int64_t)blockIdx.x * OUT_THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * OUT_THREADS) {
+    const int64_t pt = e / cols;
+    const int o = (int)(e % cols);
+    const float* src = raw + ((size_t)(pt / P) * N + (size_t)(pt % P)) * HW + o;
+    const int64_t dst = pt * d_out + c0 + o;
+    u[dst] = __ldcs(src) + __ldg(a.packed + a.lay.bl() + c0 + o);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) du[dst * ND + k] = __ldcs(src + (size_t)(1 + k) * P * HW);
+    if (LAP) lapo[dst] = __ldcs(src + (size_t)(S - 1) * P * HW);
+  }
+}
+
+// reverse: the output adjoints of block a.jb as Zbar_L (every row of every tile, zeros for padding points and neurons >= d_out) for
+// w_rev_kernel with l = L, and dbL.  One CTA = 128 threads = the 128 neuron columns, grid-stride over the points.
+template <int ND, int LAP>
+__global__ void __launch_bounds__(HW) w_out_seed_kernel(WArgs a, const float* __restrict__ gu, const float* __restrict__ gdu,
+                                                         const float* __restrict__ glap) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  const int d_out = a.lay.d_out, o = threadIdx.x, c = a.jb * HW + o;
+  const int64_t npad = (a.n + P - 1) / P * P;
+  double acc_bl = 0.0;
+  for (int64_t pt = blockIdx.x; pt < npad; pt += gridDim.x) {
+    const bool on = pt < a.n && c < d_out;
+    float* dst = a.out + ((size_t)(pt / P) * N + (size_t)(pt % P)) * HW + o;
+    const float g0 = (on && gu) ? __ldg(gu + pt * d_out + c) : 0.0f;
+    acc_bl += (double)g0;
+    __stcs(dst, g0);
+#pragma unroll
+    for (int k = 0; k < ND; ++k) __stcs(dst + (size_t)(1 + k) * P * HW, (on && gdu) ? __ldg(gdu + (pt * d_out + c) * ND + k) : 0.0f);
+    if (LAP) __stcs(dst + (size_t)(S - 1) * P * HW, (on && glap) ? __ldg(glap + pt * d_out + c) : 0.0f);
+  }
+  if (c < d_out) atomicAdd(a.gacc + a.lay.bl() + c, acc_bl);
+}
+
 template <int ND, int LAP>
 struct Launch {
   static constexpr int S = 1 + ND + LAP, N = S * P;
@@ -1297,6 +1361,12 @@ struct Launch {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(TPX_E_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
     return 0;
+  }
+  // dW block (a.jb, a.kb) of matrix a.l: the per-CTA partial sums of the w_rev_kernel launch that just went out -> gradient image
+  static int reduce_dw(const WArgs& a, unsigned nctas, cudaStream_t stream) {
+    double* g = a.gacc + a.lay.w(a.l) + (size_t)(a.jb * HW) * a.lay.HP + a.kb * HW;
+    w_dw_reduce_kernel<<<HW * HW / 256, 256, 0, stream>>>(a.dwpart, (int)nctas, g, a.lay.HP);
+    return check("w_dw_reduce_kernel");
   }
   static unsigned grid(const WArgs& a, int sm_count) {
     const int64_t ntiles = (a.n + P - 1) / P;
@@ -1323,6 +1393,23 @@ struct Launch {
           w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
           if ((rc = check("w_layer_kernel<FWD>"))) return rc;
         }
+    if (u && a.lay.wide_out()) {                 // nblk == 1: raw products of matrix L, one block of 128 outputs at a time, into
+      float* raw = saved + (size_t)(L - 1) * layer;     // the (idle) Zbar array, then u / du / lap
+      const int nob = (int)(a.lay.dop() / HW);
+      for (int ob = 0; ob < nob; ++ob) {
+        a.l = L; a.jb = ob; a.kb = 0;
+        a.in = saved + (size_t)(L - 2) * layer;
+        a.out = nullptr; a.part = raw; a.part_out = 1; a.part_in = 0;
+        w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
+        if ((rc = check("w_layer_kernel<FWD> (output layer)"))) return rc;
+        const int cols = a.lay.d_out - ob * HW < HW ? a.lay.d_out - ob * HW : HW;
+        int64_t blocks = (a.n * cols + OUT_THREADS - 1) / OUT_THREADS;
+        if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
+        w_out_gather_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, raw, u, du, lapo);
+        if ((rc = check("w_out_gather_kernel"))) return rc;
+      }
+      return 0;
+    }
     if (u) {
       a.in = saved + (size_t)(L - 2) * layer;
       a.half_stride = (int64_t)per;
@@ -1339,10 +1426,12 @@ struct Launch {
     const size_t per = per_floats(a.n), layer = (size_t)nblk * per;
     float* zb[2] = {saved + (size_t)(L - 1) * layer, saved + (size_t)L * layer};
     float* part = saved + (size_t)(L + 1) * layer;
-    a.dwpart = part + (nblk > 1 ? per : 0);
+    a.dwpart = part + ((nblk > 1 || (a.lay.wide_out() && a.lay.dop() > HW)) ? per : 0);
     static const int split = env_flag("TPX_TCW_SPLIT");      // development: separate dW / adjoint launches (width <= 128)
     int rc;
-    for (int hb = 0; hb < nblk; ++hb) {
+    const bool wide_out = a.lay.wide_out();
+    const int nob = wide_out ? (int)(a.lay.dop() / HW) : 0;      // 128-output blocks of the output layer
+    for (int hb = 0; hb < nblk && !wide_out; ++hb) {
       a.kb = hb;
       a.in = saved + (size_t)(L - 2) * layer + (size_t)hb * per;
       a.out = zb[0] + (size_t)hb * per;
@@ -1356,7 +1445,7 @@ struct Launch {
       else w_out_bwd_kernel<ND, LAP, 8><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
       if ((rc = check("w_out_bwd_kernel"))) return rc;
     }
-    if (split && nblk == 1) {
+    if (split && nblk == 1 && !wide_out) {
       if ((rc = set_smem(w_layer_kernel<ND, LAP, ADJ>, layer_smem(), "w_layer_kernel<ADJ>"))) return rc;
       if ((rc = set_smem(w_dw_kernel<ND, LAP>, dw_smem(), "w_dw_kernel"))) return rc;
     } else {
@@ -1364,9 +1453,33 @@ struct Launch {
       if ((rc = set_smem(w_rev_kernel<ND, LAP, true>, rev_smem(), "w_rev_kernel"))) return rc;
     }
     int cur = 0;
+    if (wide_out) {
+      // matrix L block by block: Zbar_L[ob] = the output adjoints of the block (seed kernel); dW_L[ob] is complete per launch,
+      // Abar_{L-1} = sum_ob W_L[ob]^T Zbar_L[ob] meets in `part`; the last launch finishes Zbar_{L-1} and db_{L-1}
+      a.l = L;
+      const int64_t npad = (a.n + P - 1) / P * P;
+      const int64_t sblocks = npad < (int64_t)sm_count * 16 ? npad : (int64_t)sm_count * 16;
+      const int64_t nsub = (a.n + P - 1) / P * 2;
+      unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
+      if (g > MAX_REV_CTAS) g = MAX_REV_CTAS;
+      for (int ob = 0; ob < nob; ++ob) {
+        a.jb = ob; a.kb = 0;
+        a.out = zb[0];
+        w_out_seed_kernel<ND, LAP><<<(unsigned)sblocks, HW, 0, stream>>>(a, gu, gdu, glap);
+        if ((rc = check("w_out_seed_kernel"))) return rc;
+        a.in = zb[0];
+        a.ck = saved + (size_t)(L - 2) * layer;
+        a.out = zb[1];
+        a.part = part; a.part_out = ob < nob - 1; a.part_in = ob > 0;
+        w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
+        if ((rc = check("w_rev_kernel (output layer)"))) return rc;
+        if ((rc = reduce_dw(a, g, stream))) return rc;
+      }
+      cur = 1;
+    }
     for (int l = L - 1; l >= 1; --l) {
       a.l = l;
-      if (split && nblk == 1) {
+      if (split && nblk == 1 && !wide_out) {
         a.jb = a.kb = 0; a.part_out = a.part_in = 0;
         a.in = zb[cur];
         a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer;
@@ -1390,6 +1503,7 @@ struct Launch {
             if (l == 1) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
             else w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
             if ((rc = check("w_rev_kernel"))) return rc;
+            if ((rc = reduce_dw(a, g, stream))) return rc;
           }
       }
       cur ^= 1;
@@ -1408,7 +1522,7 @@ using namespace TCW_NS;
 #else
 bool tcw_takes_narrow(const tpx_fcn_desc* net) {
   if (net->activation != TPX_ACT_TANH && net->activation != TPX_ACT_SIN) return false;
-  if (net->n_hidden < 2 || net->d_in > MAXD || net->d_out > MAXO) return false;
+  if (net->n_hidden < 2 || net->d_in > MAXD || net->d_out > MAXO_WIDE) return false;
   for (int l = 0; l < net->n_hidden; ++l)
     if (net->widths[l] > 64) return false;
   return !tc_net_fits(net);
@@ -1423,7 +1537,7 @@ bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
   if (wmax > 2 * HW) return false;                   // 129..256: two 128-neuron blocks per layer
   if (wmax <= 64 && !tcw_takes_narrow(net)) return false;
-  if (net->d_in > MAXD || net->d_out > MAXO) return false;
+  if (net->d_in > MAXD || net->d_out > (wmax <= HW ? MAXO_WIDE : MAXO)) return false;   // 9..128 outputs: Layout::wide_out
   if (lap && nd == 0) return false;
   if (nd < 0 || nd > 3) return false;
   return true;
@@ -1436,7 +1550,8 @@ size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n) {
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
   const size_t nblk = wmax > HW ? 2 : 1;
   const size_t per = (size_t)((n + P - 1) / P) * (size_t)((1 + nd + lap) * P) * HW * sizeof(float);
-  return ((size_t)(net->n_hidden + 1) * nblk + (nblk > 1 ? 1 : 0)) * per + (size_t)MAX_REV_CTAS * HW * HW * sizeof(float);
+  const bool out_chain = nblk == 1 && net->d_out > HW;       // more than one block of outputs: their adjoint products meet in `part`
+  return ((size_t)(net->n_hidden + 1) * nblk + ((nblk > 1 || out_chain) ? 1 : 0)) * per + (size_t)MAX_REV_CTAS * HW * HW * sizeof(float);
 }
 
 #endif  // !TCW_ACT_SIN

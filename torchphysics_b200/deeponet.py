@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, jets
-from .engine import JetSpec
+from .engine import FcnEngine, JetSpec
 from .functionsets import FunctionSet
 from .models import Model, Sequential, _NativeFcnMixin, _fc_layers, strict_native
 from .spaces import Points
@@ -153,6 +153,11 @@ class BranchNet(Model):
     def grid(self):
         return Points(self.grid_buffer, self.input_space.input_space)
 
+    def _release_graph(self):
+        """drop the autograd graph of the last ``fix_input`` (``Trainer`` calls this before it captures a CUDA graph: the kept
+        coefficients would keep the eager step's AccumulateGrad nodes -- bound to the default stream -- alive)."""
+        self.current_out = self.current_out.detach()
+
     def finalize(self, output_space, output_neurons):
         self.output_neurons = output_neurons
         self.output_space = output_space
@@ -209,11 +214,12 @@ class DeepONetEvaluation:
     ``tev`` is the trunk's JetEvaluation on the rows the trunk really has to evaluate; every
     stream of u is the contraction of that trunk stream with the branch coefficients."""
 
-    def __init__(self, tev, branch_out, batch_shape, copied, leaf_cols, plain_fn):
+    def __init__(self, tev, branch_out, batch_shape, copied, leaf_cols, plain_fn, folded=False):
         self.tev = tev
         self.B = branch_out                       # (Fb, o, p), graph to the branch parameters
         self.batch_shape = tuple(batch_shape)     # shape of the model output without its last axis
         self.copied = copied
+        self.folded = folded                      # tev's columns are already (function, output): no contraction left
         self.leaf_cols = leaf_cols
         self.plain_fn = plain_fn
         self._plain = None
@@ -224,11 +230,14 @@ class DeepONetEvaluation:
         """(rows, o*p) trunk stream -> (..., o) stream of u."""
         Fb, o, p = self.B.shape
         if self.copied:
-            T = stream.reshape(-1, o, p)                                  # (n, o, p)
-            if o == 1:
-                out = torch.matmul(self.B[:, 0, :], T[:, 0, :].t()).unsqueeze(-1)      # (Fb, n, 1)
+            if self.folded:
+                out = stream.reshape(-1, Fb, o).permute(1, 0, 2)          # (n, Fb * o) -> (Fb, n, o), a view
             else:
-                out = torch.einsum("nop,fop->fno", T, self.B)
+                T = stream.reshape(-1, o, p)                              # (n, o, p)
+                if o == 1:
+                    out = torch.matmul(self.B[:, 0, :], T[:, 0, :].t()).unsqueeze(-1)      # (Fb, n, 1)
+                else:
+                    out = torch.einsum("nop,fop->fno", T, self.B)
             lead = self.batch_shape[0]
             if lead != Fb:
                 if Fb == 1:
@@ -332,6 +341,23 @@ class DeepONet(Model):
             trunk_inputs = trunk.default_trunk_input.repeat(self.branch.current_out.shape[0])
         return Points(self.constrain_fn(trunk_inputs.join(points_out).coordinates), self.output_space)
 
+    def _folded_engine(self, n_cols):
+        """Engine of the trunk's hidden layers with ``n_cols`` = functions x output dim output columns (cached per
+        width; False when no kernel takes that shape, e.g. more than TPX_MAX_DOUT columns: the trunk then keeps its
+        own output layer and the streams are contracted with the branch coefficients by torch)."""
+        cache = self.__dict__.setdefault("_folded", {})
+        if n_cols not in cache:
+            base = self.trunk._native_engine()
+            try:
+                eng = FcnEngine(base.linears, base.activation, d_out=n_cols)
+                eng.workspace(JetSpec(), next(self.trunk.parameters()).device)    # has a reverse kernel for this shape
+            except _lib.TpxError as err:
+                if err.code != _lib.TPX_E_UNSUPPORTED:
+                    raise
+                eng = False
+            cache[n_cols] = eng
+        return cache[n_cols]
+
     def _native(self, trunk_inputs):
         trunk = self.trunk
         points = trunk._points_or_default(trunk_inputs)
@@ -350,9 +376,26 @@ class DeepONet(Model):
         spec = hints.get(key) if leaves is not None else None
         if spec is None:
             spec = JetSpec()
-        tev = jets.JetEvaluation(eng, rows.contiguous(), rows.shape[:-1], {}, hints, key, None, spec)
         B = self.branch.current_out
         B = B.reshape(B.shape[0], self.branch.output_space.dim, self.branch.output_neurons)
+        folded = self._folded_engine(B.shape[0] * B.shape[1]) if trunk.trunk_input_copied else False
+        if folded is not False:
+            # u[f, n, o] = sum_p B[f, o, p] (W_L a(x_n) + b_L)[o, p] = (B W_L)[f, o, :] a(x_n) + (B b_L)[f, o]: the inner product
+            # with the branch coefficients IS an output layer of F * o columns on the trunk's last hidden layer.  The
+            # two parameter-sized products below (F x p x h) are the only library calls; everything of size N runs in
+            # the jet kernels (the output layer as UMMA products, 128 (function, output) columns per launch).
+            Fb, o, p = B.shape
+            last = [m for m in trunk.sequential if isinstance(m, nn.Linear)][-1]
+            Wl, bl = last.weight.reshape(o, p, -1), last.bias.reshape(o, p)
+            if o == 1:
+                W_eff, b_eff = B[:, 0, :].matmul(Wl[0]), B[:, 0, :].matmul(bl[0])
+            else:
+                W_eff = torch.einsum("fop,oph->foh", B, Wl).reshape(Fb * o, -1)
+                b_eff = torch.einsum("fop,op->fo", B, bl).reshape(Fb * o)
+            params = eng.params()[:-2] + [W_eff, b_eff]
+            tev = jets.JetEvaluation(folded, rows.contiguous(), rows.shape[:-1], {}, hints, key, None, spec, params)
+        else:
+            tev = jets.JetEvaluation(eng, rows.contiguous(), rows.shape[:-1], {}, hints, key, None, spec)
         ev = DeepONetEvaluation(tev, B, batch, trunk.trunk_input_copied, leaf_cols,
-                                lambda: self._generic(points))
+                                lambda: self._generic(points), folded=folded is not False)
         return jets.JetTensor.wrap(ev.value(), ev, range(self.output_space.dim))

@@ -75,14 +75,18 @@ def _void_p_array(tensors):
 class FcnEngine:
     """Native evaluator of one fully connected net (list of nn.Linear + one activation)."""
 
-    def __init__(self, linears, activation):
+    def __init__(self, linears, activation, d_out=None):
+        """``d_out`` replaces the output width of the last Linear: the caller then always passes its own parameter
+        tensors (``jet(..., params=...)``), e.g. a DeepONet's trunk with the branch coefficients folded into the output
+        layer (``deeponet.py``)."""
         self.linears = list(linears)
+        self._own_params = d_out is None
         if activation not in ("tanh", "sin"):
             raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, f"activation {activation!r}")
         self.activation = activation
         d = _lib.FcnDesc()
         d.d_in = self.linears[0].in_features
-        d.d_out = self.linears[-1].out_features
+        d.d_out = self.linears[-1].out_features if d_out is None else int(d_out)
         d.n_hidden = len(self.linears) - 1
         if d.n_hidden < 1 or d.n_hidden > _lib.TPX_MAX_HIDDEN:
             raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, f"{d.n_hidden} hidden layers")
@@ -101,6 +105,8 @@ class FcnEngine:
 
     # ---- parameters ------------------------------------------------------------------
     def params(self):
+        if not self._own_params:
+            raise _lib.TpxError(_lib.TPX_E_ARG, "this engine has no output layer of its own: pass params")
         out = []
         for lin in self.linears:
             if lin.bias is None:

@@ -146,11 +146,17 @@ class FunctionSampler:
 
 
 class FunctionSamplerRandomUniform(FunctionSampler):
-    """random subset, ``torch.randperm`` on the host generator (reference ``function_sampler.py:61-67``)."""
+    """random subset, ``torch.randperm`` on the host generator (reference ``function_sampler.py:61-67``).  While a CUDA graph is
+    being captured (``Trainer(cuda_graph=True)``) the subset is drawn on the device instead -- ranks of uniform keys from torch's
+    capture-aware CUDA generator -- so that every replay picks new functions without a host round trip."""
 
     def sample_functions(self, device="cpu"):
         self._check_recreate_functions(device=device)
-        self.current_indices = torch.randperm(self.function_set.function_set_size)[:self.n_functions]
+        size = self.function_set.function_set_size
+        if torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing():
+            self.current_indices = torch.rand(size, device=device).argsort()[:self.n_functions]
+        else:
+            self.current_indices = torch.randperm(size)[:self.n_functions]
         return self.function_set.get_function(self.current_indices)
 
 

@@ -115,6 +115,10 @@ class Trainer:
             self.losses.append(one_step())
         if n_eager == self.max_steps:
             return n_eager
+        for m in solver.modules():                           # tensors kept from the eager steps must not carry their graphs
+            release = getattr(m, "_release_graph", None)
+            if release is not None:
+                release()
         try:
             domains.use_device_key(self.device)
             optimizer.use_device_step(True)
