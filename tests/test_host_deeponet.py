@@ -14,10 +14,22 @@ from tests.golden_io import load, relerr
 class _TorchJetEngine:
     """stand-in for FcnEngine.jet: value / d_k / weighted-Laplacian streams with torch ops."""
 
-    def __init__(self, lins):
-        self.lins, self.d_out = lins, lins[-1].out_features
+    def __init__(self, lins, d_out=None):
+        self.lins, self.d_out = lins, lins[-1].out_features if d_out is None else d_out
+
+    def params(self):
+        return [p for lin in self.lins for p in (lin.weight, lin.bias)]
+
+    def with_outputs(self, n_cols, device):
+        """FcnEngine.with_outputs: same hidden layers, the caller's output layer of n_cols columns"""
+        return _TorchJetEngine(self.lins, d_out=n_cols)
 
     def jet(self, x, spec, params=None):
+        if params is not None:
+            class _L:
+                def __init__(self, w, b):
+                    self.weight, self.bias = w, b
+            return _TorchJetEngine([_L(params[2 * i], params[2 * i + 1]) for i in range(len(params) // 2)], self.d_out).jet(x, spec)
         n, nd = x.shape[0], spec.nd
         h = x
         d = [torch.zeros_like(x) for _ in range(nd)]

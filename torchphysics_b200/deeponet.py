@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, jets
-from .engine import FcnEngine, JetSpec
+from .engine import JetSpec
 from .functionsets import FunctionSet
 from .models import Model, Sequential, _NativeFcnMixin, _fc_layers, strict_native
 from .spaces import Points
@@ -349,8 +349,7 @@ class DeepONet(Model):
         if n_cols not in cache:
             base = self.trunk._native_engine()
             try:
-                eng = FcnEngine(base.linears, base.activation, d_out=n_cols)
-                eng.workspace(JetSpec(), next(self.trunk.parameters()).device)    # has a reverse kernel for this shape
+                eng = base.with_outputs(n_cols, next(self.trunk.parameters()).device)
             except _lib.TpxError as err:
                 if err.code != _lib.TPX_E_UNSUPPORTED:
                     raise

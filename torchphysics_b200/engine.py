@@ -103,6 +103,13 @@ class FcnEngine:
         self._ws = {}
         self._ckpt_pool = _CheckpointPool()
 
+    def with_outputs(self, n_cols, device):
+        """an engine on the same hidden layers whose output layer has ``n_cols`` columns and takes its parameters from
+        the caller; raises TpxError(TPX_E_UNSUPPORTED) when no kernel pair (forward + reverse) takes that shape."""
+        eng = FcnEngine(self.linears, self.activation, d_out=n_cols)
+        eng.workspace(JetSpec(), device)
+        return eng
+
     # ---- parameters ------------------------------------------------------------------
     def params(self):
         if not self._own_params:
