@@ -60,6 +60,11 @@ typedef struct tpx_jet_desc {
   int32_t dcol[TPX_MAX_ND];
   int32_t lap;
   float lap_w[TPX_MAX_ND];
+  int32_t out_major;   /* 0: u (n, d_out), du (n, d_out, nd), lap (n, d_out) -- and their adjoints -- as documented below;
+                        * 1: output-major  u (d_out, n), du (nd, d_out, n), lap (d_out, n): the layout of a DeepONet's
+                        *    (function, point) outputs when the inner product with the branch coefficients is folded into
+                        *    the trunk's output layer (models/deeponet/deeponet.py:91-102).  Only for networks with 9 or
+                        *    more outputs on the layer-major tensor-core kernels; TPX_E_UNSUPPORTED otherwise. */
 } tpx_jet_desc;
 
 int tpx_version(void);

@@ -424,3 +424,39 @@ def test_round2_split_fp16_kernels_in_a_subprocess():
                         "or test_against_float64_oracle or test_linearity_of_reverse_at_scale"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("d_in,d_out,hidden,dcols,lap_w,N", [(1, 256, (64,) * 4, (0,), (1.0,), 16384 + 5),
+                                                             (2, 40, (128, 96), (0, 1), None, 333),
+                                                             (2, 300, (32, 32, 32), (1,), (0.5,), 70001)])
+def test_output_major_streams_equal_the_transposed_standard_ones(d_in, d_out, hidden, dcols, lap_w, N):
+    """tpx_jet_desc.out_major (the layout of a DeepONet's (function, point) outputs): the same kernels write u (d_out, n),
+    du (nd, d_out, n), lap (d_out, n) and read the adjoints in that layout -- bit-identical streams, dtheta up to the order of
+    the reductions; with and without a saved buffer (the second in chunks through the workspace: a column range per chunk)."""
+    from torchphysics_b200.engine import FcnEngine, JetSpec
+    torch.manual_seed(11)
+    seq = ref_autograd.build_fcn(d_in, d_out, hidden).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    std, tr = JetSpec(dcols, lap_w), JetSpec(dcols, lap_w, out_major=True)
+    x = torch.rand(N, d_in, device="cuda")
+    packed = eng.packed(eng.params())
+    gu = torch.randn(N, d_out, device="cuda")
+    gdu = torch.randn(N, d_out, len(dcols), device="cuda")
+    glap = torch.randn(N, d_out, device="cuda") if lap_w else None
+    gu_t, gdu_t = gu.t().contiguous(), gdu.permute(2, 1, 0).contiguous()
+    glap_t = glap.t().contiguous() if lap_w else None
+    for use_saved in (True, False):
+        s1 = torch.empty(eng.saved_bytes(std, N), dtype=torch.uint8, device="cuda") if use_saved else None
+        s2 = torch.empty(eng.saved_bytes(tr, N), dtype=torch.uint8, device="cuda") if use_saved else None
+        u, du, lap = eng.forward_raw(packed, x, std, s1)
+        ut, dut, lapt = eng.forward_raw(packed, x, tr, s2)
+        assert ut.shape == (d_out, N) and dut.shape == (len(dcols), d_out, N)
+        assert torch.equal(ut.t(), u) and torch.equal(dut.permute(2, 1, 0), du)
+        if lap_w:
+            assert torch.equal(lapt.t(), lap)
+        g1 = eng.backward_raw(packed, x, std, gu, gdu, glap, s1)
+        g2 = eng.backward_raw(packed, x, tr, gu_t, gdu_t, glap_t, s2)
+        assert float((g1 - g2).abs().max() / g1.abs().max()) < 1e-6
+    small = FcnEngine([m for m in ref_autograd.build_fcn(2, 3, (32, 32)).cuda() if isinstance(m, nn.Linear)], "tanh")
+    with pytest.raises(Exception):                       # 8 or fewer outputs: no output-major kernels, refused loudly
+        small.forward_raw(small.packed(small.params()), torch.rand(10, 2, device="cuda"), JetSpec((0,), None, out_major=True))

@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
 def test_struct_layouts_match_header():
     from torchphysics_b200 import _lib
     assert ctypes.sizeof(_lib.FcnDesc) == 4 * (3 + 16 + 1)
-    assert ctypes.sizeof(_lib.JetDesc) == 4 * (1 + 3 + 1 + 3)
+    assert ctypes.sizeof(_lib.JetDesc) == 4 * (1 + 3 + 1 + 3 + 1)
     assert ctypes.sizeof(_lib.Shape) == 32
     assert ctypes.sizeof(_lib.Region) == 8 + 8 * 32 + 24 * 4
 

@@ -91,6 +91,7 @@ class JetDesc(ctypes.Structure):
         ("dcol", ctypes.c_int32 * TPX_MAX_ND),
         ("lap", ctypes.c_int32),
         ("lap_w", ctypes.c_float * TPX_MAX_ND),
+        ("out_major", ctypes.c_int32),
     ]
 
 

@@ -59,6 +59,15 @@ static int check_jet(const tpx_fcn_desc* net, const tpx_jet_desc* jet, JetArgs* 
   if (jet->nd < 0 || jet->nd > TPX_MAX_ND) return fail(TPX_E_UNSUPPORTED, "nd=%d outside 0..%d", jet->nd, TPX_MAX_ND);
   if (jet->lap && jet->nd == 0) return fail(TPX_E_ARG, "lap requires nd >= 1");
   ja->nd = jet->nd;
+  ja->out_major = jet->out_major ? 1 : 0;
+  ja->out_ld = 0;
+  if (ja->out_major) {
+    Layout lay;
+    int rc = make_layout(net, &lay);
+    if (rc) return rc;
+    if (!lay.wide_out() || !tcw_supported(net, jet->nd, jet->lap ? 1 : 0))
+      return fail(TPX_E_UNSUPPORTED, "output-major streams need 9 or more outputs on the layer-major tensor-core kernels");
+  }
   for (int k = 0; k < TPX_MAX_ND; ++k) {
     ja->dcol[k] = 0;
     ja->lap_w[k] = 0.f;
@@ -259,6 +268,7 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
   if (jet->lap && !lap) return fail(TPX_E_ARG, "lap is NULL but lap requested");
   a.packed = packed; a.x = x; a.n = n; a.u = u; a.du = du; a.lapo = lap;
   a.stream = (cudaStream_t)stream;
+  a.jet.out_ld = n;
   if (tcp_supported(net, jet->nd, a.lap) && (!saved || tce_bwd_supported(net, jet->nd, a.lap))) {
     float *ck = nullptr, *st = nullptr, *dw = nullptr;
     if (saved) tce_saved_split(net, jet->nd, a.lap, (n + 127) / 128, saved, &ck, &st, &dw);
@@ -271,7 +281,8 @@ static int jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const f
   }
   if (saved && tcw_supported(net, jet->nd, a.lap))     // the launcher recorded the message
     return (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(a.lay, a.jet, a.lap, packed, x, n, u, du, lap, saved, a.sm_count, a.stream);
-  if (a.lay.d_out > 256) return fail(TPX_E_UNSUPPORTED, "d_out=%d > 256 runs on the wide tensor-core path only (hidden width <= 128, d_in <= 4)", a.lay.d_out);
+  if (a.lay.d_out > 256 || a.jet.out_major)
+    return fail(TPX_E_UNSUPPORTED, "d_out=%d > 256 / output-major streams run on the wide tensor-core path only: call tpx_fcn_jet_forward_ws or _save", a.lay.d_out);
   switch (a.lay.HP) {
     case 32: rc = launch_fwd<32>(a); break;
     case 64: rc = launch_fwd<64>(a); break;
@@ -318,10 +329,12 @@ int tpx_fcn_jet_forward_ws(const tpx_fcn_desc* net, const tpx_jet_desc* jet, con
   const int sms = sm_count();
   if (sms <= 0) return fail(TPX_E_CUDA, "no CUDA device");
   const int d_in = net->d_in, d_out = net->d_out, nd = jet->nd;
+  ja.out_ld = n;
   for (int64_t p0 = 0; p0 < n; p0 += cpts) {
     const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
-    rc = (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(lay, ja, lp, packed, x + p0 * d_in, m, u + p0 * d_out, du ? du + p0 * d_out * nd : nullptr,
-                     lap ? lap + p0 * d_out : nullptr, (float*)workspace, sms, (cudaStream_t)stream);
+    const int64_t ou = ja.out_major ? p0 : p0 * d_out, odu = ja.out_major ? p0 : p0 * d_out * nd;   // output-major: a column range
+    rc = (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(lay, ja, lp, packed, x + p0 * d_in, m, u + ou, du ? du + odu : nullptr,
+                     lap ? lap + ou : nullptr, (float*)workspace, sms, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return 0;
@@ -401,6 +414,7 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
   a.gu = gu; a.gdu = jet->nd > 0 ? gdu : nullptr; a.glap = jet->lap ? glap : nullptr;
   a.gacc = grad_acc; a.ckpt = (float*)workspace; a.ckpt_bytes = workspace_bytes;
   a.stream = (cudaStream_t)stream;
+  a.jet.out_ld = n;
   if (tce_bwd_supported(net, jet->nd, a.lap))
     return tce_backward(net, a.lay, a.jet, a.lap, packed + tcp_image_offset(net, a.lay), x, n, a.gu, a.gdu, a.glap, grad_acc,
                         (float*)workspace, workspace_bytes, saved, a.sm_count, a.stream);   // the launcher recorded the message
@@ -425,15 +439,17 @@ static int jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
         const int64_t m = (n - p0 < cpts) ? n - p0 : cpts;
         rc = (net->activation == TPX_ACT_SIN ? tcws_forward : tcw_forward)(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, nullptr, nullptr, nullptr, (float*)workspace, a.sm_count, a.stream);
         if (rc) return rc;
-        rc = (net->activation == TPX_ACT_SIN ? tcws_backward : tcw_backward)(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, a.gu ? a.gu + p0 * d_out : nullptr,
-                          a.gdu ? a.gdu + p0 * d_out * nd : nullptr, a.glap ? a.glap + p0 * d_out : nullptr, grad_acc,
+        const int64_t ou = a.jet.out_major ? p0 : p0 * d_out, odu = a.jet.out_major ? p0 : p0 * d_out * nd;
+        rc = (net->activation == TPX_ACT_SIN ? tcws_backward : tcw_backward)(a.lay, a.jet, a.lap, packed, x + p0 * d_in, m, a.gu ? a.gu + ou : nullptr,
+                          a.gdu ? a.gdu + odu : nullptr, a.glap ? a.glap + ou : nullptr, grad_acc,
                           (float*)workspace, a.sm_count, a.stream);
         if (rc) return rc;
       }
       return 0;
     }
   }
-  if (a.lay.d_out > 256) return fail(TPX_E_UNSUPPORTED, "d_out=%d > 256 runs on the wide tensor-core path only (hidden width <= 128, d_in <= 4)", a.lay.d_out);
+  if (a.lay.d_out > 256 || a.jet.out_major)
+    return fail(TPX_E_UNSUPPORTED, "d_out=%d > 256 / output-major streams run on the wide tensor-core path only (workspace of %zu bytes holds no tile)", a.lay.d_out, workspace_bytes);
   switch (a.lay.HP) {
     case 32: rc = launch_bwd<32>(a); break;
     case 64: rc = launch_bwd<64>(a); break;

@@ -45,6 +45,8 @@ struct JetArgs {
   int nd;
   int dcol[TPX_MAX_ND];
   float lap_w[TPX_MAX_ND];
+  int out_major;         // outputs and their adjoints as (d_out, n) / (nd, d_out, n): wide tensor-core path with wide_out only
+  long long out_ld;      // ... their row stride = the caller's n (a launch may cover a chunk of the points)
 };
 
 template <int HP_, int ND_, int LAP_, int TP_>

@@ -1341,6 +1341,79 @@ __global__ void __launch_bounds__(HW) w_out_seed_kernel(WArgs a, const float* __
   if (c < d_out) atomicAdd(a.gacc + a.lay.bl() + c, acc_bl);
 }
 
+// the same two kernels for output-major streams (JetArgs::out_major: u (d_out, n), du (nd, d_out, n), lap (d_out, n), row stride
+// out_ld): one CTA per tile of 16 points, transposed through shared memory so that the raw rows are read / written as 512-byte rows
+// and the caller's arrays as 64-byte runs of 16 consecutive points
+template <int ND, int LAP>
+__global__ void __launch_bounds__(OUT_THREADS) w_out_gather_t_kernel(WArgs a, const float* __restrict__ raw, float* __restrict__ u,
+                                                                     float* __restrict__ du, float* __restrict__ lapo) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  __shared__ float t[N][HW + 1];
+  const int d_out = a.lay.d_out, c0 = a.jb * HW;
+  const int cols = d_out - c0 < HW ? d_out - c0 : HW;
+  const int64_t ntiles = (a.n + P - 1) / P, ld = a.jet.out_ld;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const float* src = raw + (size_t)tile * N * HW;
+    for (int v = threadIdx.x; v < N * HW; v += OUT_THREADS) t[v / HW][v % HW] = __ldcs(src + v);
+    __syncthreads();
+    const int p = threadIdx.x % P;
+    const int64_t pt = tile * P + p;
+    if (pt < a.n) {
+      for (int o = threadIdx.x / P; o < cols; o += OUT_THREADS / P) {
+        const int64_t row = c0 + o;
+        u[row * ld + pt] = t[p][o] + __ldg(a.packed + a.lay.bl() + row);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) du[((int64_t)k * d_out + row) * ld + pt] = t[(1 + k) * P + p][o];
+        if (LAP) lapo[row * ld + pt] = t[(S - 1) * P + p][o];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int ND, int LAP>
+__global__ void __launch_bounds__(OUT_THREADS) w_out_seed_t_kernel(WArgs a, const float* __restrict__ gu, const float* __restrict__ gdu,
+                                                                   const float* __restrict__ glap) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  __shared__ float t[N][HW + 1];
+  __shared__ float sdb[HW];
+  const int d_out = a.lay.d_out, c0 = a.jb * HW;
+  const int64_t ntiles = (a.n + P - 1) / P, ld = a.jet.out_ld;
+  for (int v = threadIdx.x; v < HW; v += OUT_THREADS) sdb[v] = 0.0f;
+  float acc[HW / 32];                                        // value-stream adjoints of outputs lane + 32 q, summed over this CTA's points
+#pragma unroll
+  for (int q = 0; q < HW / 32; ++q) acc[q] = 0.0f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int p = threadIdx.x % P;
+    const int64_t pt = tile * P + p;
+    for (int o = threadIdx.x / P; o < HW; o += OUT_THREADS / P) {
+      const int64_t row = c0 + o;
+      const bool on = pt < a.n && row < d_out;
+      t[p][o] = (on && gu) ? __ldg(gu + row * ld + pt) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) t[(1 + k) * P + p][o] = (on && gdu) ? __ldg(gdu + ((int64_t)k * d_out + row) * ld + pt) : 0.0f;
+      if (LAP) t[(S - 1) * P + p][o] = (on && glap) ? __ldg(glap + row * ld + pt) : 0.0f;
+    }
+    __syncthreads();
+    float* dst = a.out + (size_t)tile * N * HW;
+    for (int r = warp; r < N; r += OUT_THREADS / 32) {
+#pragma unroll
+      for (int q = 0; q < HW / 32; ++q) {
+        const float v = t[r][q * 32 + lane];
+        __stcs(dst + (size_t)r * HW + q * 32 + lane, v);
+        if (r < P) acc[q] += v;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < HW / 32; ++q) atomicAdd(&sdb[q * 32 + lane], acc[q]);
+  __syncthreads();
+  for (int o = threadIdx.x; o < HW; o += OUT_THREADS)
+    if (c0 + o < d_out) atomicAdd(a.gacc + a.lay.bl() + c0 + o, (double)sdb[o]);
+}
+
 template <int ND, int LAP>
 struct Launch {
   static constexpr int S = 1 + ND + LAP, N = S * P;
@@ -1405,7 +1478,13 @@ struct Launch {
         const int cols = a.lay.d_out - ob * HW < HW ? a.lay.d_out - ob * HW : HW;
         int64_t blocks = (a.n * cols + OUT_THREADS - 1) / OUT_THREADS;
         if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
-        w_out_gather_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, raw, u, du, lapo);
+        if (a.jet.out_major) {
+          const int64_t ntiles = (a.n + P - 1) / P;
+          const int64_t tb = ntiles < (int64_t)sm_count * 8 ? ntiles : (int64_t)sm_count * 8;
+          w_out_gather_t_kernel<ND, LAP><<<(unsigned)tb, OUT_THREADS, 0, stream>>>(a, raw, u, du, lapo);
+        } else {
+          w_out_gather_kernel<ND, LAP><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, raw, u, du, lapo);
+        }
         if ((rc = check("w_out_gather_kernel"))) return rc;
       }
       return 0;
@@ -1465,7 +1544,13 @@ struct Launch {
       for (int ob = 0; ob < nob; ++ob) {
         a.jb = ob; a.kb = 0;
         a.out = zb[0];
-        w_out_seed_kernel<ND, LAP><<<(unsigned)sblocks, HW, 0, stream>>>(a, gu, gdu, glap);
+        if (a.jet.out_major) {
+          const int64_t ntiles = (a.n + P - 1) / P;
+          const int64_t tb = ntiles < (int64_t)sm_count * 8 ? ntiles : (int64_t)sm_count * 8;
+          w_out_seed_t_kernel<ND, LAP><<<(unsigned)tb, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+        } else {
+          w_out_seed_kernel<ND, LAP><<<(unsigned)sblocks, HW, 0, stream>>>(a, gu, gdu, glap);
+        }
         if ((rc = check("w_out_seed_kernel"))) return rc;
         a.in = zb[0];
         a.ck = saved + (size_t)(L - 2) * layer;

@@ -230,7 +230,9 @@ class DeepONetEvaluation:
         """(rows, o*p) trunk stream -> (..., o) stream of u."""
         Fb, o, p = self.B.shape
         if self.copied:
-            if self.folded:
+            if self.folded and self.tev.spec.out_major:
+                out = stream.reshape(Fb, o, -1).permute(0, 2, 1)          # (Fb * o, n) -> (Fb, n, o): contiguous for o = 1
+            elif self.folded:
                 out = stream.reshape(-1, Fb, o).permute(1, 0, 2)          # (n, Fb * o) -> (Fb, n, o), a view
             else:
                 T = stream.reshape(-1, o, p)                              # (n, o, p)
@@ -266,7 +268,7 @@ class DeepONetEvaluation:
         k = self.tev.spec.dcols.index(in_col)
         key = ("d", id(self.tev.du), k)
         if key not in self._cache:
-            self._cache[key] = self._contract(self.tev.du[:, :, k])
+            self._cache[key] = self._contract(self.tev.du[k] if self.tev.spec.out_major else self.tev.du[:, :, k])
         return jets.JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
 
     def second(self, out_cols):
@@ -392,8 +394,13 @@ class DeepONet(Model):
                 W_eff = torch.einsum("fop,oph->foh", B, Wl).reshape(Fb * o, -1)
                 b_eff = torch.einsum("fop,op->fo", B, bl).reshape(Fb * o)
             params = eng.params()[:-2] + [W_eff, b_eff]
+            want = bool(getattr(folded, "out_major", False))
+            if spec.out_major != want:
+                spec = JetSpec(spec.dcols, spec.lap_w, out_major=want)
             tev = jets.JetEvaluation(folded, rows.contiguous(), rows.shape[:-1], {}, hints, key, None, spec, params)
         else:
+            if spec.out_major:
+                spec = JetSpec(spec.dcols, spec.lap_w)
             tev = jets.JetEvaluation(eng, rows.contiguous(), rows.shape[:-1], {}, hints, key, None, spec)
         ev = DeepONetEvaluation(tev, B, batch, trunk.trunk_input_copied, leaf_cols,
                                 lambda: self._generic(points), folded=folded is not False)

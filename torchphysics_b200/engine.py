@@ -17,9 +17,11 @@ class JetSpec:
     """Which derivative streams to propagate: ``dcols`` = input columns of the (<= 3)
     directions, ``lap_w`` = weights of the second-derivative sum (None: no Laplacian)."""
 
-    __slots__ = ("dcols", "lap_w")
+    __slots__ = ("dcols", "lap_w", "out_major")
 
-    def __init__(self, dcols=(), lap_w=None):
+    def __init__(self, dcols=(), lap_w=None, out_major=False):
+        # out_major: the streams (and their adjoints) as u (d_out, n), du (nd, d_out, n), lap (d_out, n) -- tpx_jet_desc.out_major
+        self.out_major = bool(out_major)
         self.dcols = tuple(int(c) for c in dcols)
         self.lap_w = None if lap_w is None else tuple(float(w) for w in lap_w)
         if len(self.dcols) > _lib.TPX_MAX_ND:
@@ -48,11 +50,12 @@ class JetSpec:
         return True
 
     def key(self):
-        return (self.dcols, self.lap_w)
+        return (self.dcols, self.lap_w, self.out_major)
 
     def c_struct(self):
         j = _lib.JetDesc()
         j.nd = self.nd
+        j.out_major = 1 if self.out_major else 0
         for k, c in enumerate(self.dcols):
             j.dcol[k] = c
         j.lap = 1 if self.lap else 0
@@ -62,7 +65,7 @@ class JetSpec:
         return j
 
     def __repr__(self):
-        return f"JetSpec(dcols={self.dcols}, lap_w={self.lap_w})"
+        return f"JetSpec(dcols={self.dcols}, lap_w={self.lap_w}" + (", out_major=True)" if self.out_major else ")")
 
 
 def _void_p_array(tensors):
@@ -107,7 +110,14 @@ class FcnEngine:
         """an engine on the same hidden layers whose output layer has ``n_cols`` columns and takes its parameters from
         the caller; raises TpxError(TPX_E_UNSUPPORTED) when no kernel pair (forward + reverse) takes that shape."""
         eng = FcnEngine(self.linears, self.activation, d_out=n_cols)
-        eng.workspace(JetSpec(), device)
+        try:                                   # output-major streams where the kernels offer them (9 or more columns)
+            eng.workspace(JetSpec(out_major=True), device)
+            eng.out_major = True
+        except _lib.TpxError as err:
+            if err.code != _lib.TPX_E_UNSUPPORTED:
+                raise
+            eng.workspace(JetSpec(), device)
+            eng.out_major = False
         return eng
 
     # ---- parameters ------------------------------------------------------------------
@@ -148,7 +158,7 @@ class FcnEngine:
         return self._packed
 
     def workspace(self, spec, device):
-        k = (spec.nd, spec.lap, str(device))
+        k = (spec.nd, spec.lap, spec.out_major, str(device))
         ws = self._ws.get(k)
         if ws is None:
             nbytes = ctypes.c_size_t(0)
@@ -173,9 +183,14 @@ class FcnEngine:
 
     def _forward_raw_impl(self, packed, x, spec, saved=None):
         n = x.shape[0]
-        u = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device)
-        du = torch.empty((n, self.d_out, spec.nd), dtype=torch.float32, device=x.device) if spec.nd else None
-        lap = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device) if spec.lap else None
+        if spec.out_major:
+            u = torch.empty((self.d_out, n), dtype=torch.float32, device=x.device)
+            du = torch.empty((spec.nd, self.d_out, n), dtype=torch.float32, device=x.device) if spec.nd else None
+            lap = torch.empty((self.d_out, n), dtype=torch.float32, device=x.device) if spec.lap else None
+        else:
+            u = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device)
+            du = torch.empty((n, self.d_out, spec.nd), dtype=torch.float32, device=x.device) if spec.nd else None
+            lap = torch.empty((n, self.d_out), dtype=torch.float32, device=x.device) if spec.lap else None
         j = spec.c_struct()
         if saved is None:
             try:                                    # widths 65..256: activation arrays of the tensor-core kernels
@@ -307,8 +322,12 @@ class _FcnJetFn(torch.autograd.Function):
         ctx.params = params
         ctx.set_materialize_grads(False)
         outs = [u]
-        outs.append(du if du is not None else x.new_zeros((x.shape[0], engine.d_out, 0)))
-        outs.append(lap if lap is not None else x.new_zeros((x.shape[0], 0)))
+        if spec.out_major:
+            outs.append(du if du is not None else x.new_zeros((0, engine.d_out, x.shape[0])))
+            outs.append(lap if lap is not None else x.new_zeros((0, x.shape[0])))
+        else:
+            outs.append(du if du is not None else x.new_zeros((x.shape[0], engine.d_out, 0)))
+            outs.append(lap if lap is not None else x.new_zeros((x.shape[0], 0)))
         ctx.mark_non_differentiable(*[o for o in outs[1:] if o.numel() == 0 and x.shape[0] > 0])
         return tuple(outs)
 

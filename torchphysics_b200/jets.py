@@ -104,7 +104,7 @@ class JetEvaluation:
             lap_w = [wmap.get(c, 0.0) for c in cols]
         if len(cols) > 3:
             return False
-        new = JetSpec(cols, lap_w)
+        new = JetSpec(cols, lap_w, out_major=self.spec.out_major)
         u, du, lap = self.engine.jet(self.x, new, self.params)
         self.spec, self.du, self.lap = new, du, lap      # value stream: keep the first u
         self._u2 = u

@@ -237,7 +237,9 @@ class Points:
     @property
     def coordinates(self):
         sl = self.space.column_slices()
-        return {name: self._t[..., sl[name]] for name in self.space}
+        width = self._t.shape[-1]
+        # a variable that spans every column IS the tensor: no slice node (its backward would be a zero fill + copy of the batch)
+        return {name: (self._t if (sl[name].start, sl[name].stop) == (0, width) else self._t[..., sl[name]]) for name in self.space}
 
     @property
     def as_tensor(self):
