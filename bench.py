@@ -399,8 +399,8 @@ def roofline_block(cfg, n, ms_bwd, ms_fwd, peaks):
     achieved = n * (2.0 / 3.0) * c["flop"] / (ms_bwd * 1e-3) / 1e12       # the reverse sweep is 2 of the 3 forward-equivalents
     # dram bytes per launch from the ncu captures under profiles/ (per Mi points), where one exists for the kernel
     traffic = {1: 4.342e9}.get(cfg)
-    kernels = {1: "tc_bwd_kernel (tcgen05 reverse sweep: tf32 adjoint product from TMEM + bf16 gradient product from shared-memory "
-                  "operand images, saved checkpoints)",
+    kernels = {1: "tc_bwd_kernel (tcgen05 reverse sweep: split-tf32 adjoint product with A from TMEM + split-tf32 gradient product "
+                  "from transposed shared-memory operands, saved checkpoints)",
                2: "w_rev_kernel sweep (tcgen05, width 128: one launch per hidden matrix)",
                3: "w_rev_kernel sweep (tcgen05, width 128: one launch per hidden matrix)",
                5: "w_rev_kernel sweep (tcgen05, width 256 as 128 x 128 blocks)"}
@@ -410,8 +410,8 @@ def roofline_block(cfg, n, ms_bwd, ms_fwd, peaks):
             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained",
             "algorithmic_flop_per_point": (2.0 / 3.0) * c["flop"], "ms_per_launch": ms_bwd, "forward_kernel_ms": ms_fwd,
             "note": "FLOP = algorithmic GEMM FLOP of SURVEY 8(d) (reverse = 2 x forward).  The kernels issue 3 split products per "
-                    "algorithmic product to hold fp32 accuracy (tf32 at half the bf16 rate for the adjoint product, bf16 for the "
-                    "gradient product), so the ceiling of frac is ~0.15; what bounds them is in profiles/README.md"}
+                    "algorithmic product to hold fp32 accuracy, in tf32 at half the bf16 rate, so the ceiling of frac is 1/6; what bounds "
+                    "them is in profiles/README.md"}
 
 
 def run_config1_resident(ctx, args, N):

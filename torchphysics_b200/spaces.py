@@ -399,6 +399,8 @@ class Points:
         leaves so that the native jet path can identify derivative variables."""
         coords = self.coordinates
         for name in coords:
+            if coords[name] is self._t:            # a variable spanning every column: a leaf of its own, not the caller's buffer
+                coords[name] = self._t.detach() if not self._t.requires_grad else self._t[..., :]
             coords[name].requires_grad = True
         tracked = Points.from_coordinates(coords)
         tracked._coord_leaves = coords
