@@ -34,7 +34,7 @@ class _SquaredErrorMean(torch.autograd.Function):
         from . import _lib
         r = r.contiguous()
         acc = torch.zeros(1, dtype=torch.float64, device=r.device)
-        with torch.cuda.device(r.device):
+        with _lib.on_device(r.device):
             _lib.check(_lib.lib().tpx_squared_error_mean(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
                                                          _lib.ptr(acc), _lib.stream_ptr()))
         ctx.save_for_backward(r)
@@ -48,7 +48,7 @@ class _SquaredErrorMean(torch.autograd.Function):
         (r,) = ctx.saved_tensors
         g = g.to(device=r.device, dtype=torch.float32).contiguous()
         gr = torch.empty_like(r)
-        with torch.cuda.device(r.device):
+        with _lib.on_device(r.device):
             _lib.check(_lib.lib().tpx_squared_error_mean_backward(_lib.ptr(r), ctypes.c_int64(r.numel()), ctypes.c_int64(r.shape[0]),
                                                                   _lib.ptr(g), _lib.ptr(gr), _lib.stream_ptr()))
         return gr
@@ -162,11 +162,11 @@ class SingleModuleCondition(Condition):
         eng = eng_of()
         if spec is None or eng is False:
             return 1
-        from .engine import save_budget_bytes
+        from .engine import save_budget_bytes, within_save_budget
         need = eng.saved_bytes(spec, t.shape[0])
-        budget = save_budget_bytes(t.device)
-        if need == 0 or need <= budget:
+        if need == 0 or within_save_budget(need, t.device):
             return 1
+        budget = save_budget_bytes(t.device)
         return min(int(-(-need // max(budget // 2, 1))), 64)
 
     def _loss_on(self, x):

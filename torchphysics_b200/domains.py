@@ -196,7 +196,7 @@ class Domain:
         shapes, ops = self._program(col)
         rg = _region_struct(shapes, ops)
         mask = torch.empty(n, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(_lib.lib().tpx_region_contains(ctypes.byref(rg), _lib.ptr(rows), ctypes.c_int64(n),
                                                       ctypes.c_int32(stride), _lib.ptr(mask), _lib.stream_ptr()))
         return mask.bool().reshape(-1, 1).to(out_device)
@@ -208,7 +208,7 @@ class Domain:
         rows = self._count(n, d, params)
         dev = _compute_device(device)
         out = torch.empty((rows, self.dim_cols()), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             self._fill_random(out, 0, rows)
         return Points(out.to(device), self.space)
 
@@ -217,7 +217,7 @@ class Domain:
             return self._sample_grid_with_d(d, params, device)
         rows = self._count(n, d, params)
         dev = _compute_device(device)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             out = self._grid(rows, dev, exact=not d or bool(n))
         return Points(out.to(device), self.space)
 
@@ -445,7 +445,7 @@ class BoundaryDomain(_ShapeDomain):
         rows = rows.detach().to(device=dev, dtype=torch.float32).contiguous()
         n, stride = rows.shape
         out = torch.empty((n, self.space.dim), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             _lib.check(_lib.lib().tpx_boundary_normal(ctypes.byref(self._shape(0)), _lib.ptr(rows), ctypes.c_int64(n),
                                                       ctypes.c_int32(stride), _lib.ptr(out), _lib.stream_ptr()))
         return out.to(out_device)

@@ -7,6 +7,7 @@ Replaces, for a stack of ``nn.Linear`` + tanh/sin layers, what the reference doe
 differentialoperators.py:34,40,64``) and the final ``loss.backward()`` through all of them.
 """
 import ctypes
+import os
 
 import torch
 
@@ -132,7 +133,7 @@ class FcnEngine:
         return out
 
     def packed(self, params):
-        with torch.cuda.device(params[0].device):       # launches go to the stream of the tensors' device, not the current one
+        with _lib.on_device(params[0].device):       # launches go to the stream of the tensors' device, not the current one
             return self._packed_impl(params)
 
     def _packed_impl(self, params):
@@ -178,7 +179,7 @@ class FcnEngine:
         return nbytes.value
 
     def forward_raw(self, packed, x, spec, saved=None):
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             return self._forward_raw_impl(packed, x, spec, saved)
 
     def _forward_raw_impl(self, packed, x, spec, saved=None):
@@ -213,7 +214,7 @@ class FcnEngine:
         return u, du, lap
 
     def backward_raw(self, packed, x, spec, gu, gdu, glap, saved=None):
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             return self._backward_raw_impl(packed, x, spec, gu, gdu, glap, saved)
 
     def _backward_raw_impl(self, packed, x, spec, gu, gdu, glap, saved=None):
@@ -235,7 +236,7 @@ class FcnEngine:
         return gacc
 
     def unpack(self, gacc, params, skip_last_bias=False):
-        with torch.cuda.device(gacc.device):
+        with _lib.on_device(gacc.device):
             return self._unpack_impl(gacc, params, skip_last_bias)
 
     def _unpack_impl(self, gacc, params, skip_last_bias=False):
@@ -306,6 +307,15 @@ def save_budget_bytes(device):
     return int(0.6 * free)
 
 
+_ALWAYS_SAVED = 1 << 30
+
+
+def within_save_budget(nbytes, device):
+    """True if ``nbytes`` of checkpoints may be saved.  Up to 1 GiB the answer is yes without asking the driver:
+    cudaMemGetInfo costs ~0.3 ms, more than a whole 10,000-point step."""
+    return nbytes <= _ALWAYS_SAVED and "TPX_SAVE_GB" not in os.environ or nbytes <= save_budget_bytes(device)
+
+
 class _FcnJetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, spec, *params):
@@ -315,7 +325,7 @@ class _FcnJetFn(torch.autograd.Function):
             nbytes = engine.saved_bytes(spec, x.shape[0])
             if nbytes > 0:
                 pooled = any(b.device == x.device and nbytes <= b.numel() <= 2 * nbytes for b in engine._ckpt_pool.free)
-                if pooled or nbytes <= save_budget_bytes(x.device):
+                if pooled or within_save_budget(nbytes, x.device):
                     saved = engine._ckpt_pool.acquire(nbytes, x.device)
         u, du, lap = engine.forward_raw(packed, x, spec, None if saved is None else saved.buf)
         ctx.engine, ctx.spec, ctx.x, ctx.packed, ctx.saved = engine, spec, x, packed, saved

@@ -73,7 +73,7 @@ class Adam(torch.optim.Optimizer):
             tl.param[i], tl.grad[i] = p.data_ptr(), g.data_ptr()
             tl.exp_avg[i], tl.exp_avg_sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
             tl.numel[i] = p.numel()
-        with torch.cuda.device(todo[0][0].device):
+        with _lib.on_device(todo[0][0].device):
             _lib.check(_lib.lib().tpx_adam_step_dstep(
                 ctypes.byref(tl), ctypes.c_float(lr), ctypes.c_float(group["betas"][0]), ctypes.c_float(group["betas"][1]),
                 ctypes.c_float(group["eps"]), ctypes.c_float(group["weight_decay"]), _lib.ptr(dev_steps[gi]), _lib.stream_ptr()))
@@ -105,7 +105,7 @@ class Adam(torch.optim.Optimizer):
                     tl.param[i], tl.grad[i] = p.data_ptr(), p.grad.data_ptr()
                     tl.exp_avg[i], tl.exp_avg_sq[i] = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
                     tl.numel[i] = p.numel()
-                with torch.cuda.device(chunk[0][0].device):
+                with _lib.on_device(chunk[0][0].device):
                     _lib.check(_lib.lib().tpx_adam_step(
                         ctypes.byref(tl), ctypes.c_float(lr), ctypes.c_float(group["betas"][0]),
                         ctypes.c_float(group["betas"][1]), ctypes.c_float(group["eps"]),

@@ -318,7 +318,7 @@ class LHSSampler(PointSampler):
         dev = domains._compute_device(device)
         n, d = self.n_points, self.domain.dim
         lib = _lib.lib()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             box = torch.tensor(self.domain._box(), dtype=torch.float32, device=dev)
             keys = torch.empty((d, n), dtype=torch.int64, device=dev)
             key = domains._rng.next_key()
@@ -364,7 +364,7 @@ class HostStreamSampler(PointSampler):
             raise ValueError("HostStreamSampler delivers to a CUDA device")
         if self._dev != dev:
             self._dev = dev
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 self._stream = torch.cuda.Stream()
                 self._bufs = [torch.empty(self.batches[0].shape, dtype=torch.float32, device=dev) for _ in range(2)]
                 self._ready = [torch.cuda.Event(), torch.cuda.Event()]
