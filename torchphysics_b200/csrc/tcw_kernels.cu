@@ -26,6 +26,10 @@
 //                        dW_l[j][i] += sum_n Zbar_l[n][j] a_{l-1}[n][i]   (A = Zbar^T in TMEM, written by its lane-bound
 //                        loader warps; B = a^T in shared memory, 16-byte stores of a thread's own row; K = n) and
 //                        Abar_{l-1} = W_l^T Zbar_l -> adjoint jets with ckpt_{l-1} -> Zbar_{l-1}, db_{l-1} (l = 1: dW0, db0)
+//   w_dw_reduce_kernel   float64 sum over CTAs of w_rev_kernel's per-CTA fp32 partial sums of dW -> gradient image
+//   w_out_gather[_t]_kernel / w_out_seed[_t]_kernel   9 or more outputs (hidden width <= 128; DeepONet trunks): the output layer runs as
+//                        "matrix L" of w_layer_kernel<FWD> (raw-product exit) / w_rev_kernel, 128 outputs per launch; these move the
+//                        products / output adjoints between the [tile][n][128] arrays and the caller's (optionally output-major) arrays
 //   w_dw_kernel, w_layer_kernel<ADJ>   the same two products as separate launches (TPX_TCW_SPLIT=1, development)
 // HBM traffic per point and hidden matrix: forward 2, reverse 3 activation rows of S * 512 bytes.  The forward launches
 // are HBM-bound (~75 % of the copy peak), the fused reverse launch is bound by the tensor pipe and load latency

@@ -5,11 +5,17 @@ SURVEY 8(a) rows a12/a13.  The reference evaluates the trunk on F copies of the 
 points (``deeponet_condition.py:63``) and gets every derivative of ``u[f,n,o] = sum_p
 T[n,o,p] B[f,o,p]`` from autograd sweeps through that (F, N, o, p) tensor.  Here the trunk's
 value / first-derivative / Laplacian streams are propagated ONCE per point by the sm_100a jet
-kernel (output width o*p), and every stream of ``u`` is the same contraction with the branch
-coefficients: ``d_k u = sum_p (d_k T) B``, ``Lap u = sum_p (Lap T) B`` -- a plain
-(F x p)(p x N) library GEMM per stream.  The reverse sweep of the trunk is one launch of the
-native reverse kernel fed with the adjoints of the three streams; the branch net (F rows of
-sensor values, d_in = #sensors > TPX_MAX_DIN) is a caller of the path and stays on torch ops.
+kernels, and the inner product with the branch coefficients is folded into the trunk's output
+layer: ``u[f,n,o] = (B W_L)[f,o,:] a(x_n) + (B b_L)[f,o]`` with ``a`` the last hidden layer, so
+the trunk is evaluated as a network of F*o outputs whose output layer runs as tensor-core products
+(``csrc/tcw_kernels.cu``, "wide output layer") and whose streams come back as (function, point)
+arrays (``tpx_jet_desc.out_major``).  ``d_k u`` and ``Lap u`` are the other streams of the same
+evaluation; the reverse sweep returns dL/d(B W_L), which autograd carries on to the branch net and
+to W_L through the two parameter-sized products.  Trunks that see different points per function
+(``trunk_input_copied=False``), or more than TPX_MAX_DOUT (function, output) columns, keep their
+own output layer and contract each stream with the branch coefficients by a torch einsum.  The
+branch net (F rows of sensor values, d_in = #sensors > TPX_MAX_DIN) is a caller of the path and
+stays on torch ops.
 """
 import torch
 import torch.nn as nn
