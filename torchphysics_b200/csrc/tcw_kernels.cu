@@ -425,10 +425,17 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int st = it & 1;
-        mbar_wait_w(&bar_dfull[st], (it >> 1) & 1);
-        fence_after();
         float* dst = (part_out ? a.part : a.out) + (size_t)tile * N * HW + j;
         const float* pin = a.part + (size_t)tile * N * HW + j;
+        // the other K block of a 256-wide layer: its partial products are in flight while the warp waits for this tile's
+        // product, stream s + 1 while stream s is finished (loaded after the TMEM read they were an exposed HBM latency per stream)
+        float pv[16];
+        if (part_in) {
+#pragma unroll
+          for (int p = 0; p < P; ++p) pv[p] = __ldcs(pin + (size_t)p * HW);
+        }
+        mbar_wait_w(&bar_dfull[st], (it >> 1) & 1);
+        fence_after();
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           float d[16];
@@ -438,9 +445,13 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dempty[st]);
           }
-          if (part_in) {                       // the other K block of a 256-wide layer
+          if (part_in) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) d[p] += __ldcs(pin + (size_t)(s * P + p) * HW);
+            for (int p = 0; p < P; ++p) d[p] += pv[p];
+            if (s + 1 < S) {
+#pragma unroll
+              for (int p = 0; p < P; ++p) pv[p] = __ldcs(pin + (size_t)((s + 1) * P + p) * HW);
+            }
           }
           if (s == 0 && !part_out) {
 #pragma unroll
@@ -1055,6 +1066,16 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_fa[set]);
       TPX_WSTAMP(2 + set, 2);
+      // 256-wide layers / several blocks of outputs: the partial sum of the other blocks, in flight during the wait (S <= 3: the
+      // registers are there; loaded after the TMEM read it was an exposed HBM latency per step)
+      constexpr bool PART_PREFETCH = S <= 3;
+      float pv[PART_PREFETCH ? S : 1][8];
+      if (PART_PREFETCH && a.part_in) {
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp)
+#pragma unroll
+          for (int s = 0; s < (PART_PREFETCH ? S : 1); ++s) pv[s][pp] = __ldcs(a.part + row0 + (size_t)(s * P + pp) * HW);
+      }
       // the adjoint product of this step
       mbar_wait_w(&bar_dfull[set], ph2);
       fence_after();
@@ -1066,11 +1087,14 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_dempty);
       TPX_WSTAMP(2 + set, 4);
-      if (a.part_in) {                         // 256-wide layers: the other block of output neurons
+      if (a.part_in) {
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp)
 #pragma unroll
-          for (int s = 0; s < S; ++s) ab[s][pp] += __ldcs(a.part + row0 + (size_t)(s * P + pp) * HW);
+          for (int s = 0; s < S; ++s) {
+            if (PART_PREFETCH) ab[s][pp] += pv[s][pp];
+            else ab[s][pp] += __ldcs(a.part + row0 + (size_t)(s * P + pp) * HW);
+          }
       }
       if (a.part_out) {                        // ... not complete yet: park the raw product, no adjoint jets
 #pragma unroll
