@@ -124,3 +124,19 @@ def test_non_pointwise_functions_still_raise():
     x, ev, u = _setup()
     t = torch.cumsum(u, dim=0)
     assert not isinstance(t, jets.JetTensor) or getattr(t, "_jet", None) is None
+
+
+def test_laplacian_accepts_only_its_own_gradient_as_grad_argument():
+    """reference differentialoperators.py:11-44: laplacian(u, x, grad=g) differentiates the tensor it is given.  The native streams
+    carry no graph to x, so g must be tp.utils.grad of the same output w.r.t. the same variables (then the Laplacian stream is the
+    answer); anything else is refused instead of being ignored."""
+    import pytest
+    from torchphysics_b200 import _lib
+    x, ev, u = _setup()
+    u0 = u[:, :1]
+    g = operators.grad(u0, x)
+    assert torch.equal(operators.laplacian(u0, x, grad=g), operators.laplacian(u0, x))
+    with pytest.raises(_lib.TpxError):
+        operators.laplacian(u0, x, grad=operators.grad(u[:, 1:], x))         # the gradient of another output column
+    with pytest.raises(_lib.TpxError):
+        operators.laplacian(u0, x, grad=torch.ones(len(x), 2, dtype=torch.float64))

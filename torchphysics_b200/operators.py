@@ -53,7 +53,13 @@ def grad(model_out, *derivative_variable):
     if hit is not None:
         ev, oc, per_var = hit
         pieces = [_sum_last(ev.first(oc, c)) for cols in per_var for c in cols]
-        return pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=-1)
+        out = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=-1)
+        if len(pieces) > 1 or not hasattr(out, "_tpx_grad_of"):
+            try:                                     # lets laplacian(u, x, grad=this) recognise its own gradient
+                out._tpx_grad_of = (id(ev), tuple(oc), tuple(c for cols in per_var for c in cols))
+            except AttributeError:
+                pass
+        return out
     u = plain_of(model_out)
     return torch.column_stack([_d(u.sum(), v) for v in derivative_variable])
 
@@ -61,7 +67,15 @@ def grad(model_out, *derivative_variable):
 def laplacian(model_out, *derivative_variable, grad=None):
     hit = _native(model_out, derivative_variable, True)
     if hit is not None:
-        ev, oc, _ = hit
+        ev, oc, per_var = hit
+        if grad is not None:
+            # the reference differentiates the tensor it is given (differentialoperators.py:34-43); the native streams carry
+            # no graph to the coordinates, so only tp.utils.grad of this very output w.r.t. these variables is accepted
+            want = (id(ev), tuple(oc), tuple(c for cols in per_var for c in cols))
+            if getattr(grad, "_tpx_grad_of", None) != want:
+                from . import _lib
+                raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "laplacian(..., grad=g): g is not tp.utils.grad of this model output "
+                                    "with respect to the same variables; drop the argument (the Laplacian stream needs no gradient)")
         return _sum_last(ev.second(oc))
     u = plain_of(model_out)
     out = torch.zeros((*u.shape[:-1], 1), device=u.device)
