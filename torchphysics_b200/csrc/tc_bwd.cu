@@ -460,10 +460,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
         }
 #pragma unroll
         for (int i = 0; i < B_CH; i += 2) {
-          const float h0 = tf32_hi(hi[i]), h1 = tf32_hi(hi[i + 1]);
-          const F2 l = fma2(f2(-1.0f), f2(h0, h1), f2(hi[i], hi[i + 1]));      // x - hi, exact
-          lo[i] = l.v.x; lo[i + 1] = l.v.y;
-          hi[i] = h0; hi[i + 1] = h1;
+          const F2 l = fma2(f2(-1.0f), f2(tf32_trunc(hi[i]), tf32_trunc(hi[i + 1])), f2(hi[i], hi[i + 1]));      // x - trunc(x), exact
+          lo[i] = l.v.x; lo[i + 1] = l.v.y;            // hi stays the raw word: the MMA truncates it (tc_common.cuh)
         }
         tmem_st16(tAh + jc, hi);
         tmem_st16(tAl + jc, lo);
@@ -491,14 +489,14 @@ __global__ void __launch_bounds__(B_THREADS, 1) tc_bwd_kernel(BwdArgs a) {
       for (int s = 0; s < S; ++s)
 #pragma unroll
         for (int i = 0; i < B_NW; i += 2) {
-          const float zh0 = tf32_hi(zb[s][i]), zh1 = tf32_hi(zb[s][i + 1]);
-          const F2 zl = fma2(f2(-1.0f), f2(zh0, zh1), f2(zb[s][i], zb[s][i + 1]));       // x - hi, exact
+          const float zh0 = zb[s][i], zh1 = zb[s][i + 1];                                // raw words: the MMA truncates them
+          const F2 zl = fma2(f2(-1.0f), f2(tf32_trunc(zh0), tf32_trunc(zh1)), f2(zh0, zh1));   // x - trunc(x), exact
           Zt[s * 4096 + i * 32 + xo[i]] = zh0;
           Zt[s * 4096 + (i + 1) * 32 + xo[i + 1]] = zh1;
           Zt[s * 4096 + (64 + i) * 32 + xo[i]] = zl.v.x;
           Zt[s * 4096 + (64 + i + 1) * 32 + xo[i + 1]] = zl.v.y;
-          const float ah0 = tf32_hi(ap[s][i]), ah1 = tf32_hi(ap[s][i + 1]);
-          const F2 al = fma2(f2(-1.0f), f2(ah0, ah1), f2(ap[s][i], ap[s][i + 1]));
+          const float ah0 = ap[s][i], ah1 = ap[s][i + 1];
+          const F2 al = fma2(f2(-1.0f), f2(tf32_trunc(ah0), tf32_trunc(ah1)), f2(ah0, ah1));
           At[s * 4096 + i * 32 + xo[i]] = ah0;
           At[s * 4096 + (i + 1) * 32 + xo[i + 1]] = ah1;
           At[s * 4096 + (64 + i) * 32 + xo[i]] = al.v.x;

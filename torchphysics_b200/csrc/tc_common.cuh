@@ -121,6 +121,14 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+// Split of an activation-side operand for the 3 x tf32 products WITHOUT rounding the high part: the tensor core truncates the
+// low 13 mantissa bits of every tf32 operand word itself (measured, see the header), so the raw fp32 word serves as "hi" and
+// lo = x - trunc(x) is exact (13 bits, the MMA keeps its top 11).  One LOP3 + half a packed FADD per element instead of
+// VIADD + LOP3 + half a packed FADD.  The truncated hi makes lo non-negative relative to x, so the bits the MMA drops from lo
+// (< 2^-21 |x|) are a near-uniform relative bias of ~2^-22 on every term of a dot product -- a scaling, not amplified by
+// cancellation -- where the rounded split has a zero-mean error of half that size (parity margins: tests/test_gpu_fcn_jet.py).
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // 8 consecutive columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];

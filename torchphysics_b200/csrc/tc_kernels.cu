@@ -388,10 +388,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_fwd_kernel(FwdArgs a) {
               }
 #pragma unroll
               for (int i = 0; i < CH; i += 2) {
-                const float h0 = tf32_hi(hi[i]), h1 = tf32_hi(hi[i + 1]);
-                const F2 l = fma2(f2(-1.0f), f2(h0, h1), f2(hi[i], hi[i + 1]));      // x - hi, exact
-                lo[i] = l.v.x; lo[i + 1] = l.v.y;
-                hi[i] = h0; hi[i + 1] = h1;
+                const F2 l = fma2(f2(-1.0f), f2(tf32_trunc(hi[i]), tf32_trunc(hi[i + 1])), f2(hi[i], hi[i + 1]));      // x - trunc(x), exact
+                lo[i] = l.v.x; lo[i + 1] = l.v.y;        // hi stays the raw word: the MMA truncates it (tc_common.cuh)
               }
               tmem_st16(tAh + j0 + c * CH, hi);
               tmem_st16(tAl + j0 + c * CH, lo);
