@@ -47,6 +47,44 @@ def test_argument_errors_without_gpu():
     assert lib.tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)) == 0 and n.value > 64 * 64
 
 
+def test_packed_layout_of_wide_output_and_deep_narrow_networks():
+    """Layout rules of csrc/fcn_common.cuh (no compute): a narrow net the resident-weight kernels cannot hold (more than 5
+    hidden layers, or more than 8 outputs) is laid out as one padded 128-neuron block per layer for the layer-major
+    tensor-core kernels, and 9 or more outputs store the output layer like a hidden matrix (Wt | W | b, padded to 128)."""
+    from torchphysics_b200 import _lib
+    lib = _lib.lib()
+
+    def floats(d_in, d_out, widths):
+        d = _lib.FcnDesc()
+        d.d_in, d.d_out, d.n_hidden = d_in, d_out, len(widths)
+        for l, w in enumerate(widths):
+            d.widths[l] = w
+        d.activation = _lib.TPX_ACT_TANH
+        n = ctypes.c_size_t(0)
+        _lib.check(lib.tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)))
+        return n.value
+
+    def fp32_image(hp, d_in, L, out_floats):             # (the tensor-core images behind it start 1 KB aligned)
+        return (d_in * hp + hp + (L - 1) * (2 * hp * hp + hp) + out_floats + 255) // 256 * 256
+
+    pad4 = lambda k: (k + 3) // 4 * 4                                             # noqa: E731
+    # 6 x 64, one output: HP = 128, CUDA-core output layer (d_out x HP weights + padded bias), no width-64 tensor-core image
+    assert floats(2, 1, (64,) * 6) == fp32_image(128, 2, 6, 128 + pad4(1))
+    # DeepONet trunk 4 x 64 with 64 outputs: HP = 128, output layer as a 128 x 128 hidden-style block
+    assert floats(1, 64, (64,) * 4) == fp32_image(128, 1, 4, 2 * 128 * 128 + 128)
+    # 300 (function, output) columns: three blocks of 128 outputs
+    assert floats(1, 300, (64,) * 4) == fp32_image(128, 1, 4, 2 * 128 * 384 + 384)
+    # width 256 keeps the plain output layer (and is limited to 256 outputs by the FP32 kernels at run time)
+    assert floats(2, 40, (256, 256)) == fp32_image(256, 2, 2, 40 * 256 + pad4(40))
+    # the width-64 path appends its own images behind the (1 KB aligned) FP32 image: strictly more than the FP32 image
+    assert floats(2, 1, (64,) * 4) > fp32_image(64, 2, 4, 64 + pad4(1))
+    d = _lib.FcnDesc()
+    d.d_in, d.d_out, d.n_hidden, d.activation = 2, _lib.TPX_MAX_DOUT + 1, 2, _lib.TPX_ACT_TANH
+    d.widths[0] = d.widths[1] = 64
+    n = ctypes.c_size_t(0)
+    assert lib.tpx_fcn_packed_floats(ctypes.byref(d), ctypes.byref(n)) == _lib.TPX_E_UNSUPPORTED
+
+
 def test_region_programs():
     import torchphysics_b200 as tp
     from torchphysics_b200 import _lib
