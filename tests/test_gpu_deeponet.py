@@ -110,3 +110,73 @@ def test_deeponet_full_size_equals_generic_autograd_definition():
     assert len(ref) == len(got)
     for a, w in zip(got, ref):
         assert relerr(a.cpu().numpy(), w.cpu().numpy()) < 2e-5      # two fp32 evaluations, 4.2e6-term sums
+
+
+def test_folded_deeponet_with_two_outputs_and_2d_trunk_input():
+    """the branch coefficients folded into the trunk's output layer (F * o = 80 (function, output) columns: the wide output
+    layer of csrc/tcw_kernels.cu, output-major streams) for a DeepONet with TWO outputs on a 2-D trunk input: value, gradient
+    and Laplacian streams and dLoss/dtheta against the reference's definition with torch autograd on the same modules, and
+    against the unfolded native path (trunk with its own output layer + torch contraction)."""
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import jets
+    torch.manual_seed(3)
+    F, N, p = 40, 3001, 24
+    X, U, Fs = tp.spaces.R2("x"), tp.spaces.R2("u"), tp.spaces.R1("f")
+    fspace = tp.spaces.FunctionSpace(X, Fs)
+    grid = torch.rand(1, 30, 2)
+    trunk = tp.models.FCTrunkNet(X, hidden=(48, 48, 48), default_trunk_input=grid)
+    branch = tp.models.FCBranchNet(fspace, hidden=(32, 32), grid=grid)
+    net = tp.models.DeepONet(trunk, branch, U, output_neurons=p).cuda()
+    sensors = torch.randn(F, 30, 1, device="cuda")
+    x = torch.rand(N, 2, device="cuda")
+
+    def native():
+        net.zero_grad(set_to_none=True)
+        pts = tp.spaces.Points(x.unsqueeze(0).expand(F, N, 2), X)
+        coords, pts = pts.track_coord_gradients()
+        with jets.scope("t"):
+            u = net(pts, tp.spaces.Points(sensors, Fs), device="cuda").as_tensor
+            lap = tp.utils.laplacian(u[..., :1], coords["x"]) + 0.5 * tp.utils.laplacian(u[..., 1:], coords["x"])
+            g = tp.utils.grad(u[..., 1:], coords["x"])
+            r = lap + g.sum(dim=-1, keepdim=True) * u[..., :1].as_subclass(torch.Tensor) + u[..., 1:].as_subclass(torch.Tensor) ** 2
+        loss = (r ** 2).mean()
+        loss.backward()
+        return (u.as_subclass(torch.Tensor).detach().clone(), lap.detach().clone(), float(loss),
+                [q.grad.clone() for q in net.parameters() if q.grad is not None])
+
+    native()                                                  # the first call learns the jet spec
+    u1, lap1, loss1, g1 = native()
+    folded = net._folded[F * 2]
+    assert folded is not False and folded.out_major            # the folded tensor-core path ran
+    net._folded[F * 2] = False                                 # unfolded: trunk output layer + torch contraction
+    net.__dict__.pop("_jet_hints", None)
+    native()
+    u2, lap2, loss2, g2 = native()
+    net._folded.pop(F * 2)
+    assert relerr(u1.cpu().numpy(), u2.cpu().numpy()) < TOL and relerr(lap1.cpu().numpy(), lap2.cpu().numpy()) < TOL
+    assert abs(loss1 - loss2) < TOL * abs(loss2)
+    for a, b in zip(g1, g2):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < TOL
+    # the reference's definition: the same modules through torch ops and two create_graph sweeps
+    net.zero_grad(set_to_none=True)
+    xx = x.unsqueeze(0).repeat(F, 1, 1).requires_grad_(True)
+    net.fix_branch_input(tp.spaces.Points(sensors, Fs), device="cuda")
+    u = net._generic(tp.spaces.Points(xx, X))
+
+    def lap_of(v):
+        gv = torch.autograd.grad(v.sum(), xx, create_graph=True)[0]
+        return sum(torch.autograd.grad(gv[..., i].sum(), xx, create_graph=True)[0][..., i:i + 1] for i in range(2)), gv
+
+    l0, _ = lap_of(u[..., :1])
+    l1, gv1 = lap_of(u[..., 1:])
+    lap = l0 + 0.5 * l1
+    r = lap + gv1.sum(dim=-1, keepdim=True) * u[..., :1] + u[..., 1:] ** 2
+    want = (r ** 2).mean()
+    want.backward()
+    assert relerr(u1.cpu().numpy(), u.detach().cpu().numpy()) < TOL
+    assert relerr(lap1.cpu().numpy(), lap.detach().cpu().numpy()) < TOL
+    assert abs(loss1 - float(want)) < TOL * abs(float(want))
+    ref = [q.grad for q in net.parameters() if q.grad is not None]
+    assert len(ref) == len(g1)
+    for a, w in zip(g1, ref):
+        assert relerr(a.cpu().numpy(), w.cpu().numpy()) < TOL
