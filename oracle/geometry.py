@@ -31,6 +31,9 @@ def dim(dom):
         return 2
     if kind in ("cut", "union"):
         return dim(dom[1])
+    if kind == "intersection":
+        # domainoperations/intersection.py:34-37
+        return contains(dom[1], pts) & contains(dom[2], pts)
     if kind == "product":
         return dim(dom[1]) + dim(dom[2])
     raise ValueError(kind)
@@ -338,3 +341,47 @@ def intersection_boundary_grid_d(A, B, d):
     ga = boundary_grid(("boundary", A), int(np.ceil(f32(d) * boundary_volume(("boundary", A)))))      # domain.py:273-287
     gb = boundary_grid(("boundary", B), int(np.ceil(f32(d) * boundary_volume(("boundary", B)))))
     return np.concatenate([ga[contains(B, ga)], gb[contains(A, gb)]])
+
+
+# boundaries of boolean domains whose operands may be boolean domains themselves (the reference recurses through
+# domain_a.boundary / domain_b.boundary: cut.py:111-201, union.py:153-266, intersection.py:112-206)
+_PRIMS = ("interval", "parallelogram", "circle")
+
+
+def any_boundary_contains(dom, pts):
+    pts = np.asarray(pts, f32)
+    if dom[0] in _PRIMS:
+        return boundary_contains(("boundary", dom), pts)
+    A, B = dom[1], dom[2]
+    in_a, in_b = contains(A, pts), contains(B, pts)
+    on_a, on_b = any_boundary_contains(A, pts), any_boundary_contains(B, pts)
+    if dom[0] == "cut":
+        return (on_a & ~in_b) | (on_b & in_a & ~on_a)
+    if dom[0] == "intersection":
+        return (on_a & in_b) | (on_b & in_a)
+    if dom[0] == "union":
+        on_both = on_a & on_b
+        ok = np.ones(len(pts), bool)
+        if on_both.any():
+            na, nb = any_boundary_normal(A, pts[on_both]), any_boundary_normal(B, pts[on_both])
+            ok[on_both] = (na * nb).sum(axis=1, dtype=f32) >= f32(0.5)
+        return ((on_a & ~in_b) | (on_b & ~in_a) | on_both) & ok
+    raise ValueError(dom)
+
+
+def any_boundary_normal(dom, pts):
+    pts = np.asarray(pts, f32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if dom[0] in _PRIMS:
+            return boundary_normal(("boundary", dom), pts)
+        A, B = dom[1], dom[2]
+        on_a = any_boundary_contains(A, pts)
+        na, nb = any_boundary_normal(A, pts), any_boundary_normal(B, pts)
+    return np.where(on_a[:, None], na, -nb if dom[0] == "cut" else nb)
+
+
+def any_boundary_volume(dom):
+    """the reference's estimate: the operands' boundary lengths add up at every level"""
+    if dom[0] in _PRIMS:
+        return boundary_volume(("boundary", dom))
+    return any_boundary_volume(dom[1]) + any_boundary_volume(dom[2])

@@ -383,6 +383,40 @@ def intersection_boundary():
     save("intersection_boundary", **out)
 
 
+# ---------------------------------------------------------------------------- boundaries of nested boolean domains
+def nested_boundary():
+    """boundaries whose operands are boolean domains themselves: a cut of a cut, a cut of a union, a cut BY a union
+    (reference domainoperations/cut.py:111-201 with domain_a.boundary / domain_b.boundary boolean boundaries)."""
+    X = tp.spaces.R2("x")
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    sq = tp.domains.Parallelogram(X, [-0.25, -0.25], [0.25, -0.25], [-0.25, 0.25])
+    bite = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    sq3 = tp.domains.Parallelogram(X, [0.0, -0.8], [0.5, -0.8], [0.0, -0.4])
+    sq4 = tp.domains.Parallelogram(X, [-0.5, 0.0], [1.0, 0.0], [-0.5, 0.5])
+    prims = [circ, sq, bite, sq3, sq4]
+    out = {}
+    g = torch.Generator().manual_seed(61)
+    on = torch.cat([p.boundary.sample_grid(120).as_tensor for p in prims], dim=0)
+    far = torch.rand(300, 2, generator=g) * 3.0 - 1.5
+    cand = torch.cat([on, on + (torch.rand(on.shape, generator=g) * 4e-5 - 2e-5), far], dim=0)
+    out["cand"] = cand
+    cases = (("cutcut", (circ - sq) - bite), ("unioncut", (sq4 + bite) - sq), ("cutunion", circ - (sq + sq3)))
+    for nm, dom in cases:
+        b = dom.boundary
+        inside = b._contains(tp.spaces.Points(cand.clone(), X)).reshape(-1)
+        out["in_" + nm] = inside
+        onb = cand[inside]
+        out["on_" + nm] = onb
+        out["normal_" + nm] = b.normal(tp.spaces.Points(onb.clone(), X))
+        out["vol_" + nm] = b.volume().reshape(-1)
+        for n in (40, 200):
+            torch.manual_seed(62)
+            out[f"ngrid_{nm}_{n}"] = np.array(len(b.sample_grid(n)))
+        torch.manual_seed(63)
+        out["n_random_" + nm] = np.array(len(b.sample_random_uniform(n=500)))
+    save("nested_boundary", **out)
+
+
 # ---------------------------------------------------------------------------- hard constraint (SURVEY f3)
 def poisson_hard_constraint(hidden, n, name):
     """Poisson residual on tp.models.HardConstraint(FCN, g): the output transform g(u, x) = x1 (1 - x1) x2 (1 - x2) u
@@ -472,6 +506,7 @@ if __name__ == "__main__":
         "cut_boundary": cut_boundary,
         "union_boundary": union_boundary,
         "intersection_boundary": intersection_boundary,
+        "nested_boundary": nested_boundary,
         # hidden width 128 (configs 2 and 3 of BASELINE.json at reduced depth): the wide tensor-core path
         "heat_3x128": lambda: heat((128, 128, 128), 211, "heat_3x128"),
         "ns_3x128": lambda: navier_stokes((128, 128, 128), 147, "ns_3x128"),

@@ -438,6 +438,50 @@ def test_product_boundary_is_the_union_of_the_two_faces():
         assert not b._contains(off).any()
 
 
+def test_nested_boolean_boundaries_match_reference():
+    """boundaries whose operands are boolean domains themselves -- a cut of a cut, a cut of a union, a cut BY a union (the
+    reference recurses through domain_a.boundary, cut.py:111-201): membership bit for bit, normals, volume, counts, every
+    sampled point on the boundary."""
+    import warnings
+    import torchphysics_b200 as tp
+    from tests.test_oracle_golden import NESTED
+    G = load("nested_boundary")
+    X = tp.spaces.R2("x")
+    circ = tp.domains.Circle(X, [0.1, -0.2], 0.9)
+    sq = tp.domains.Parallelogram(X, [-0.25, -0.25], [0.25, -0.25], [-0.25, 0.25])
+    bite = tp.domains.Circle(X, [0.7, 0.1], 0.45)
+    sq3 = tp.domains.Parallelogram(X, [0.0, -0.8], [0.5, -0.8], [0.0, -0.4])
+    sq4 = tp.domains.Parallelogram(X, [-0.5, 0.0], [1.0, 0.0], [-0.5, 0.5])
+    cases = (("cutcut", (circ - sq) - bite), ("unioncut", (sq4 + bite) - sq), ("cutunion", circ - (sq + sq3)))
+    for nm, dom in cases:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            b = dom.boundary
+            cand = tp.spaces.Points(torch.from_numpy(G["cand"]).cuda(), X)
+            assert np.array_equal(b._contains(cand).reshape(-1).cpu().numpy(), G["in_" + nm]), nm
+            assert abs(float(b.volume()) - float(G["vol_" + nm][0])) < 1e-5
+            nrm = b.normal(tp.spaces.Points(torch.from_numpy(G["on_" + nm]).cuda(), X)).cpu().numpy()
+            assert np.allclose(nrm, G["normal_" + nm], rtol=1e-6, atol=1e-7), nm
+            for n in (40, 200):
+                assert len(b.sample_grid(n, device="cuda")) == int(G[f"ngrid_{nm}_{n}"]) == n
+            torch.manual_seed(13)
+            p = b.sample_random_uniform(n=2000, device="cuda").as_tensor.cpu().numpy()
+            assert len(p) == 2000
+            assert geometry.any_boundary_contains(NESTED[nm], p).mean() > 0.97      # (isclose membership is brittle by an ulp)
+            d = b.sample_random_uniform(d=20.0, device="cuda")
+            assert 0 < len(d) <= int(np.ceil(20.0 * float(b.volume()))) + 4
+    # a Dirichlet condition on the boundary of the doubly cut disc trains through the native path
+    U = tp.spaces.R1("u")
+    model = tp.models.FCN(X, U, hidden=(16, 16)).cuda()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bnd = ((circ - sq) - bite).boundary
+        cond = tp.conditions.PINNCondition(model, tp.samplers.RandomUniformSampler(bnd, n_points=300), lambda u: u - 1.0)
+        loss = cond(device="cuda")
+        loss.backward()
+    assert torch.isfinite(loss)
+
+
 def test_union_boundary_matches_reference():
     """boundary of A + B: overlapping shapes and two squares sharing an edge (normal-agreement test of reference
     union.py:161-192): membership bit for bit, normals, volume, counts."""

@@ -631,12 +631,47 @@ class CutBoundaryDomain(Domain):
 
     def __init__(self, domain):
         a, b = domain.domain_a, domain.domain_b
-        if not (isinstance(a, _ShapeDomain) and isinstance(b, _ShapeDomain)) or isinstance(a, BoundaryDomain) \
-                or isinstance(b, BoundaryDomain):
-            raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "boundary of a cut: both operands must be basic shapes")
+        for d in (a, b):
+            if isinstance(d, BoundaryDomain) or not isinstance(d, (_ShapeDomain, _BooleanDomain)):
+                raise _lib.TpxError(_lib.TPX_E_UNSUPPORTED, "boundary of a boolean domain: the operands must be basic shapes "
+                                    "or cuts / unions / intersections of them")
         super().__init__(space=domain.space, dim=domain.dim - 1)
         self.domain = domain
         self.necessary_variables = domain.necessary_variables
+        # two basic shapes: membership is ONE region program and the rejection sampler one kernel per round; nested operands
+        # (a cut of a cut, ...) compose their operands' membership / sampling / normal calls on the device, as the reference
+        # does on the host (cut.py:111-201 with domain_a.boundary itself a boolean boundary)
+        self._basic = isinstance(a, _ShapeDomain) and isinstance(b, _ShapeDomain)
+
+    def _mask(self, in_a, in_b, on_a, on_b):
+        return (on_a & ~in_b) | (on_b & in_a & ~on_a)
+
+    def _contains_rows(self, rows, col, out_device):
+        if self._basic:
+            return super()._contains_rows(rows, col, out_device)
+        a, b = self.domain.domain_a, self.domain.domain_b
+        dev = _compute_device(rows.device)
+        rows = rows.to(device=dev, dtype=torch.float32).contiguous()
+        return self._mask(a._contains_rows(rows, col, dev), b._contains_rows(rows, col, dev),
+                          a.boundary._contains_rows(rows, col, dev), b.boundary._contains_rows(rows, col, dev)).to(out_device)
+
+    def _fill_random_composed(self, out, col, n):
+        """sampler_helper.py:166-200 with the operands' own samplers: candidates alternate between the two boundaries (in
+        proportion to their lengths), kept where they lie on this boundary, appended in candidate order."""
+        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
+        vm = _F32(self._volume_value())
+        scaled = [int(_F32(n) * _F32(a._volume_value()) / vm) + 1, int(_F32(n) * _F32(b._volume_value()) / vm) + 1]
+        filled, use_b, rounds = 0, 0, 0
+        while filled < n:
+            cand = torch.zeros((scaled[use_b], out.shape[1]), dtype=torch.float32, device=out.device)
+            (b if use_b else a)._fill_random(cand, col, scaled[use_b])
+            good = self._masked(cand, self._contains_rows(cand, col, out.device))[:n - filled]
+            out[filled:filled + len(good), col:col + self.space.dim] = good[:, col:col + self.space.dim]
+            filled += len(good)
+            use_b = 1 - use_b
+            rounds += 1
+            if rounds > 4000:
+                raise RuntimeError("Rejection sampling on the boundary of a boolean domain does not find enough points.")
 
     def __call__(self, **data):
         return self
@@ -668,6 +703,8 @@ class CutBoundaryDomain(Domain):
     def _fill_random(self, out, col, n):
         if n == 0:
             return
+        if not self._basic:
+            return self._fill_random_composed(out, col, n)
         a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
         vm = _F32(self._volume_value())
         scaled = [int(_F32(n) * _F32(a._volume_value()) / vm) + 1, int(_F32(n) * _F32(b._volume_value()) / vm) + 1]
@@ -776,22 +813,8 @@ class UnionBoundaryDomain(CutBoundaryDomain):
         return _F32(self.domain.domain_a.boundary._volume_value()) + _F32(self.domain.domain_b.boundary._volume_value())
 
     def _fill_random(self, out, col, n):
-        if n == 0:
-            return
-        a, b = self.domain.domain_a.boundary, self.domain.domain_b.boundary
-        vm = _F32(self._volume_value())
-        scaled = [int(_F32(n) * _F32(a._volume_value()) / vm) + 1, int(_F32(n) * _F32(b._volume_value()) / vm) + 1]
-        filled, use_b, rounds = 0, 0, 0
-        while filled < n:                          # sampler_helper.py:166-200
-            cand = torch.zeros((scaled[use_b], out.shape[1]), dtype=torch.float32, device=out.device)
-            (b if use_b else a)._fill_random(cand, col, scaled[use_b])
-            good = self._masked(cand, self._contains_rows(cand, col, out.device))[:n - filled]
-            out[filled:filled + len(good), col:col + self.space.dim] = good[:, col:col + self.space.dim]
-            filled += len(good)
-            use_b = 1 - use_b
-            rounds += 1
-            if rounds > 4000:
-                raise RuntimeError("Rejection sampling on the union boundary does not find enough points.")
+        if n > 0:
+            self._fill_random_composed(out, col, n)
 
     def _parts_with_d(self, sample, d, params, device):
         """density mode (union.py:215-224 / 250-259): A's boundary outside B, B's boundary not strictly inside A."""
@@ -822,6 +845,9 @@ class IntersectionBoundaryDomain(CutBoundaryDomain):
         # (on dA and in B) or (on dB and in A)
         ops = [S | (0 << 8), S | (1 << 8), AND, S | (2 << 8), S | (3 << 8), AND, OR]
         return shapes, ops
+
+    def _mask(self, in_a, in_b, on_a, on_b):
+        return (on_a & in_b) | (on_b & in_a)
 
     def _get_volume(self):
         warnings.warn("Exact volume of this intersection-boundary is not known, will use the estimate: volume = boundary_a + "
