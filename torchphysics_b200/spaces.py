@@ -238,8 +238,12 @@ class Points:
     def coordinates(self):
         sl = self.space.column_slices()
         width = self._t.shape[-1]
-        # a variable that spans every column IS the tensor: no slice node (its backward would be a zero fill + copy of the batch)
-        return {name: (self._t if (sl[name].start, sl[name].stop) == (0, width) else self._t[..., sl[name]]) for name in self.space}
+        # a variable that spans every column of a tensor with a graph (a model output) IS that tensor: no slice node, whose
+        # backward would be a zero fill + copy of the batch.  Tensors without a graph keep the reference's fresh views
+        # (``points.py:158-165``): callers may mark those as leaves.
+        whole = self._t.requires_grad
+        return {name: (self._t if whole and (sl[name].start, sl[name].stop) == (0, width) else self._t[..., sl[name]])
+                for name in self.space}
 
     @property
     def as_tensor(self):
@@ -399,8 +403,6 @@ class Points:
         leaves so that the native jet path can identify derivative variables."""
         coords = self.coordinates
         for name in coords:
-            if coords[name] is self._t:            # a variable spanning every column: a leaf of its own, not the caller's buffer
-                coords[name] = self._t.detach() if not self._t.requires_grad else self._t[..., :]
             coords[name].requires_grad = True
         tracked = Points.from_coordinates(coords)
         tracked._coord_leaves = coords
