@@ -188,6 +188,35 @@ def cpu_reference_rate(cfg, steps, warmup, n_points):
     return n_points * len(times) / total, 1e3 * total / len(times), cores, kind, what
 
 
+def gpu_reference_rate(cfg, steps, warmup, n_points, device):
+    """BASELINE.md section 3, optional second row: the UNMODIFIED reference (baseline/_ref) with device='cuda' on this B200 --
+    stock PyTorch kernels through its own autograd graphs -- for the same step; (rate, ms/step) or raises."""
+    import torch
+    ref, why = import_reference()
+    if ref is None:
+        raise RuntimeError(why)
+    torch.manual_seed(0)
+    model, cond, _ = build_config(ref, cfg, n_points, device)
+    model.to(device)
+    dev = str(device)
+    for _ in range(warmup):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device=dev)
+        loss.backward()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.zero_grad(set_to_none=True)
+        loss = cond(device=dev)
+        loss.backward()
+    e1.record()
+    e1.synchronize()
+    float(loss.detach())
+    ms = e0.elapsed_time(e1) / steps
+    return n_points / (ms * 1e-3), ms
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -565,6 +594,16 @@ def run_native(args):
                                         "sample": f"8 steps of {c['cpu_points']} points after 2 warm-ups, {what}"}
             except Exception as e:
                 line["cpu_baseline"] = {"error": repr(e)[:300]}
+            if cfg == 1:
+                # optional second row of BASELINE.md section 3: the unmodified reference on THIS GPU (stock PyTorch kernels)
+                try:
+                    npts = 1 << 18                      # its autograd graphs of a 2 Mi-point step do not fit comfortably; flat in N
+                    rate, ms = gpu_reference_rate(cfg, 5, 3, npts, ctx.dev)
+                    line["reference_on_gpu"] = {"value": rate, "unit": c["unit"], "ms_per_step": ms,
+                                                "sample": f"5 steps of {npts} points after 3 warm-ups, boschresearch/torchphysics "
+                                                          "(baseline/_ref) Condition.forward(device='cuda') + loss.backward() on the same B200"}
+                except Exception as e:
+                    line["reference_on_gpu"] = {"error": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         ctx.dist.destroy_process_group()
