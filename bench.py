@@ -300,7 +300,8 @@ class Ctx:
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
-        os.environ.pop("TPX_ALLOW_TORCH", None)             # the torch fallback switch never applies to a benchmark
+        for name in ("TPX_ALLOW_TORCH", "TPX_DISABLE_TC", "TPX_DISABLE_TCW", "TPX_TCW_SPLIT", "TPX_TCP", "TPX_SAVE_GB"):
+            os.environ.pop(name, None)                      # development switches never apply to a benchmark
         from torchphysics_b200 import _lib
         _lib.lib()                                          # fail loudly if libtpx.so is missing
 

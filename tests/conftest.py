@@ -8,6 +8,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# The development switches of the library must not leak into a test run from the caller's environment:
+# a parity test that silently ran the torch fallback or another kernel family would prove nothing.  Tests that compare kernel
+# families set the switch themselves, in a subprocess.
+for _name in ("TPX_ALLOW_TORCH", "TPX_DISABLE_TC", "TPX_DISABLE_TCW", "TPX_TCW_SPLIT", "TPX_TCP", "TPX_SAVE_GB"):
+    os.environ.pop(_name, None)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
