@@ -11,8 +11,10 @@ if ROOT not in sys.path:
 # The development switches of the library must not leak into a test run from the caller's environment:
 # a parity test that silently ran the torch fallback or another kernel family would prove nothing.  Tests that compare kernel
 # families set the switch themselves, in a subprocess.
-for _name in ("TPX_ALLOW_TORCH", "TPX_DISABLE_TC", "TPX_DISABLE_TCW", "TPX_TCW_SPLIT", "TPX_TCP", "TPX_SAVE_GB"):
-    os.environ.pop(_name, None)
+# (A test that re-runs pytest under a switch marks its child with TPX_TEST_SUBPROCESS=1.)
+if os.environ.get("TPX_TEST_SUBPROCESS") != "1":
+    for _name in ("TPX_ALLOW_TORCH", "TPX_DISABLE_TC", "TPX_DISABLE_TCW", "TPX_TCW_SPLIT", "TPX_TCP", "TPX_SAVE_GB"):
+        os.environ.pop(_name, None)
 
 
 def pytest_configure(config):

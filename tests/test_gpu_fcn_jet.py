@@ -418,7 +418,7 @@ def test_round2_split_fp16_kernels_in_a_subprocess():
     import os
     import subprocess
     import sys
-    env = dict(os.environ, TPX_TCP="1")
+    env = dict(os.environ, TPX_TCP="1", TPX_TEST_SUBPROCESS="1")       # (conftest.py removes the switches otherwise)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
                         "test_poisson_golden or test_heat_golden or test_navier_stokes_golden or test_deep_ritz_golden "
                         "or test_against_float64_oracle or test_linearity_of_reverse_at_scale"],
