@@ -411,6 +411,19 @@ def test_reverse_at_scale_equals_float64_sum_of_short_sweeps(width, N):
         assert float((full - ref).abs().max() / ref.abs().max()) < TOL       # 1.1e-4 before the periodic flush
 
 
+def test_round2_switch_is_active_in_the_child_run():
+    """runs only inside the child pytest of the next test: with TPX_TCP=1 the checkpoint buffer of a 4 x 64 net has the layout of
+    tcp_fwd / tce_bwd (128-point tiles + row statistics), not tc_fwd's -- i.e. the switch reached the library"""
+    import os
+    if os.environ.get("TPX_TCP") != "1":
+        pytest.skip("only meaningful under TPX_TCP=1")
+    from torchphysics_b200.engine import FcnEngine, JetSpec
+    seq = ref_autograd.build_fcn(2, 1, (64,) * 4).cuda()
+    eng = FcnEngine([m for m in seq if isinstance(m, nn.Linear)], "tanh")
+    n = 4096
+    assert eng.saved_bytes(JetSpec((0, 1), (1.0, 1.0)), n) != ((n + 31) // 32) * 4 * 4 * 64 * 32 * 4 + 160 * 5 * 64 * 64 * 4
+
+
 def test_round2_split_fp16_kernels_in_a_subprocess():
     """TPX_TCP=1 (a development A/B switch, read once per process) routes width <= 64 networks through the round-2
     kernels tcp_fwd_kernel (points as TMEM lanes, split-fp16 operands with power-of-two scales from bounds) and
@@ -421,9 +434,10 @@ def test_round2_split_fp16_kernels_in_a_subprocess():
     env = dict(os.environ, TPX_TCP="1", TPX_TEST_SUBPROCESS="1")       # (conftest.py removes the switches otherwise)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
                         "test_poisson_golden or test_heat_golden or test_navier_stokes_golden or test_deep_ritz_golden "
-                        "or test_against_float64_oracle or test_linearity_of_reverse_at_scale"],
+                        "or test_against_float64_oracle or test_linearity_of_reverse_at_scale or test_round2_switch_is_active"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]           # the switch check ran, i.e. the child saw TPX_TCP
 
 
 @pytest.mark.parametrize("d_in,d_out,hidden,dcols,lap_w,N", [(1, 256, (64,) * 4, (0,), (1.0,), 16384 + 5),
