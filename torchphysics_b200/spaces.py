@@ -8,6 +8,7 @@ which input column is which variable, and ``track_coord_gradients`` (reference
 called with; the native jet path recognises those leaves by identity
 (``torchphysics_b200/jets.py``).
 """
+import math
 from collections import Counter, OrderedDict
 
 import numpy as np
@@ -262,7 +263,7 @@ class Points:
         return len(self) == 0 and self.space.dim == 0
 
     def __len__(self):
-        return int(np.prod(self._t.shape[:-1]))
+        return math.prod(self._t.shape[:-1])
 
     def __repr__(self):
         return f"{type(self).__name__}:\n{self.coordinates}"
