@@ -517,7 +517,7 @@ def run_native(args):
     value = N * world / (ms_step * 1e-3)
 
     # ---- end to end through the public API, host buffers ---------------------------------
-    ms_e2e, h2d, _ = api_step_rate(ctx, cfg, N, args.steps, max(3, args.warmup), host=True)
+    ms_e2e, h2d, _ = api_step_rate(ctx, cfg, N, args.steps, max(5, args.warmup), host=True)   # (3 were too few at 4 ranks: pinned buffers, NCCL streams)
     e2e = N * world / (ms_e2e * 1e-3)
     # ---- dominant kernel alone (roofline) ---------------------------------------------------
     ms_bwd, ms_fwd = reverse_kernel_ms(ctx, cfg, N)
