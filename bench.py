@@ -507,7 +507,7 @@ def run_native(args):
     extra = {}
     if cfg == 1:
         ms_step, n_batches, bytes_per_batch, n_theta = run_config1_resident(ctx, args, N)
-        launches = 10          # fwd, 5 elementwise kernels of f, residual add, loss, loss adjoint, bwd, unpack (+ copies)
+        launches = 11          # fwd, 5 elementwise kernels of f, residual add, loss, loss adjoint, bwd, dW reduction, unpack (6 of them libtpx's)
         extra = {"l2": f"{n_batches} rotating input batches of {bytes_per_batch/1e6:.0f} MB (> 126 MB L2 in total)", "theta": n_theta}
     else:
         ms_step, _, _ = api_step_rate(ctx, cfg, N, args.steps, args.warmup)
@@ -539,7 +539,9 @@ def run_native(args):
             "clocks": clk,
         }
         if line["gpu_launches"] is None:
-            line["gpu_launches"] = {2: 40, 3: 60, 4: 30, 5: 120}.get(cfg, 10)   # kernel launches of this repo per step (layer-major sweeps)
+            # libtpx kernel launches per step, counted in the torch.profiler tables of profiles/r02b_*_step_kernels.txt (layer-major
+            # sweeps: forward, reverse and dW-reduction launch per hidden matrix; config 5: 13 micro-batches of 4 blocks per matrix)
+            line["gpu_launches"] = {2: 23, 3: 23, 4: 25, 5: 1150}.get(cfg, 11)
     # ---- the other configurations (short runs) ----------------------------------------------
     if cfg == 1 and not args.no_other_configs:
         blocks = {}
