@@ -148,7 +148,9 @@ class Trainer:
         torch.cuda.synchronize(self.device)
         domains.use_device_key(None)
         optimizer.use_device_step(False)
-        self._graph = graph
+        # the graph is not kept: its private memory pool (and, with several ranks, the captured NCCL kernels -- a process group
+        # cannot be destroyed while a graph that holds them is alive) goes away here; the losses above are copies
+        del graph, static_loss
         self._last = self.losses[-1]
         return self.max_steps
 
