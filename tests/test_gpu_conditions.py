@@ -559,3 +559,34 @@ def test_micro_batched_condition_equals_the_single_batch(monkeypatch):
         assert (a is None) == (b is None)                 # the output bias keeps grad None (reference parity)
         if a is not None:
             assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())
+
+
+@pytest.mark.parametrize("hidden", [(48,) * 3, (128,) * 3])            # width-64 kernels / wide path
+def test_heat_equation_in_three_space_dimensions(hidden):
+    """u_t = Lap_xyz u needs four derivative directions, one more than a jet carries (TPX_MAX_ND = 3): the time derivative
+    comes from a second native evaluation of the same network on the same points (jets.JetEvaluation.extra) instead of a
+    TpxError.  Loss and dLoss/dtheta against the reference's definition with torch autograd on the same modules."""
+    import torchphysics_b200 as tp
+    torch.manual_seed(2)
+    X, T, U = tp.spaces.R3("x"), tp.spaces.R1("t"), tp.spaces.R1("u")
+    model = tp.models.FCN(X * T, U, hidden=hidden).cuda()
+    pts = torch.rand(2000, 4)
+    sampler = tp.samplers.DataSampler(tp.spaces.Points(pts, X * T))
+    cond = tp.conditions.PINNCondition(model, sampler, lambda u, x, t: tp.utils.grad(u, t) - 0.3 * tp.utils.laplacian(u, x))
+    for it in range(3):                                                  # the first call learns the jet spec
+        model.zero_grad(set_to_none=True)
+        loss = cond(device="cuda")
+        loss.backward()
+    got = _grads(model)
+    model.zero_grad(set_to_none=True)
+    x = pts[:, :3].cuda().requires_grad_(True)
+    t = pts[:, 3:].cuda().requires_grad_(True)
+    u = model.sequential(torch.cat([x, t], dim=1))
+    g = torch.autograd.grad(u.sum(), x, create_graph=True)[0]
+    lap = sum(torch.autograd.grad(g[:, i].sum(), x, create_graph=True)[0][:, i:i + 1] for i in range(3))
+    ut = torch.autograd.grad(u.sum(), t, create_graph=True)[0]
+    want = ((ut - 0.3 * lap) ** 2).mean()
+    want.backward()
+    assert abs(float(loss) - float(want)) < TOL * abs(float(want))
+    for a, w in zip(got[:-1], _grads(model)[:-1]):
+        assert relerr(a, w) < TOL

@@ -29,6 +29,9 @@ class AnalyticEvaluation:
         self.spec = need
         return True
 
+    def lap_spec(self):
+        return self.spec
+
     def _x(self):
         x = self.leaf.detach()
         return x[..., 0], x[..., 1]
@@ -140,3 +143,51 @@ def test_laplacian_accepts_only_its_own_gradient_as_grad_argument():
         operators.laplacian(u0, x, grad=operators.grad(u[:, 1:], x))         # the gradient of another output column
     with pytest.raises(_lib.TpxError):
         operators.laplacian(u0, x, grad=torch.ones(len(x), 2, dtype=torch.float64))
+
+
+def test_streams_beyond_one_jet_come_from_further_evaluations():
+    """a heat equation in three space dimensions needs d/dt next to the Laplacian in (x, y, z): four directions, more than one
+    jet carries (TPX_MAX_ND = 3).  JetEvaluation answers such requests from a second evaluation of the same network on the same
+    points instead of refusing; the same holds for two different Laplacians.  (Stand-in engine: torch ops, same protocol.)"""
+    from tests.test_host_deeponet import _TorchJetEngine
+    torch.manual_seed(0)
+    lins = [torch.nn.Linear(4, 16), torch.nn.Linear(16, 16), torch.nn.Linear(16, 2)]
+    for lin in lins:
+        lin.double()
+    eng = _TorchJetEngine(lins)
+    n = 50
+    xyz = torch.rand(n, 3, dtype=torch.float64).requires_grad_(True)
+    t = torch.rand(n, 1, dtype=torch.float64).requires_grad_(True)
+    pts = torch.cat([xyz, t], dim=1)
+    leaf_cols = {id(xyz): (xyz, [0, 1, 2]), id(t): (t, [3])}
+    hints = {}
+    ev = jets.JetEvaluation(eng, pts.detach(), (n,), leaf_cols, hints, "k", None, JetSpec())
+    u = jets.JetTensor.wrap(ev.value(), ev, [0, 1])
+    lap = operators.laplacian(u[:, :1], xyz)
+    ut = operators.grad(u[:, :1], t)
+    lap_t = operators.laplacian(u[:, 1:], t)                  # a second, different Laplacian
+    gx = operators.grad(u[:, 1:], xyz)
+    assert len(ev.extra) >= 1                                 # the requests did not fit one jet
+    # the reference's definition on the same modules
+    h = pts
+    for i, lin in enumerate(lins):
+        h = lin(h)
+        if i < len(lins) - 1:
+            h = torch.tanh(h)
+
+    def d(y, v):
+        return torch.autograd.grad(y.sum(), v, create_graph=True)[0]
+
+    g0 = d(h[:, 0], xyz)
+    want_lap = sum(d(g0[:, i], xyz)[:, i] for i in range(3))[:, None]
+    assert torch.allclose(lap, want_lap, rtol=1e-9, atol=1e-10)
+    assert torch.allclose(ut, d(h[:, 0], t), rtol=1e-9, atol=1e-10)
+    assert torch.allclose(lap_t, d(d(h[:, 1], t)[:, 0], t), rtol=1e-9, atol=1e-10)
+    assert torch.allclose(gx, d(h[:, 1], xyz), rtol=1e-9, atol=1e-10)
+    # parameter gradients flow through every evaluation
+    loss = ((ut - lap) ** 2).mean() + (lap_t ** 2).mean() + (gx ** 2).mean()
+    want = ((d(h[:, 0], t) - want_lap) ** 2).mean() + (d(d(h[:, 1], t)[:, 0], t) ** 2).mean() + (d(h[:, 1], xyz) ** 2).mean()
+    g_native = torch.autograd.grad(loss, [lin.weight for lin in lins])
+    g_want = torch.autograd.grad(want, [lin.weight for lin in lins])
+    for a, b in zip(g_native, g_want):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-10)

@@ -267,20 +267,25 @@ class DeepONetEvaluation:
     def ensure(self, need):
         return self.tev.ensure(need)
 
+    def lap_spec(self):
+        return self.tev.lap_spec()
+
     def value(self):
         return self._value
 
     def first(self, out_cols, in_col):
-        k = self.tev.spec.dcols.index(in_col)
-        key = ("d", id(self.tev.du), k)
+        part = self.tev.part_with(in_col)
+        k = part.spec.dcols.index(in_col)
+        key = ("d", id(part.du), k)
         if key not in self._cache:
-            self._cache[key] = self._contract(self.tev.du[k] if self.tev.spec.out_major else self.tev.du[:, :, k])
+            self._cache[key] = self._contract(part.du[k] if part.spec.out_major else part.du[:, :, k])
         return jets.JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
 
     def second(self, out_cols):
-        key = ("lap", id(self.tev.lap))
+        lap = self.tev.lap_part().lap
+        key = ("lap", id(lap))
         if key not in self._cache:
-            self._cache[key] = self._contract(self.tev.lap)
+            self._cache[key] = self._contract(lap)
         return jets.JetEvaluation._columns(self._cache[key], out_cols, self._cache[key].dim() - 1)
 
     def plain(self):

@@ -71,6 +71,11 @@ class JetEvaluation:
         self.spec = spec
         self.params = params                # None: the engine's own module parameters
         self.u, self.du, self.lap = engine.jet(x2d, spec, params)
+        # Streams that do not fit ONE jet (more than 3 derivative directions in total -- a Laplacian in three space dimensions
+        # next to a time derivative -- or two different Laplacians) come from further evaluations of the same network on the
+        # same points, created on demand; ``_hit`` is the evaluation that answered the last ``ensure``.
+        self.extra = []
+        self._hit = self
 
     def columns_of(self, var):
         hit = self.leaf_cols.get(id(var))
@@ -87,6 +92,20 @@ class JetEvaluation:
 
     def ensure(self, need):
         """make sure the computed streams cover ``need``; returns False if impossible."""
+        for ev in [self] + self.extra:
+            if ev._ensure_own(need):
+                self._hit = ev
+                return True
+        if need.nd > 3:
+            return False
+        ev = JetEvaluation(self.engine, self.x, self.batch_shape, self.leaf_cols, {}, None, None,
+                           JetSpec(need.dcols, need.lap_w, out_major=self.spec.out_major), self.params)
+        self.extra.append(ev)
+        self._hit = ev
+        return True
+
+    def _ensure_own(self, need):
+        """extend THIS evaluation's jet to cover ``need`` if the union still is one jet."""
         if self.spec.covers(need):
             return True
         cols = list(self.spec.dcols)
@@ -126,13 +145,30 @@ class JetEvaluation:
             return t.narrow(axis, cols[0], len(cols))
         return t.index_select(axis, torch.as_tensor(cols, device=t.device))
 
+    def part_with(self, in_col):
+        """the evaluation (this one or a further one) whose jet carries direction ``in_col``"""
+        if in_col in self._hit.spec.dcols:
+            return self._hit
+        for ev in [self] + self.extra:
+            if in_col in ev.spec.dcols:
+                return ev
+        raise KeyError(in_col)
+
+    def lap_part(self):
+        """the evaluation whose Laplacian stream answers the last ``ensure``"""
+        return self._hit if self._hit.spec.lap else self
+
+    def lap_spec(self):
+        """directions and weights of the Laplacian stream that ``second`` returns"""
+        return self.lap_part().spec
+
     def first(self, out_cols, in_col):
-        k = self.spec.dcols.index(in_col)
-        d = self.du.select(2, k)
+        ev = self.part_with(in_col)
+        d = ev.du.select(2, ev.spec.dcols.index(in_col))
         return self._columns(d, out_cols, 1).reshape(*self.batch_shape, len(out_cols))
 
     def second(self, out_cols):
-        return self._columns(self.lap, out_cols, 1).reshape(*self.batch_shape, len(out_cols))
+        return self._columns(self.lap_part().lap, out_cols, 1).reshape(*self.batch_shape, len(out_cols))
 
     def plain(self):
         """the same output through torch ops with a graph to the coordinate leaves."""
@@ -166,6 +202,9 @@ class JoinedEvaluation:
     @property
     def spec(self):
         return self.parts[0][0].spec
+
+    def lap_spec(self):
+        return self.parts[0][0].lap_spec()
 
     def _gather(self, out_cols, fn):
         pieces, run_ev, run_cols = [], None, []
@@ -260,6 +299,9 @@ class ConstrainedEvaluation:
     def spec(self):
         return self.inner.spec
 
+    def lap_spec(self):
+        return self.inner.lap_spec()
+
     def value(self):
         if "value" not in self._cache:
             self._cache["value"] = self._apply({}, self.inner.value())
@@ -276,7 +318,7 @@ class ConstrainedEvaluation:
 
     def second(self, out_cols):
         if "lap" not in self._cache:
-            spec = self.inner.spec
+            spec = self.inner.lap_spec()
             acc = self._path(None, self.inner.second(list(range(self.inner.engine.d_out))), 1)[0]
             for c, w in zip(spec.dcols, spec.lap_w):
                 if w != 0.0:
@@ -326,6 +368,9 @@ class ExprEvaluation:
     def spec(self):
         return self.base.spec
 
+    def lap_spec(self):
+        return self.base.lap_spec()
+
     def ensure(self, need):
         self._cache.clear()
         seen, ok = set(), True
@@ -360,7 +405,7 @@ class ExprEvaluation:
         if op[0] == "jet":
             return op[1].second(op[2]).reshape(op[3].shape)
         acc = None
-        spec = self.spec
+        spec = self.lap_spec()
         for c, w in zip(spec.dcols, spec.lap_w or ()):
             if w == 0.0:
                 continue
@@ -410,7 +455,7 @@ class ExprEvaluation:
 
     def second(self, out_cols):
         if "lap" not in self._cache:
-            spec = self.spec
+            spec = self.lap_spec()
             acc = self._path([self._second_of(op) for op in self.operands], 1)[0]
             for c, w in zip(spec.dcols, spec.lap_w):
                 if w != 0.0:
