@@ -212,3 +212,37 @@ def test_deeponet_refuses_cpu_evaluation():
     assert branch.current_out.shape == (1, 1, 16)
     with pytest.raises(_lib.TpxError):
         net(tp.spaces.Points(torch.tensor([[[2.0], [0.0]]]), tp.spaces.R1("t")))
+
+
+def test_deeponet_step_leaves_no_evaluation_behind(monkeypatch):
+    """every native evaluation of a step (trunk jets, the DeepONet wrapper around them) is released by reference counting when
+    the step's loss goes away -- no cycle keeps batch-sized streams or the step's autograd graph alive."""
+    import gc
+    import weakref
+    import torchphysics_b200 as tp
+    from torchphysics_b200 import deeponet, jets
+    created = []
+    for cls in (jets.JetEvaluation, deeponet.DeepONetEvaluation):
+        orig = cls.__init__
+
+        def recording(self, *a, _orig=orig, **k):
+            _orig(self, *a, **k)
+            created.append(weakref.ref(self))
+        monkeypatch.setattr(cls, "__init__", recording)
+    G = load("deeponet_2x32")
+    net, trunk, branch, fsampler, tsampler = build_deeponet(tp, G)
+    object.__setattr__(trunk, "_engine", _TorchJetEngine([m for m in trunk.sequential if isinstance(m, torch.nn.Linear)]))
+    cond = tp.conditions.PIDeepONetCondition(net, fsampler, tsampler, lambda u, t, f: tp.utils.laplacian(u, t) + tp.utils.grad(u, t) + f)
+    gc.collect()
+    gc.disable()
+    try:
+        for _ in range(2):
+            net.zero_grad(set_to_none=True)
+            loss = cond(device="cpu")
+            loss.backward()
+            del loss
+        assert len(created) >= 4
+        # what the modules legitimately keep is a tensor (the branch coefficients of the last fix_input), not an evaluation
+        assert all(ref() is None for ref in created)
+    finally:
+        gc.enable()

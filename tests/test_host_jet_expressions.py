@@ -191,3 +191,31 @@ def test_streams_beyond_one_jet_come_from_further_evaluations():
     g_want = torch.autograd.grad(want, [lin.weight for lin in lins])
     for a, b in zip(g_native, g_want):
         assert torch.allclose(a, b, rtol=1e-8, atol=1e-10)
+
+
+def test_evaluations_die_with_their_step_without_the_cycle_collector():
+    """the streams of a step (and the autograd graph behind them) must be released by reference counting when the step's tensors
+    go away: an evaluation kept alive by a reference cycle would hold batch-sized tensors until the next gc run and keep the
+    AccumulateGrad nodes of an eager step alive into a CUDA-graph capture (which then fails)."""
+    import gc
+    import weakref
+    from tests.test_host_deeponet import _TorchJetEngine
+    lins = [torch.nn.Linear(4, 8).double(), torch.nn.Linear(8, 8).double(), torch.nn.Linear(8, 1).double()]
+    eng = _TorchJetEngine(lins)
+    xyz = torch.rand(20, 3, dtype=torch.float64).requires_grad_(True)
+    t = torch.rand(20, 1, dtype=torch.float64).requires_grad_(True)
+    gc.collect()
+    gc.disable()
+    try:
+        ev = jets.JetEvaluation(eng, torch.cat([xyz, t], dim=1).detach(), (20,), {id(xyz): (xyz, [0, 1, 2]), id(t): (t, [3])},
+                                {}, "k", None, JetSpec())
+        u = jets.JetTensor.wrap(ev.value(), ev, [0])
+        r = operators.grad(u, t) - operators.laplacian(u * u, xyz)          # a second evaluation and an expression evaluation
+        loss = (r ** 2).mean()
+        loss.backward()
+        refs = [weakref.ref(ev)] + [weakref.ref(e) for e in ev.extra]
+        assert len(refs) >= 2
+        del ev, u, r, loss
+        assert all(ref() is None for ref in refs)
+    finally:
+        gc.enable()

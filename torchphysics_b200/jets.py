@@ -75,7 +75,7 @@ class JetEvaluation:
         # next to a time derivative -- or two different Laplacians) come from further evaluations of the same network on the
         # same points, created on demand; ``_hit`` is the evaluation that answered the last ``ensure``.
         self.extra = []
-        self._hit = self
+        self._hit = None                    # None: this evaluation itself (no reference cycle: the streams must die with the step)
 
     def columns_of(self, var):
         hit = self.leaf_cols.get(id(var))
@@ -94,7 +94,7 @@ class JetEvaluation:
         """make sure the computed streams cover ``need``; returns False if impossible."""
         for ev in [self] + self.extra:
             if ev._ensure_own(need):
-                self._hit = ev
+                self._hit = None if ev is self else ev
                 return True
         if need.nd > 3:
             return False
@@ -147,8 +147,9 @@ class JetEvaluation:
 
     def part_with(self, in_col):
         """the evaluation (this one or a further one) whose jet carries direction ``in_col``"""
-        if in_col in self._hit.spec.dcols:
-            return self._hit
+        hit = self._hit or self
+        if in_col in hit.spec.dcols:
+            return hit
         for ev in [self] + self.extra:
             if in_col in ev.spec.dcols:
                 return ev
@@ -156,7 +157,8 @@ class JetEvaluation:
 
     def lap_part(self):
         """the evaluation whose Laplacian stream answers the last ``ensure``"""
-        return self._hit if self._hit.spec.lap else self
+        hit = self._hit or self
+        return hit if hit.spec.lap else self
 
     def lap_spec(self):
         """directions and weights of the Laplacian stream that ``second`` returns"""
