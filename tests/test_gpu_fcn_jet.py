@@ -139,7 +139,12 @@ CASES = [
     (3, 2, (65, 80), "tanh", (2, 0), None, 1),
     (4, 1, (128, 72, 128, 90), "tanh", (3, 0, 1), None, 2371),
     (2, 4, (112,) * 3, "tanh", (1,), (0.75,), 2500),
-    (5, 1, (128,) * 3, "tanh", (0, 4), (1.0, 1.0), 150),       # d_in > 4: FP32 kernels
+    # 5..8 inputs: layer 0 has kernels of its own on the wide path (w_in_fwd_kernel / w_in_bwd_kernel); narrow nets are padded to it
+    (5, 1, (128,) * 3, "tanh", (0, 4), (1.0, 1.0), 150),
+    (6, 2, (64,) * 3, "tanh", (1, 5, 3), (1.0, 0.5, 0.0), 700),
+    (8, 1, (200, 256), "tanh", (0, 7), None, 300),
+    (5, 3, (96,) * 3, "sin", (4,), (1.0,), 1001),
+    (7, 20, (48, 48), "tanh", (6, 2), (1.0, 1.0), 77),
     # widths 129..256: two 128-neuron blocks per layer on the wide path
     (3, 2, (200, 256, 130), "tanh", (0, 1, 2), (1.0, 1.0, 0.0), 1000),
     (2, 1, (256, 256), "tanh", (0, 1), (1.0, 1.0), 5000),

@@ -78,6 +78,29 @@ def test_packed_layout_of_wide_output_and_deep_narrow_networks():
     assert floats(2, 40, (256, 256)) == fp32_image(256, 2, 2, 40 * 256 + pad4(40))
     # the width-64 path appends its own images behind the (1 KB aligned) FP32 image: strictly more than the FP32 image
     assert floats(2, 1, (64,) * 4) > fp32_image(64, 2, 4, 64 + pad4(1))
+    # checkpoint buffers of the layer-major kernels (host arithmetic only): per array = tiles x S x 16 x 128 floats; hidden layers
+    # 1..L-1 + two adjoint arrays (+ one array of partial products for several output blocks, + layer 0's own checkpoints for
+    # 5..8 inputs), then 160 per-CTA dW partial sums.  A size > 0 also says: this shape runs on the tensor-core kernels.
+    def saved(d_in, d_out, widths, nd, lap, n):
+        d = _lib.FcnDesc()
+        d.d_in, d.d_out, d.n_hidden, d.activation = d_in, d_out, len(widths), _lib.TPX_ACT_TANH
+        for l, w in enumerate(widths):
+            d.widths[l] = w
+        j = _lib.JetDesc()
+        j.nd, j.lap = nd, lap
+        for k in range(nd):
+            j.dcol[k], j.lap_w[k] = k, 1.0
+        nb = ctypes.c_size_t(0)
+        _lib.check(lib.tpx_fcn_saved_bytes(ctypes.byref(d), ctypes.byref(j), ctypes.c_int64(n), ctypes.byref(nb)))
+        return nb.value
+
+    per = lambda n, S: (n + 15) // 16 * S * 16 * 128 * 4                               # noqa: E731
+    tail = 160 * 128 * 128 * 4
+    assert saved(2, 1, (64,) * 6, 2, 1, 1000) == (6 + 1) * per(1000, 4) + tail          # deep narrow net
+    assert saved(1, 64, (64,) * 4, 1, 1, 1000) == (4 + 1) * per(1000, 3) + tail         # DeepONet trunk, one block of outputs
+    assert saved(1, 300, (64,) * 4, 1, 1, 1000) == (4 + 1 + 1) * per(1000, 3) + tail    # three blocks: + partial products
+    assert saved(6, 2, (64,) * 3, 3, 1, 1000) == (3 + 1 + 1) * per(1000, 5) + tail      # 6 inputs: + layer 0's checkpoints
+    assert saved(6, 2, (200, 256), 2, 0, 1000) == ((2 + 1) * 2 + 1 + 2) * per(1000, 3) + tail   # ... with two 128-neuron blocks
     d = _lib.FcnDesc()
     d.d_in, d.d_out, d.n_hidden, d.activation = 2, _lib.TPX_MAX_DOUT + 1, 2, _lib.TPX_ACT_TANH
     d.widths[0] = d.widths[1] = 64

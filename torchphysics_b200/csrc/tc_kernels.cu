@@ -459,7 +459,7 @@ bool tc_net_fits(const tpx_fcn_desc* net) {
   if (net->n_hidden < 2) return false;                 // needs at least one hidden x hidden product
   for (int l = 0; l < net->n_hidden; ++l)
     if (net->widths[l] > HP) return false;
-  if (net->d_out > 8) return false;
+  if (net->d_out > 8 || net->d_in > 4) return false;   // (the reverse kernel takes 4 inputs; such nets run on the layer-major kernels)
   // all weight images stay resident in shared memory next to the exchange buffers: up to 4 hidden matrices
   const TcLayout lay{net->n_hidden, net->d_in, net->d_out};
   if ((size_t)fwd_smem(lay).total * sizeof(float) + 1024 > 227 * 1024) return false;

@@ -142,6 +142,7 @@ struct WArgs {
   float* out;            // FWD: ckpt_l; ADJ: Zbar_{l-1} (unused for l = 1)
   double* gacc;
   // hidden width 129..256: the matrices are processed as 128 x 128 blocks, activations are stored as two half-arrays
+  int in0;               // d_in > 4: layer 0 has its own kernels; matrix 1 reads its checkpoints from `in` / `ck` like any other
   int jb, kb;            // FWD: output-neuron block jb, input-neuron block kb.  REV: Zbar (output-neuron) block jb, input-neuron block kb
   int part_out, part_in; // the product is one K block of a sum: write it raw to `part` / add `part` to it before the epilogue
   float* part;           // half-array of partial products
@@ -321,15 +322,16 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
     const int i = kb * 32 + lane;
     Layer0 l0;
     float dz0[NDX];
-    if (MODE == FWD && l == 1) {
+    const bool first = (l == 1) && !a.in0;     // layer 0 recomputed from x on the fly (d_in <= 4)
+    if (MODE == FWD && first) {
       l0.load(lay, a.packed, a.kb * HW + i);
 #pragma unroll
       for (int k = 0; k < NDX; ++k) dz0[k] = l0.col(dcol[k]);
     }
     int it = 0;
     constexpr bool PREFETCH = S <= 4;          // S = 5: no registers for it (128 per thread)
-    float vn[8][S];                            // forward, l > 1: the next tile's rows, in flight during this tile
-    if (PREFETCH && MODE == FWD && l > 1) {
+    float vn[8][S];                            // forward, checkpoints from memory: the next tile's rows, in flight during this tile
+    if (PREFETCH && MODE == FWD && !first) {
       const float* src = a.in + ((size_t)blockIdx.x * N + half * 8) * HW + i;
 #pragma unroll
       for (int pp = 0; pp < 8; ++pp)
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
       if (MODE == FWD) {
         // rows n = s * P + p for this warp's 8 points
         float v[8][S];
-        if (l == 1) {
+        if (first) {
 #pragma unroll
           for (int pp = 0; pp < 8; ++pp) {
             const int64_t gp = tile * P + half * 8 + pp;
@@ -1132,7 +1134,7 @@ __global__ void __launch_bounds__(THREADS, 1) w_rev_kernel(WArgs a) {
       TPX_WSTAMP(2 + set, 5);
     }
     if (!a.part_out) {
-      atomicAdd(a.gacc + (FIRST ? lay.b0() : lay.b(l - 1)) + a.kb * HW + i, acc_db);
+      atomicAdd(a.gacc + ((FIRST || l == 1) ? lay.b0() : lay.b(l - 1)) + a.kb * HW + i, acc_db);
       if (FIRST) {
 #pragma unroll
         for (int c = 0; c < MAXD; ++c)
@@ -1442,6 +1444,84 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_seed_t_kernel(WArgs a, cons
     if (c0 + o < d_out) atomicAdd(a.gacc + a.lay.bl() + c0 + o, (double)sdb[o]);
 }
 
+// ---- d_in = 5..8 (TPX_MAX_DIN): the layer kernels keep layer 0 in registers for at most MAXD inputs, so a wider input layer gets
+// kernels of its own: its checkpoints (keep(z0), d_k z0 = W0[:, dcol_k], L z0 = 0) are written once per sweep and matrix 1 reads them
+// like any other layer's; the reverse sweep leaves Zbar_0 in memory and w_in_bwd_kernel turns it into dW0 (db0 comes from w_rev_kernel).
+// One CTA = the 128 neurons of block a.kb, grid-stride over the tiles.
+template <int ND, int LAP>
+__global__ void __launch_bounds__(HW) w_in_fwd_kernel(WArgs a) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  const Layout lay = a.lay;
+  const int d_in = lay.d_in, j = a.kb * HW + threadIdx.x;
+  float w[TPX_MAX_DIN];
+#pragma unroll
+  for (int c = 0; c < TPX_MAX_DIN; ++c) w[c] = (c < d_in) ? __ldg(a.packed + lay.w0() + (size_t)c * lay.HP + j) : 0.0f;
+  const float b = __ldg(a.packed + lay.b0() + j);
+  float dz[ND > 0 ? ND : 1];
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    float r = w[0];
+#pragma unroll
+    for (int c = 1; c < TPX_MAX_DIN; ++c) r = (a.jet.dcol[k] == c) ? w[c] : r;
+    dz[k] = r;
+  }
+  const int64_t ntiles = (a.n + P - 1) / P;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    float* dst = a.out + (size_t)tile * N * HW + threadIdx.x;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+      const int64_t gp = tile * P + p;
+      float z = b;
+      if (gp < a.n) {
+#pragma unroll
+        for (int c = 0; c < TPX_MAX_DIN; ++c)
+          if (c < d_in) z = fmaf(w[c], __ldg(a.x + gp * d_in + c), z);
+      }
+      __stcs(dst + (size_t)p * HW, keep_of(z));
+#pragma unroll
+      for (int k = 0; k < ND; ++k) __stcs(dst + (size_t)((1 + k) * P + p) * HW, dz[k]);
+      if (LAP) __stcs(dst + (size_t)((S - 1) * P + p) * HW, 0.0f);
+    }
+  }
+}
+
+template <int ND, int LAP>
+__global__ void __launch_bounds__(HW) w_in_bwd_kernel(WArgs a) {
+  constexpr int S = 1 + ND + LAP, N = S * P;
+  const Layout lay = a.lay;
+  const int d_in = lay.d_in, j = a.kb * HW + threadIdx.x;
+  double acc[TPX_MAX_DIN];
+#pragma unroll
+  for (int c = 0; c < TPX_MAX_DIN; ++c) acc[c] = 0.0;
+  const int64_t ntiles = (a.n + P - 1) / P;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const float* src = a.in + (size_t)tile * N * HW + threadIdx.x;      // Zbar_0 of this block
+    float part[TPX_MAX_DIN];
+#pragma unroll
+    for (int c = 0; c < TPX_MAX_DIN; ++c) part[c] = 0.0f;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+      const int64_t gp = tile * P + p;
+      if (gp >= a.n) break;
+      const float zb = __ldcs(src + (size_t)p * HW);
+#pragma unroll
+      for (int c = 0; c < TPX_MAX_DIN; ++c)
+        if (c < d_in) part[c] = fmaf(zb, __ldg(a.x + gp * d_in + c), part[c]);
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        const float zk = __ldcs(src + (size_t)((1 + k) * P + p) * HW);
+#pragma unroll
+        for (int c = 0; c < TPX_MAX_DIN; ++c) part[c] += (a.jet.dcol[k] == c) ? zk : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < TPX_MAX_DIN; ++c) acc[c] += (double)part[c];
+  }
+#pragma unroll
+  for (int c = 0; c < TPX_MAX_DIN; ++c)
+    if (c < d_in) atomicAdd(a.gacc + lay.w0() + (size_t)c * lay.HP + j, acc[c]);
+}
+
 template <int ND, int LAP>
 struct Launch {
   static constexpr int S = 1 + ND + LAP, N = S * P;
@@ -1477,18 +1557,31 @@ struct Launch {
   // Storage (floats): per = one half-array = ntiles x N x 128; a layer is nblk = HP / 128 consecutive half-arrays.
   //   [checkpoints of hidden layers 1..L-1][Zbar A][Zbar B][partial products (nblk = 2 only)]
   static size_t per_floats(int64_t n) { return (size_t)((n + P - 1) / P) * N * HW; }
+  // the partial-product array exists for 256-wide layers and for more than one block of outputs
+  static bool has_part(const Layout& lay) { return lay.HP > HW || (lay.wide_out() && lay.dop() > HW); }
 
   static int forward(WArgs a, float* saved, float* u, float* du, float* lapo, int sm_count, cudaStream_t stream) {
     const int L = a.lay.L, nblk = a.lay.HP / HW;
     const size_t per = per_floats(a.n), layer = (size_t)nblk * per;
     float* part = saved + (size_t)(L + 1) * layer;
+    float* ck0 = part + (has_part(a.lay) ? per : 0);             // checkpoints of layer 0 (d_in > MAXD only)
+    a.in0 = a.lay.d_in > MAXD;
     int rc = set_smem(w_layer_kernel<ND, LAP, FWD>, layer_smem(), "w_layer_kernel<FWD>");
     if (rc) return rc;
+    if (a.in0) {
+      const int64_t ntiles = (a.n + P - 1) / P;
+      const int64_t blocks = ntiles < (int64_t)sm_count * 16 ? ntiles : (int64_t)sm_count * 16;
+      for (int hb = 0; hb < nblk; ++hb) {
+        a.kb = hb; a.out = ck0 + (size_t)hb * per;
+        w_in_fwd_kernel<ND, LAP><<<(unsigned)blocks, HW, 0, stream>>>(a);
+        if ((rc = check("w_in_fwd_kernel"))) return rc;
+      }
+    }
     for (int l = 1; l < L; ++l)
       for (int jb = 0; jb < nblk; ++jb)
         for (int kb = 0; kb < nblk; ++kb) {      // z_l[jb] = sum_kb W_l[jb][kb] a_{l-1}[kb]: the K blocks meet in `part`
           a.l = l; a.jb = jb; a.kb = kb;
-          a.in = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer + (size_t)kb * per;
+          a.in = (l == 1) ? (a.in0 ? ck0 + (size_t)kb * per : nullptr) : saved + (size_t)(l - 2) * layer + (size_t)kb * per;
           a.out = saved + (size_t)(l - 1) * layer + (size_t)jb * per;
           a.part = part; a.part_out = kb < nblk - 1; a.part_in = kb > 0;
           w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
@@ -1533,7 +1626,9 @@ struct Launch {
     const size_t per = per_floats(a.n), layer = (size_t)nblk * per;
     float* zb[2] = {saved + (size_t)(L - 1) * layer, saved + (size_t)L * layer};
     float* part = saved + (size_t)(L + 1) * layer;
-    a.dwpart = part + ((nblk > 1 || (a.lay.wide_out() && a.lay.dop() > HW)) ? per : 0);
+    float* ck0 = part + (has_part(a.lay) ? per : 0);             // checkpoints of layer 0 (d_in > MAXD only)
+    a.in0 = a.lay.d_in > MAXD;
+    a.dwpart = ck0 + (a.in0 ? layer : 0);
     static const int split = env_flag("TPX_TCW_SPLIT");      // development: separate dW / adjoint launches (width <= 128)
     int rc;
     const bool wide_out = a.lay.wide_out();
@@ -1552,7 +1647,7 @@ struct Launch {
       else w_out_bwd_kernel<ND, LAP, 8><<<(unsigned)blocks, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
       if ((rc = check("w_out_bwd_kernel"))) return rc;
     }
-    if (split && nblk == 1 && !wide_out) {
+    if (split && nblk == 1 && !wide_out && !a.in0) {
       if ((rc = set_smem(w_layer_kernel<ND, LAP, ADJ>, layer_smem(), "w_layer_kernel<ADJ>"))) return rc;
       if ((rc = set_smem(w_dw_kernel<ND, LAP>, dw_smem(), "w_dw_kernel"))) return rc;
     } else {
@@ -1592,7 +1687,7 @@ struct Launch {
     }
     for (int l = L - 1; l >= 1; --l) {
       a.l = l;
-      if (split && nblk == 1 && !wide_out) {
+      if (split && nblk == 1 && !wide_out && !a.in0) {
         a.jb = a.kb = 0; a.part_out = a.part_in = 0;
         a.in = zb[cur];
         a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer;
@@ -1607,19 +1702,28 @@ struct Launch {
           for (int jb = 0; jb < nblk; ++jb) {
             a.jb = jb; a.kb = ib;
             a.in = zb[cur] + (size_t)jb * per;
-            a.ck = (l == 1) ? nullptr : saved + (size_t)(l - 2) * layer + (size_t)ib * per;
+            a.ck = (l == 1) ? (a.in0 ? ck0 + (size_t)ib * per : nullptr) : saved + (size_t)(l - 2) * layer + (size_t)ib * per;
             a.out = zb[cur ^ 1] + (size_t)ib * per;
             a.part = part; a.part_out = jb < nblk - 1; a.part_in = jb > 0;
             const int64_t nsub = (a.n + P - 1) / P * 2;
             unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
             if (g > MAX_REV_CTAS) g = MAX_REV_CTAS;
-            if (l == 1) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
+            if (l == 1 && !a.in0) w_rev_kernel<ND, LAP, true><<<g, THREADS, rev_smem(), stream>>>(a);
             else w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
             if ((rc = check("w_rev_kernel"))) return rc;
             if ((rc = reduce_dw(a, g, stream))) return rc;
           }
       }
       cur ^= 1;
+    }
+    if (a.in0) {                                 // Zbar_0 (the last sweep's output) -> dW0
+      const int64_t ntiles = (a.n + P - 1) / P;
+      const int64_t blocks = ntiles < (int64_t)sm_count * 8 ? ntiles : (int64_t)sm_count * 8;
+      for (int hb = 0; hb < nblk; ++hb) {
+        a.kb = hb; a.in = zb[cur] + (size_t)hb * per;
+        w_in_bwd_kernel<ND, LAP><<<(unsigned)blocks, HW, 0, stream>>>(a);
+        if ((rc = check("w_in_bwd_kernel"))) return rc;
+      }
     }
     return 0;
   }
@@ -1635,10 +1739,10 @@ using namespace TCW_NS;
 #else
 bool tcw_takes_narrow(const tpx_fcn_desc* net) {
   if (net->activation != TPX_ACT_TANH && net->activation != TPX_ACT_SIN) return false;
-  if (net->n_hidden < 2 || net->d_in > MAXD || net->d_out > MAXO_WIDE) return false;
+  if (net->n_hidden < 2 || net->d_in > TPX_MAX_DIN || net->d_out > MAXO_WIDE) return false;
   for (int l = 0; l < net->n_hidden; ++l)
     if (net->widths[l] > 64) return false;
-  return !tc_net_fits(net);
+  return !tc_net_fits(net);                       // more than 5 hidden layers, more than 8 outputs, or more than 4 inputs
 }
 
 bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
@@ -1650,7 +1754,7 @@ bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
   if (wmax > 2 * HW) return false;                   // 129..256: two 128-neuron blocks per layer
   if (wmax <= 64 && !tcw_takes_narrow(net)) return false;
-  if (net->d_in > MAXD || net->d_out > (wmax <= HW ? MAXO_WIDE : MAXO)) return false;   // 9..128 outputs: Layout::wide_out
+  if (net->d_in > TPX_MAX_DIN || net->d_out > (wmax <= HW ? MAXO_WIDE : MAXO)) return false;   // 9 or more outputs: Layout::wide_out; 5..8 inputs: w_in_*_kernel
   if (lap && nd == 0) return false;
   if (nd < 0 || nd > 3) return false;
   return true;
@@ -1664,7 +1768,8 @@ size_t tcw_saved_bytes(const tpx_fcn_desc* net, int nd, int lap, int64_t n) {
   const size_t nblk = wmax > HW ? 2 : 1;
   const size_t per = (size_t)((n + P - 1) / P) * (size_t)((1 + nd + lap) * P) * HW * sizeof(float);
   const bool out_chain = nblk == 1 && net->d_out > HW;       // more than one block of outputs: their adjoint products meet in `part`
-  return ((size_t)(net->n_hidden + 1) * nblk + ((nblk > 1 || out_chain) ? 1 : 0)) * per + (size_t)MAX_REV_CTAS * HW * HW * sizeof(float);
+  const size_t in0 = net->d_in > MAXD ? nblk : 0;            // checkpoints of layer 0 when it has kernels of its own
+  return ((size_t)(net->n_hidden + 1) * nblk + ((nblk > 1 || out_chain) ? 1 : 0) + in0) * per + (size_t)MAX_REV_CTAS * HW * HW * sizeof(float);
 }
 
 #endif  // !TCW_ACT_SIN
