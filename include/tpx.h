@@ -30,7 +30,7 @@ extern "C" {
 #define TPX_MAX_DIN 8       /* columns of the model input                          */
 #define TPX_MAX_ND 3        /* derivative directions propagated through the net    */
 #define TPX_MAX_WIDTH 256   /* widest hidden layer                                 */
-#define TPX_MAX_DOUT 4096   /* outputs; more than 256 only on the wide tensor-core path (hidden width <= 128) */
+#define TPX_MAX_DOUT 4096   /* outputs; more than 256 only on the layer-major tensor-core kernels (two or more hidden layers) */
 
 #define TPX_E_ARG (-1)       /* invalid argument                      */
 #define TPX_E_UNSUPPORTED (-2) /* valid network, but no kernel for it  */
@@ -89,7 +89,7 @@ int tpx_fcn_jet_forward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const 
                         const float* x, int64_t n, float* u, float* du, float* lap, void* stream);
 
 /* The same forward jet with a caller workspace of at least tpx_fcn_backward_workspace_bytes() bytes: networks of
- * hidden width 65..256 (tanh or sin, d_out <= 8; up to width 128 any d_out, and narrower nets that are deeper than
+ * hidden width 65..256 (tanh or sin, and narrower nets that are deeper than
  * 5 hidden layers or have more than 8 outputs or more than 4 inputs) then run on the layer-major tensor-core kernels
  * (csrc/tcw_kernels.cu), whose per-layer activation arrays live in the workspace (chunks of points); every other
  * network ignores the workspace.  tpx_fcn_jet_backward uses its workspace for those networks in the same way. */
@@ -116,7 +116,7 @@ int tpx_fcn_jet_backward(const tpx_fcn_desc* net, const tpx_jet_desc* jet, const
  * per-layer jets (8 KB per point for a 4x64 net; HBM is 180 GB) and the reverse kernel reads them instead of
  * re-running the forward sweep.  *bytes = 0 when this network / jet has no saving kernel.  The size includes a
  * fixed tail (<= 13 MB) of per-CTA fp32 partial sums the reverse kernels flush their TMEM dW accumulators into.
- * Hidden widths 65..256 (tanh or sin, d_out <= 8; up to width 128 any d_out) run on the layer-major tensor-core kernels
+ * Hidden widths 65..256 (tanh or sin) run on the layer-major tensor-core kernels
  * (csrc/tcw_kernels.cu); through this pair of calls their `saved` buffer holds the checkpoints of the
  * hidden layers 1..L-1 ([tile of 16 points][stream * 16 + point][128 neurons] fp32 per layer and 128-neuron
  * block: one block up to width 128, two above) followed by two scratch arrays of the same size for the reverse

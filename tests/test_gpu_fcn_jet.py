@@ -172,6 +172,10 @@ CASES = [
     (1, 256, (64,) * 4, "tanh", (0,), (1.0,), 900),
     (2, 300, (128, 96), "tanh", (0, 1), (1.0, 1.0), 401),
     (3, 200, (48,) * 3, "sin", (0, 2), None, 333),
+    # ... on 256-wide hidden layers (two input blocks per output block, the K blocks meet in the partial-product array)
+    (2, 40, (256, 200), "tanh", (0, 1), (1.0, 1.0), 500),
+    (2, 300, (160, 256, 256), "tanh", (1,), None, 257),
+    (6, 130, (256, 256), "sin", (0, 5), (1.0, 1.0), 100),
 ]
 
 
@@ -447,7 +451,8 @@ def test_round2_split_fp16_kernels_in_a_subprocess():
 
 @pytest.mark.parametrize("d_in,d_out,hidden,dcols,lap_w,N", [(1, 256, (64,) * 4, (0,), (1.0,), 16384 + 5),
                                                              (2, 40, (128, 96), (0, 1), None, 333),
-                                                             (2, 300, (32, 32, 32), (1,), (0.5,), 70001)])
+                                                             (2, 300, (32, 32, 32), (1,), (0.5,), 70001),
+                                                             (2, 150, (256, 256), (0, 1), (1.0, 1.0), 4097)])
 def test_output_major_streams_equal_the_transposed_standard_ones(d_in, d_out, hidden, dcols, lap_w, N):
     """tpx_jet_desc.out_major (the layout of a DeepONet's (function, point) outputs): the same kernels write u (d_out, n),
     du (nd, d_out, n), lap (d_out, n) and read the adjoints in that layout -- bit-identical streams, dtheta up to the order of

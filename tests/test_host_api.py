@@ -74,8 +74,9 @@ def test_packed_layout_of_wide_output_and_deep_narrow_networks():
     assert floats(1, 64, (64,) * 4) == fp32_image(128, 1, 4, 2 * 128 * 128 + 128)
     # 300 (function, output) columns: three blocks of 128 outputs
     assert floats(1, 300, (64,) * 4) == fp32_image(128, 1, 4, 2 * 128 * 384 + 384)
-    # width 256 keeps the plain output layer (and is limited to 256 outputs by the FP32 kernels at run time)
-    assert floats(2, 40, (256, 256)) == fp32_image(256, 2, 2, 40 * 256 + pad4(40))
+    # width 256: the same block layout with 256-wide rows (Wt [256][128] | W [128][256] | b [128] for 40 outputs)
+    assert floats(2, 40, (256, 256)) == fp32_image(256, 2, 2, 2 * 256 * 128 + 128)
+    assert floats(2, 8, (256, 256)) == fp32_image(256, 2, 2, 8 * 256 + pad4(8))          # up to 8 outputs: the plain output layer
     # the width-64 path appends its own images behind the (1 KB aligned) FP32 image: strictly more than the FP32 image
     assert floats(2, 1, (64,) * 4) > fp32_image(64, 2, 4, 64 + pad4(1))
     # checkpoint buffers of the layer-major kernels (host arithmetic only): per array = tiles x S x 16 x 128 floats; hidden layers
@@ -101,6 +102,7 @@ def test_packed_layout_of_wide_output_and_deep_narrow_networks():
     assert saved(1, 300, (64,) * 4, 1, 1, 1000) == (4 + 1 + 1) * per(1000, 3) + tail    # three blocks: + partial products
     assert saved(6, 2, (64,) * 3, 3, 1, 1000) == (3 + 1 + 1) * per(1000, 5) + tail      # 6 inputs: + layer 0's checkpoints
     assert saved(6, 2, (200, 256), 2, 0, 1000) == ((2 + 1) * 2 + 1 + 2) * per(1000, 3) + tail   # ... with two 128-neuron blocks
+    assert saved(2, 300, (256, 256), 2, 1, 1000) == ((2 + 1) * 2 + 1) * per(1000, 4) + tail     # 256-wide with three output blocks
     d = _lib.FcnDesc()
     d.d_in, d.d_out, d.n_hidden, d.activation = 2, _lib.TPX_MAX_DOUT + 1, 2, _lib.TPX_ACT_TANH
     d.widths[0] = d.widths[1] = 64

@@ -385,6 +385,10 @@ int tpx_fcn_backward_workspace_bytes(const tpx_fcn_desc* net, const tpx_jet_desc
     case 256: rc = bwd_workspace<256>(jet->nd, a.lap, a.lay.L, a.lay.d_out, a.sm_count, bytes); break;
     default: rc = TPX_E_UNSUPPORTED;
   }
+  if (rc && tcw_supported(net, jet->nd, a.lap)) {     // (e.g. 256-wide with many outputs: too much shared memory for the FP32 reverse kernel)
+    *bytes = 0;
+    rc = 0;
+  }
   if (rc) return fail(rc, "no reverse kernel for HP=%d nd=%d lap=%d d_out=%d", a.lay.HP, jet->nd, jet->lap, a.lay.d_out);
   if (tce_bwd_supported(net, jet->nd, a.lap)) {
     const size_t tcb = tce_saved_bytes(net, jet->nd, a.lap, (int64_t)a.sm_count * 2 * 128);   // two tiles per SM: the chunk stays in L2

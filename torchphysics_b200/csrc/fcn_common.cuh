@@ -30,7 +30,7 @@ struct Layout {
   // 9 or more outputs on a 128-wide image (DeepONet trunks; the DeepONet inner product folded into the output layer): the
   // output layer is stored like a hidden matrix -- Wt [HP][DOP] | W [DOP][HP] | b [DOP], DOP = d_out padded to 128-neuron
   // blocks, padding zero -- so that the layer-major tensor-core kernels treat it as matrix L, block by block
-  __host__ __device__ bool wide_out() const { return HP == 128 && d_out > 8; }
+  __host__ __device__ bool wide_out() const { return HP >= 128 && d_out > 8; }
   __host__ __device__ size_t dop() const { return (size_t)((d_out + 127) / 128) * 128; }
   __host__ __device__ size_t wt(int l) const { return hidden_base(l); }
   __host__ __device__ size_t wts(int l) const { return (l == L && wide_out()) ? dop() : (size_t)HP; }   // row stride of wt(l)

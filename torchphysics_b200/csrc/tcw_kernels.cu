@@ -1368,7 +1368,7 @@ __global__ void __launch_bounds__(HW) w_out_seed_kernel(WArgs a, const float* __
     for (int k = 0; k < ND; ++k) __stcs(dst + (size_t)(1 + k) * P * HW, (on && gdu) ? __ldg(gdu + (pt * d_out + c) * ND + k) : 0.0f);
     if (LAP) __stcs(dst + (size_t)(S - 1) * P * HW, (on && glap) ? __ldg(glap + pt * d_out + c) : 0.0f);
   }
-  if (c < d_out) atomicAdd(a.gacc + a.lay.bl() + c, acc_bl);
+  if (c < d_out && a.kb == 0) atomicAdd(a.gacc + a.lay.bl() + c, acc_bl);
 }
 
 // the same two kernels for output-major streams (JetArgs::out_major: u (d_out, n), du (nd, d_out, n), lap (d_out, n), row stride
@@ -1441,7 +1441,7 @@ __global__ void __launch_bounds__(OUT_THREADS) w_out_seed_t_kernel(WArgs a, cons
   for (int q = 0; q < HW / 32; ++q) atomicAdd(&sdb[q * 32 + lane], acc[q]);
   __syncthreads();
   for (int o = threadIdx.x; o < HW; o += OUT_THREADS)
-    if (c0 + o < d_out) atomicAdd(a.gacc + a.lay.bl() + c0 + o, (double)sdb[o]);
+    if (c0 + o < d_out && a.kb == 0) atomicAdd(a.gacc + a.lay.bl() + c0 + o, (double)sdb[o]);
 }
 
 // ---- d_in = 5..8 (TPX_MAX_DIN): the layer kernels keep layer 0 in registers for at most MAXD inputs, so a wider input layer gets
@@ -1587,15 +1587,19 @@ struct Launch {
           w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
           if ((rc = check("w_layer_kernel<FWD>"))) return rc;
         }
-    if (u && a.lay.wide_out()) {                 // nblk == 1: raw products of matrix L, one block of 128 outputs at a time, into
-      float* raw = saved + (size_t)(L - 1) * layer;     // the (idle) Zbar array, then u / du / lap
+    if (u && a.lay.wide_out()) {
+      // raw products of matrix L, one block of 128 outputs at a time, then u / du / lap.  One 128-neuron block per layer: into
+      // the (idle) Zbar array; two: the K blocks meet in the partial-product array, which the second launch updates in place
+      float* raw = nblk == 1 ? saved + (size_t)(L - 1) * layer : part;
       const int nob = (int)(a.lay.dop() / HW);
       for (int ob = 0; ob < nob; ++ob) {
-        a.l = L; a.jb = ob; a.kb = 0;
-        a.in = saved + (size_t)(L - 2) * layer;
-        a.out = nullptr; a.part = raw; a.part_out = 1; a.part_in = 0;
-        w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
-        if ((rc = check("w_layer_kernel<FWD> (output layer)"))) return rc;
+        for (int kb = 0; kb < nblk; ++kb) {
+          a.l = L; a.jb = ob; a.kb = kb;
+          a.in = saved + (size_t)(L - 2) * layer + (size_t)kb * per;
+          a.out = nullptr; a.part = raw; a.part_out = 1; a.part_in = kb > 0;
+          w_layer_kernel<ND, LAP, FWD><<<grid(a, sm_count), THREADS, layer_smem(), stream>>>(a);
+          if ((rc = check("w_layer_kernel<FWD> (output layer)"))) return rc;
+        }
         const int cols = a.lay.d_out - ob * HW < HW ? a.lay.d_out - ob * HW : HW;
         int64_t blocks = (a.n * cols + OUT_THREADS - 1) / OUT_THREADS;
         if (blocks > (int64_t)sm_count * 8) blocks = (int64_t)sm_count * 8;
@@ -1664,25 +1668,26 @@ struct Launch {
       const int64_t nsub = (a.n + P - 1) / P * 2;
       unsigned g = (unsigned)(sm_count < nsub ? sm_count : nsub);
       if (g > MAX_REV_CTAS) g = MAX_REV_CTAS;
-      for (int ob = 0; ob < nob; ++ob) {
-        a.jb = ob; a.kb = 0;
-        a.out = zb[0];
-        if (a.jet.out_major) {
-          const int64_t ntiles = (a.n + P - 1) / P;
-          const int64_t tb = ntiles < (int64_t)sm_count * 8 ? ntiles : (int64_t)sm_count * 8;
-          w_out_seed_t_kernel<ND, LAP><<<(unsigned)tb, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
-        } else {
-          w_out_seed_kernel<ND, LAP><<<(unsigned)sblocks, HW, 0, stream>>>(a, gu, gdu, glap);
+      for (int ib = 0; ib < nblk; ++ib)            // input-neuron block of the last hidden layer
+        for (int ob = 0; ob < nob; ++ob) {
+          a.jb = ob; a.kb = ib;                      // (the seed kernel adds dbL for kb == 0 only)
+          a.out = zb[0];
+          if (a.jet.out_major) {
+            const int64_t ntiles = (a.n + P - 1) / P;
+            const int64_t tb = ntiles < (int64_t)sm_count * 8 ? ntiles : (int64_t)sm_count * 8;
+            w_out_seed_t_kernel<ND, LAP><<<(unsigned)tb, OUT_THREADS, 0, stream>>>(a, gu, gdu, glap);
+          } else {
+            w_out_seed_kernel<ND, LAP><<<(unsigned)sblocks, HW, 0, stream>>>(a, gu, gdu, glap);
+          }
+          if ((rc = check("w_out_seed_kernel"))) return rc;
+          a.in = zb[0];
+          a.ck = saved + (size_t)(L - 2) * layer + (size_t)ib * per;
+          a.out = zb[1] + (size_t)ib * per;
+          a.part = part; a.part_out = ob < nob - 1; a.part_in = ob > 0;
+          w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
+          if ((rc = check("w_rev_kernel (output layer)"))) return rc;
+          if ((rc = reduce_dw(a, g, stream))) return rc;
         }
-        if ((rc = check("w_out_seed_kernel"))) return rc;
-        a.in = zb[0];
-        a.ck = saved + (size_t)(L - 2) * layer;
-        a.out = zb[1];
-        a.part = part; a.part_out = ob < nob - 1; a.part_in = ob > 0;
-        w_rev_kernel<ND, LAP, false><<<g, THREADS, rev_smem(), stream>>>(a);
-        if ((rc = check("w_rev_kernel (output layer)"))) return rc;
-        if ((rc = reduce_dw(a, g, stream))) return rc;
-      }
       cur = 1;
     }
     for (int l = L - 1; l >= 1; --l) {
@@ -1754,7 +1759,7 @@ bool tcw_supported(const tpx_fcn_desc* net, int nd, int lap) {
   for (int l = 0; l < net->n_hidden; ++l) wmax = net->widths[l] > wmax ? net->widths[l] : wmax;
   if (wmax > 2 * HW) return false;                   // 129..256: two 128-neuron blocks per layer
   if (wmax <= 64 && !tcw_takes_narrow(net)) return false;
-  if (net->d_in > TPX_MAX_DIN || net->d_out > (wmax <= HW ? MAXO_WIDE : MAXO)) return false;   // 9 or more outputs: Layout::wide_out; 5..8 inputs: w_in_*_kernel
+  if (net->d_in > TPX_MAX_DIN || net->d_out > MAXO_WIDE) return false;   // 9 or more outputs: Layout::wide_out; 5..8 inputs: w_in_*_kernel
   if (lap && nd == 0) return false;
   if (nd < 0 || nd > 3) return false;
   return true;
