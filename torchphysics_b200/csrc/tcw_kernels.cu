@@ -431,10 +431,15 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
         const float* pin = a.part + (size_t)tile * N * HW + j;
         // the other K block of a 256-wide layer: its partial products are in flight while the warp waits for this tile's
         // product, stream s + 1 while stream s is finished (loaded after the TMEM read they were an exposed HBM latency per stream)
-        float pv[16];
+        // S <= 3: all S x 16 values of the thread are requested before the wait (only four epilogue warps read this array:
+        // with one stream in flight per thread, Little's law holds the whole launch to ~0.7 TB/s); S > 3: one stream ahead
+        constexpr bool PART_ALL = S <= 3;
+        float pv[PART_ALL ? S : 1][16];
         if (part_in) {
 #pragma unroll
-          for (int p = 0; p < P; ++p) pv[p] = __ldcs(pin + (size_t)p * HW);
+          for (int s = 0; s < (PART_ALL ? S : 1); ++s)
+#pragma unroll
+            for (int p = 0; p < P; ++p) pv[s][p] = __ldcs(pin + (size_t)(s * P + p) * HW);
         }
         mbar_wait_w(&bar_dfull[st], (it >> 1) & 1);
         fence_after();
@@ -449,10 +454,10 @@ __global__ void __launch_bounds__(THREADS, 1) w_layer_kernel(WArgs a) {
           }
           if (part_in) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) d[p] += pv[p];
-            if (s + 1 < S) {
+            for (int p = 0; p < P; ++p) d[p] += pv[PART_ALL ? s : 0][p];
+            if (!PART_ALL && s + 1 < S) {
 #pragma unroll
-              for (int p = 0; p < P; ++p) pv[p] = __ldcs(pin + (size_t)((s + 1) * P + p) * HW);
+              for (int p = 0; p < P; ++p) pv[0][p] = __ldcs(pin + (size_t)((s + 1) * P + p) * HW);
             }
           }
           if (s == 0 && !part_out) {
